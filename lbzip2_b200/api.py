@@ -1,0 +1,233 @@
+"""ctypes mirror of include/lbzip2_b200.h (host-side convenience only)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class LbzError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libbz2b200.so")
+
+
+class BlockRec(C.Structure):
+    _fields_ = [("raw_offset", C.c_uint64)] + [
+        (n, C.c_uint32) for n in ("raw_len", "nblock", "crc", "bwt_idx", "tie_count", "nmtf",
+                                  "num_trees", "num_selectors", "out_len", "reserved")]
+
+
+class BlockMeta(C.Structure):
+    """Mirror of struct LbzBlockMeta (csrc/lbz_common.cuh)."""
+    _fields_ = [(n, C.c_uint32) for n in (
+        "n", "raw_len", "crc", "bwt_idx", "tie_count", "nmtf", "alpha_size", "num_trees",
+        "num_selectors", "tree_pad", "out_len", "unsorted", "depth", "tree_cost")] + [
+        ("used", C.c_uint32 * 8), ("pad_", C.c_uint32 * 2)]
+
+
+class Coding(C.Structure):
+    """Mirror of struct LbzCoding (csrc/lbz_common.cuh)."""
+    _fields_ = [("length", (C.c_uint8 * 260) * 6), ("code", (C.c_uint32 * 260) * 6),
+                ("selector", C.c_uint8 * 18008), ("selector_mtf", C.c_uint8 * 18008)]
+
+
+ST_RLE1, ST_BWT, ST_MTF, ST_HUFFMAN, ST_PACK = range(5)
+AR_TEXT, AR_BWT, AR_MTFV, AR_FREQ, AR_CODING, AR_OUT, AR_META, AR_SA = range(8)
+
+EXPORTS = [
+    # reference-shaped API (src/encode.h:29-36)
+    "encoder_alloc_size", "encoder_init", "collect", "encode", "transmit", "divbwt",
+    # batch API
+    "lbz_engine_create", "lbz_engine_destroy", "lbz_bound", "lbz_compress_chunks",
+    "lbz_compress_chunks_device", "lbz_compress_stream", "lbz_host_alloc", "lbz_host_free",
+    "lbz_engine_launches", "lbz_engine_last_rounds", "lbz_engine_device_bytes", "lbz_version",
+    # stage hooks
+    "lbz_dbg_load", "lbz_dbg_run", "lbz_dbg_read", "lbz_dbg_write", "lbz_dbg_num_slots",
+    "lbz_dbg_set_chunks",
+]
+
+
+def load_library():
+    """dlopen the product library.  No fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise LbzError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)" % path)
+    L = C.CDLL(path, mode=C.RTLD_LOCAL)
+    vp, u8p, szp = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_size_t)
+    L.lbz_engine_create.restype = vp
+    L.lbz_engine_create.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.lbz_engine_destroy.restype = None
+    L.lbz_engine_destroy.argtypes = [vp]
+    L.lbz_bound.restype = C.c_size_t
+    L.lbz_bound.argtypes = [C.c_size_t]
+    L.lbz_compress_chunks.restype = C.c_int
+    L.lbz_compress_chunks.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp, C.POINTER(BlockRec), C.c_size_t, szp]
+    L.lbz_compress_chunks_device.restype = C.c_int
+    L.lbz_compress_chunks_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp, C.POINTER(BlockRec), C.c_size_t, szp]
+    L.lbz_compress_stream.restype = C.c_int
+    L.lbz_compress_stream.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp]
+    L.lbz_host_alloc.restype = vp
+    L.lbz_host_alloc.argtypes = [C.c_size_t]
+    L.lbz_host_free.restype = None
+    L.lbz_host_free.argtypes = [vp]
+    L.lbz_engine_launches.restype = C.c_uint64
+    L.lbz_engine_launches.argtypes = [vp]
+    L.lbz_engine_last_rounds.restype = C.c_uint32
+    L.lbz_engine_last_rounds.argtypes = [vp]
+    L.lbz_engine_device_bytes.restype = C.c_size_t
+    L.lbz_engine_device_bytes.argtypes = [vp]
+    L.lbz_version.restype = C.c_char_p
+    L.lbz_dbg_load.restype = C.c_int
+    L.lbz_dbg_load.argtypes = [vp, vp, C.c_size_t]
+    L.lbz_dbg_run.restype = C.c_int
+    L.lbz_dbg_run.argtypes = [vp, C.c_int]
+    L.lbz_dbg_read.restype = C.c_int
+    L.lbz_dbg_read.argtypes = [vp, C.c_int, C.c_uint32, vp, C.c_size_t]
+    L.lbz_dbg_write.restype = C.c_int
+    L.lbz_dbg_write.argtypes = [vp, C.c_int, C.c_uint32, vp, C.c_size_t]
+    L.lbz_dbg_num_slots.restype = C.c_uint32
+    L.lbz_dbg_num_slots.argtypes = [vp]
+    L.lbz_dbg_set_chunks.restype = C.c_int
+    L.lbz_dbg_set_chunks.argtypes = [vp, C.c_uint32]
+    # reference-shaped API
+    L.encoder_alloc_size.restype = C.c_size_t
+    L.encoder_alloc_size.argtypes = [C.c_ulong]
+    L.encoder_init.restype = None
+    L.encoder_init.argtypes = [vp, C.c_ulong, C.c_uint]
+    L.collect.restype = C.c_int
+    L.collect.argtypes = [vp, vp, szp]
+    L.encode.restype = C.c_size_t
+    L.encode.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.transmit.restype = vp
+    L.transmit.argtypes = [vp, vp]
+    L.divbwt.restype = C.c_int32
+    L.divbwt.argtypes = [vp, vp, vp, C.c_int32]
+    _LIB = L
+    return L
+
+
+def _as_u8(data):
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data, dtype=np.uint8)
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+class Engine:
+    """One GPU context for one bzip2 level (mirror of lbz_engine)."""
+
+    def __init__(self, device=0, level=9, max_chunks=64):
+        self.L = load_library()
+        self.level = level
+        self.mbs = level * 100000
+        self.max_chunks = max_chunks
+        self.h = self.L.lbz_engine_create(device, level, max_chunks)
+        if not self.h:
+            raise LbzError("lbz_engine_create failed (no usable GPU? this package has no CPU path)")
+
+    def close(self):
+        if self.h:
+            self.L.lbz_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- batch API ----------------------------------------------------------
+    def compress_stream(self, data):
+        a = _as_u8(data)
+        cap = self.L.lbz_bound(a.size) + 64
+        out = np.empty(cap, dtype=np.uint8)
+        ln = C.c_size_t(0)
+        src = a if a.size else np.zeros(1, np.uint8)
+        rc = self.L.lbz_compress_stream(self.h, src.ctypes.data, a.size, out.ctypes.data, cap, C.byref(ln))
+        if rc:
+            raise LbzError("lbz_compress_stream failed (%d)" % rc)
+        return out[: ln.value].tobytes()
+
+    def compress_chunks(self, data):
+        a = _as_u8(data)
+        cap = self.L.lbz_bound(a.size) + 64
+        out = np.empty(cap, dtype=np.uint8)
+        maxrec = 2 * (a.size // self.mbs + 2)
+        recs = (BlockRec * maxrec)()
+        ln, nr = C.c_size_t(0), C.c_size_t(0)
+        src = a if a.size else np.zeros(1, np.uint8)
+        rc = self.L.lbz_compress_chunks(self.h, src.ctypes.data, a.size, out.ctypes.data, cap, C.byref(ln),
+                                        recs, maxrec, C.byref(nr))
+        if rc:
+            raise LbzError("lbz_compress_chunks failed (%d)" % rc)
+        return out[: ln.value].tobytes(), [recs[i] for i in range(nr.value)]
+
+    def compress_chunks_ptr(self, in_ptr, n, out_ptr, out_cap, device=False, max_recs=0):
+        """Raw-pointer form (host or device memory); returns (out_len, recs)."""
+        maxrec = max_recs or 2 * (n // self.mbs + 2)
+        recs = (BlockRec * maxrec)()
+        ln, nr = C.c_size_t(0), C.c_size_t(0)
+        fn = self.L.lbz_compress_chunks_device if device else self.L.lbz_compress_chunks
+        rc = fn(self.h, in_ptr, n, out_ptr, out_cap, C.byref(ln), recs, maxrec, C.byref(nr))
+        if rc:
+            raise LbzError("compress failed (%d)" % rc)
+        return ln.value, [recs[i] for i in range(nr.value)]
+
+    @property
+    def launches(self):
+        return self.L.lbz_engine_launches(self.h)
+
+    @property
+    def last_rounds(self):
+        return self.L.lbz_engine_last_rounds(self.h)
+
+    @property
+    def device_bytes(self):
+        return self.L.lbz_engine_device_bytes(self.h)
+
+    # ---- stage hooks (tests) ------------------------------------------------
+    def dbg_load(self, data):
+        a = _as_u8(data)
+        src = a if a.size else np.zeros(1, np.uint8)
+        if self.L.lbz_dbg_load(self.h, src.ctypes.data, a.size):
+            raise LbzError("dbg_load failed")
+
+    def dbg_set_chunks(self, k):
+        if self.L.lbz_dbg_set_chunks(self.h, k):
+            raise LbzError("dbg_set_chunks failed")
+
+    def dbg_run(self, stage):
+        if self.L.lbz_dbg_run(self.h, stage):
+            raise LbzError("stage %d failed" % stage)
+
+    def dbg_read(self, array, slot, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        if count and self.L.lbz_dbg_read(self.h, array, slot, out.ctypes.data, out.nbytes):
+            raise LbzError("dbg_read failed")
+        return out
+
+    def dbg_read_struct(self, array, slot, typ):
+        v = typ()
+        if self.L.lbz_dbg_read(self.h, array, slot, C.addressof(v), C.sizeof(v)):
+            raise LbzError("dbg_read failed")
+        return v
+
+    def dbg_write(self, array, slot, arr):
+        a = np.ascontiguousarray(arr)
+        if a.nbytes and self.L.lbz_dbg_write(self.h, array, slot, a.ctypes.data, a.nbytes):
+            raise LbzError("dbg_write failed")
+
+    def dbg_write_struct(self, array, slot, v):
+        if self.L.lbz_dbg_write(self.h, array, slot, C.addressof(v), C.sizeof(v)):
+            raise LbzError("dbg_write failed")
+
+    def meta(self, slot):
+        return self.dbg_read_struct(AR_META, slot, BlockMeta)

@@ -1,0 +1,607 @@
+// engine.cu -- host side of the B200 bzip2 block-compression engine and its C ABI.
+//
+// Owns the device slab (layout: lbz_common.cuh), sequences the stage kernels
+//   rle1.cu -> bwt.cu -> mtf.cu -> huffman.cu -> pack.cu
+// on one CUDA stream per engine, and exposes
+//   * the batch API (lbz_compress_chunks / _device / _stream),
+//   * the reference-shaped per-block API (encoder_alloc_size .. transmit,
+//     reference src/encode.h:29-36) on top of a pool of single-chunk engines,
+//   * the stage hooks used by tests/.
+// There is no CPU implementation of any stage in this library.
+#include "lbz_common.cuh"
+#include "../../include/lbzip2_b200.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <condition_variable>
+#include <vector>
+
+struct BwtBuffers {           // must match bwt.cu
+  const uint8_t *T;
+  uint32_t *sa, *sa2, *rank;
+  uint8_t *head;
+  uint64_t *key, *key2;
+  uint32_t *val, *val2, *pos, *pos2, *gs, *gs2;
+  uint32_t *hist, *digit_base, *counters;
+  uint8_t *bwt;
+};
+
+extern "C" {
+int lbz_launch_rle1(const LbzGeom *g, const uint8_t *d_in, const uint32_t *d_chunk_len, uint8_t *d_T,
+                    LbzBlockMeta *d_meta, cudaStream_t st);
+int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B, uint32_t *h_counters,
+                uint32_t *rounds_out, uint64_t *launches, cudaStream_t st);
+int lbz_launch_mtf(const LbzGeom *g, LbzBlockMeta *d_meta, const uint8_t *d_bwt, uint8_t *d_mtfrank,
+                   uint16_t *d_mtfv, uint32_t *d_freq, cudaStream_t st);
+int lbz_launch_huffman(const LbzGeom *g, LbzBlockMeta *d_meta, uint16_t *d_mtfv, const uint32_t *d_freq,
+                       void *d_coding, uint32_t cluster_factor, cudaStream_t st);
+int lbz_launch_pack(const LbzGeom *g, LbzBlockMeta *d_meta, const uint16_t *d_mtfv, const void *d_coding,
+                    uint8_t *d_out, uint32_t *d_out_off, uint32_t *d_total, uint8_t *d_packed, cudaStream_t st);
+}
+
+struct lbz_engine {
+  int device = 0;
+  int level = 9;
+  uint32_t max_chunks = 0;
+  LbzGeom g{};                 // g.nchunks = chunks of the current batch
+  cudaStream_t st = nullptr;
+  size_t dev_bytes = 0;
+  uint64_t launches = 0;
+  uint32_t last_rounds = 0;
+  // device
+  uint8_t *d_in = nullptr;     // max_chunks * mbs raw bytes
+  uint32_t *d_chunk_len = nullptr;
+  uint8_t *d_T = nullptr, *d_bwt = nullptr, *d_mtfrank = nullptr, *d_head = nullptr;
+  uint32_t *d_sa = nullptr, *d_sa2 = nullptr, *d_rank = nullptr;
+  uint64_t *d_key = nullptr, *d_key2 = nullptr;
+  uint32_t *d_val = nullptr, *d_val2 = nullptr, *d_pos = nullptr, *d_pos2 = nullptr, *d_gs = nullptr, *d_gs2 = nullptr;
+  uint32_t *d_hist = nullptr, *d_digit_base = nullptr, *d_counters = nullptr;
+  uint16_t *d_mtfv = nullptr;
+  uint32_t *d_freq = nullptr;
+  LbzCoding *d_coding = nullptr;
+  LbzBlockMeta *d_meta = nullptr;
+  uint8_t *d_out = nullptr, *d_packed = nullptr;
+  uint32_t *d_out_off = nullptr;
+  // pinned host
+  uint32_t *h_chunk_len = nullptr;
+  LbzBlockMeta *h_meta = nullptr;
+  uint32_t *h_counters = nullptr;   // [0..1] sort counters, [2] packed total
+  std::vector<void *> allocs;
+};
+
+#define ENG_CHECK(x)                                                              \
+  do {                                                                            \
+    cudaError_t e_ = (x);                                                         \
+    if (e_ != cudaSuccess) {                                                      \
+      fprintf(stderr, "lbzip2_b200: CUDA error %s at %s:%d: %s\n",                \
+              cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_));  \
+      return -1;                                                                  \
+    }                                                                             \
+  } while (0)
+
+template <class T>
+static int dev_alloc(lbz_engine *e, T **p, size_t count) {
+  void *q = nullptr;
+  const size_t bytes = count * sizeof(T) + 256;
+  cudaError_t err = cudaMalloc(&q, bytes);
+  if (err != cudaSuccess) {
+    fprintf(stderr, "lbzip2_b200: cudaMalloc(%zu) failed: %s\n", bytes, cudaGetErrorString(err));
+    return -1;
+  }
+  e->allocs.push_back(q);
+  e->dev_bytes += bytes;
+  *p = reinterpret_cast<T *>(q);
+  return 0;
+}
+
+static uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+extern "C" const char *lbz_version(void) { return "lbzip2_b200 0.1 (sm_100a)"; }
+
+extern "C" size_t lbz_bound(size_t n) {
+  // incompressible data costs ~1.005 n (reference man page :63-64); per block <= 20 bits/symbol worst case
+  return n + n / 32 + 8192 * (n / 100000 + 2) + 64;
+}
+
+extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) {
+  if (level < 1 || level > 9 || max_chunks < 1 || max_chunks > 16384) {
+    fprintf(stderr, "lbzip2_b200: bad engine parameters (level %d, max_chunks %d)\n", level, max_chunks);
+    return nullptr;
+  }
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "lbzip2_b200: no CUDA device available (%s); this library has no CPU path\n",
+            cudaGetErrorString(err));
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) {
+    fprintf(stderr, "lbzip2_b200: device %d out of range (%d devices)\n", device, ndev);
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  lbz_engine *e = new lbz_engine();
+  e->device = device;
+  e->level = level;
+  e->max_chunks = (uint32_t)max_chunks;
+  LbzGeom &g = e->g;
+  g.mbs = (uint32_t)level * 100000u;
+  g.S1 = round_up(g.mbs + 64, LBZ_TILE);
+  g.S2 = round_up(g.mbs / 4 + 64, LBZ_TILE);
+  g.stride = g.S1 + g.S2;
+  g.tiles1 = g.S1 / LBZ_TILE;
+  g.nchunks = 0;
+  g.out_cap = round_up(g.S1 * 5 / 2 + 8192, 256);
+  const size_t E = (size_t)e->max_chunks * g.stride;
+  const size_t NB = 2 * (size_t)e->max_chunks;
+  int rc = 0;
+  rc |= cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess;
+  rc |= dev_alloc(e, &e->d_in, (size_t)e->max_chunks * g.mbs);
+  rc |= dev_alloc(e, &e->d_chunk_len, e->max_chunks);
+  rc |= dev_alloc(e, &e->d_T, E);
+  rc |= dev_alloc(e, &e->d_bwt, E);
+  rc |= dev_alloc(e, &e->d_mtfrank, E);
+  rc |= dev_alloc(e, &e->d_head, E);
+  rc |= dev_alloc(e, &e->d_sa, E);
+  rc |= dev_alloc(e, &e->d_sa2, E);
+  rc |= dev_alloc(e, &e->d_rank, E);
+  rc |= dev_alloc(e, &e->d_key, E);
+  rc |= dev_alloc(e, &e->d_key2, E);
+  rc |= dev_alloc(e, &e->d_val, E);
+  rc |= dev_alloc(e, &e->d_val2, E);
+  rc |= dev_alloc(e, &e->d_pos, E);
+  rc |= dev_alloc(e, &e->d_pos2, E);
+  rc |= dev_alloc(e, &e->d_gs, E);
+  rc |= dev_alloc(e, &e->d_gs2, E);
+  rc |= dev_alloc(e, &e->d_hist, NB * g.tiles1 * 256);
+  rc |= dev_alloc(e, &e->d_digit_base, NB * 256);
+  rc |= dev_alloc(e, &e->d_counters, 8);
+  rc |= dev_alloc(e, &e->d_mtfv, E);
+  rc |= dev_alloc(e, &e->d_freq, NB * 260);
+  rc |= dev_alloc(e, &e->d_coding, NB);
+  rc |= dev_alloc(e, &e->d_meta, NB);
+  rc |= dev_alloc(e, &e->d_out, NB * (size_t)g.out_cap);
+  rc |= dev_alloc(e, &e->d_packed, lbz_bound((size_t)e->max_chunks * g.mbs));
+  rc |= dev_alloc(e, &e->d_out_off, NB);
+  rc |= cudaHostAlloc((void **)&e->h_chunk_len, e->max_chunks * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess;
+  rc |= cudaHostAlloc((void **)&e->h_meta, NB * sizeof(LbzBlockMeta), cudaHostAllocDefault) != cudaSuccess;
+  rc |= cudaHostAlloc((void **)&e->h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess;
+  if (rc) {
+    fprintf(stderr, "lbzip2_b200: engine allocation failed\n");
+    lbz_engine_destroy(e);
+    return nullptr;
+  }
+  cudaMemsetAsync(e->d_meta, 0, NB * sizeof(LbzBlockMeta), e->st);
+  cudaStreamSynchronize(e->st);
+  return e;
+}
+
+extern "C" void lbz_engine_destroy(lbz_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->st) { cudaStreamSynchronize(e->st); cudaStreamDestroy(e->st); }
+  for (void *p : e->allocs) cudaFree(p);
+  if (e->h_chunk_len) cudaFreeHost(e->h_chunk_len);
+  if (e->h_meta) cudaFreeHost(e->h_meta);
+  if (e->h_counters) cudaFreeHost(e->h_counters);
+  delete e;
+}
+
+extern "C" void *lbz_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void lbz_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" uint64_t lbz_engine_launches(const lbz_engine *e) { return e->launches; }
+extern "C" uint32_t lbz_engine_last_rounds(const lbz_engine *e) { return e->last_rounds; }
+extern "C" size_t lbz_engine_device_bytes(const lbz_engine *e) { return e->dev_bytes; }
+extern "C" uint32_t lbz_dbg_num_slots(const lbz_engine *e) { return 2 * e->g.nchunks; }
+extern "C" int lbz_dbg_set_chunks(lbz_engine *e, uint32_t nchunks) {
+  if (nchunks > e->max_chunks) return -1;
+  e->g.nchunks = nchunks;
+  return 0;
+}
+
+static BwtBuffers bwt_buffers(lbz_engine *e) {
+  BwtBuffers B;
+  B.T = e->d_T; B.sa = e->d_sa; B.sa2 = e->d_sa2; B.rank = e->d_rank; B.head = e->d_head;
+  B.key = e->d_key; B.key2 = e->d_key2; B.val = e->d_val; B.val2 = e->d_val2;
+  B.pos = e->d_pos; B.pos2 = e->d_pos2; B.gs = e->d_gs; B.gs2 = e->d_gs2;
+  B.hist = e->d_hist; B.digit_base = e->d_digit_base; B.counters = e->d_counters; B.bwt = e->d_bwt;
+  return B;
+}
+
+// Set up the chunk table for `n` raw bytes (<= max_chunks chunks).
+static int set_chunks(lbz_engine *e, size_t n) {
+  const size_t mbs = e->g.mbs;
+  const size_t nc = (n + mbs - 1) / mbs;
+  if (nc > e->max_chunks) {
+    fprintf(stderr, "lbzip2_b200: batch of %zu chunks exceeds engine capacity %u\n", nc, e->max_chunks);
+    return -1;
+  }
+  e->g.nchunks = (uint32_t)nc;
+  for (size_t c = 0; c < nc; c++) e->h_chunk_len[c] = (uint32_t)((c + 1) * mbs <= n ? mbs : n - c * mbs);
+  if (nc) ENG_CHECK(cudaMemcpyAsync(e->d_chunk_len, e->h_chunk_len, nc * sizeof(uint32_t), cudaMemcpyHostToDevice, e->st));
+  return 0;
+}
+
+static int run_stage(lbz_engine *e, int stage, const uint8_t *d_in, uint8_t *d_packed) {
+  const LbzGeom *g = &e->g;
+  const uint32_t nb = 2 * g->nchunks;
+  switch (stage) {
+    case LBZ_ST_RLE1:
+      e->launches += 1;
+      return lbz_launch_rle1(g, d_in, e->d_chunk_len, e->d_T, e->d_meta, e->st);
+    case LBZ_ST_BWT:
+      return lbz_run_bwt(g, e->d_meta, bwt_buffers(e), e->h_counters, &e->last_rounds, &e->launches, e->st);
+    case LBZ_ST_MTF:
+      e->launches += 2;
+      return lbz_launch_mtf(g, e->d_meta, e->d_bwt, e->d_mtfrank, e->d_mtfv, e->d_freq, e->st);
+    case LBZ_ST_HUFFMAN:
+      e->launches += 1;
+      return lbz_launch_huffman(g, e->d_meta, e->d_mtfv, e->d_freq, e->d_coding, CLUSTER_FACTOR, e->st);
+    case LBZ_ST_PACK:
+      e->launches += 3;
+      (void)nb;
+      return lbz_launch_pack(g, e->d_meta, e->d_mtfv, e->d_coding, e->d_out, e->d_out_off, e->d_counters + 2,
+                             d_packed, e->st);
+  }
+  return -1;
+}
+
+// Run the whole pipeline for the current chunk table; results: h_meta (host),
+// packed bytes at d_packed (device), *total = packed byte count.
+static int run_pipeline(lbz_engine *e, const uint8_t *d_in, uint8_t *d_packed, size_t *total) {
+  const uint32_t nb = 2 * e->g.nchunks;
+  *total = 0;
+  if (nb == 0) return 0;
+  for (int s = LBZ_ST_RLE1; s <= LBZ_ST_PACK; s++)
+    if (run_stage(e, s, d_in, d_packed)) return -1;
+  ENG_CHECK(cudaMemcpyAsync(e->h_meta, e->d_meta, nb * sizeof(LbzBlockMeta), cudaMemcpyDeviceToHost, e->st));
+  ENG_CHECK(cudaMemcpyAsync(e->h_counters + 2, e->d_counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->st));
+  ENG_CHECK(cudaStreamSynchronize(e->st));
+  size_t sum = 0;
+  for (uint32_t b = 0; b < nb; b++) {
+    const LbzBlockMeta &m = e->h_meta[b];
+    if (m.n == 0) continue;
+    if (m.pad_[0] != 8u * m.out_len) {
+      fprintf(stderr, "lbzip2_b200: internal error: block slot %u packed %u bits, expected %u\n", b, m.pad_[0],
+              8u * m.out_len);
+      return -1;
+    }
+    sum += m.out_len;
+  }
+  if (sum != e->h_counters[2]) {
+    fprintf(stderr, "lbzip2_b200: internal error: gathered %u bytes, expected %zu\n", e->h_counters[2], sum);
+    return -1;
+  }
+  *total = sum;
+  return 0;
+}
+
+static size_t fill_recs(lbz_engine *e, uint64_t raw_base, lbz_block_rec *recs, size_t max_recs, size_t have) {
+  const uint32_t nb = 2 * e->g.nchunks;
+  size_t k = have;
+  for (uint32_t b = 0; b < nb; b++) {
+    const LbzBlockMeta &m = e->h_meta[b];
+    if (m.n == 0) continue;
+    if (recs && k < max_recs) {
+      lbz_block_rec &r = recs[k];
+      const uint64_t chunk_off = (uint64_t)(b >> 1) * e->g.mbs;
+      r.raw_offset = raw_base + chunk_off + ((b & 1) ? e->h_meta[b - 1].raw_len : 0u);
+      r.raw_len = m.raw_len; r.nblock = m.n; r.crc = m.crc; r.bwt_idx = m.bwt_idx; r.tie_count = m.tie_count;
+      r.nmtf = m.nmtf; r.num_trees = m.num_trees; r.num_selectors = m.num_selectors; r.out_len = m.out_len;
+      r.reserved = 0;
+    }
+    k++;
+  }
+  return k;
+}
+
+extern "C" int lbz_compress_chunks(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
+                                   size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
+  if (!e) return -1;
+  ENG_CHECK(cudaSetDevice(e->device));
+  const size_t batch_bytes = (size_t)e->max_chunks * e->g.mbs;
+  size_t o = 0, nrec = 0;
+  for (size_t pos = 0; pos < n; pos += batch_bytes) {
+    const size_t len = (n - pos < batch_bytes) ? n - pos : batch_bytes;
+    if (set_chunks(e, len)) return -1;
+    ENG_CHECK(cudaMemcpyAsync(e->d_in, in + pos, len, cudaMemcpyHostToDevice, e->st));
+    size_t total;
+    if (run_pipeline(e, e->d_in, e->d_packed, &total)) return -1;
+    if (o + total > out_cap) { fprintf(stderr, "lbzip2_b200: output buffer too small\n"); return -2; }
+    ENG_CHECK(cudaMemcpyAsync(out + o, e->d_packed, total, cudaMemcpyDeviceToHost, e->st));
+    ENG_CHECK(cudaStreamSynchronize(e->st));
+    nrec = fill_recs(e, pos, recs, max_recs, nrec);
+    o += total;
+  }
+  if (out_len) *out_len = o;
+  if (num_recs) *num_recs = nrec;
+  return 0;
+}
+
+extern "C" int lbz_compress_chunks_device(lbz_engine *e, const void *d_in, size_t n, void *d_out, size_t out_cap,
+                                          size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
+  if (!e) return -1;
+  ENG_CHECK(cudaSetDevice(e->device));
+  if (set_chunks(e, n)) return -1;
+  if (out_cap < lbz_bound(n)) { fprintf(stderr, "lbzip2_b200: device output buffer too small\n"); return -2; }
+  size_t total;
+  if (run_pipeline(e, reinterpret_cast<const uint8_t *>(d_in), reinterpret_cast<uint8_t *>(d_out), &total)) return -1;
+  const size_t nrec = fill_recs(e, 0, recs, max_recs, 0);
+  if (out_len) *out_len = total;
+  if (num_recs) *num_recs = nrec;
+  return 0;
+}
+
+extern "C" int lbz_compress_stream(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
+                                   size_t *out_len) {
+  if (!e || out_cap < 14) return -1;
+  const size_t mbs = e->g.mbs;
+  const size_t maxrec = 2 * ((n + mbs - 1) / mbs) + 2;
+  std::vector<lbz_block_rec> recs(maxrec);
+  size_t blen = 0, nrec = 0;
+  out[0] = 'B'; out[1] = 'Z'; out[2] = 'h'; out[3] = (uint8_t)('0' + e->level);     // compress.c:290-301
+  if (lbz_compress_chunks(e, in, n, out + 4, out_cap - 14, &blen, recs.data(), maxrec, &nrec)) return -1;
+  uint32_t cc = 0;
+  for (size_t i = 0; i < nrec; i++) cc = ((cc << 1) ^ (cc >> 31)) ^ ~recs[i].crc;     // combine_crc, encode.h:38
+  uint8_t *p = out + 4 + blen;
+  static const uint8_t eos[6] = {0x17, 0x72, 0x45, 0x38, 0x50, 0x90};               // compress.c:304-321
+  memcpy(p, eos, 6);
+  p[6] = (uint8_t)(cc >> 24); p[7] = (uint8_t)(cc >> 16); p[8] = (uint8_t)(cc >> 8); p[9] = (uint8_t)cc;
+  if (out_len) *out_len = 4 + blen + 10;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Stage hooks (tests only)
+extern "C" int lbz_dbg_load(lbz_engine *e, const uint8_t *in, size_t n) {
+  ENG_CHECK(cudaSetDevice(e->device));
+  if (set_chunks(e, n)) return -1;
+  if (n) ENG_CHECK(cudaMemcpyAsync(e->d_in, in, n, cudaMemcpyHostToDevice, e->st));
+  ENG_CHECK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+extern "C" int lbz_dbg_run(lbz_engine *e, int stage) {
+  ENG_CHECK(cudaSetDevice(e->device));
+  if (run_stage(e, stage, e->d_in, e->d_packed)) return -1;
+  ENG_CHECK(cudaStreamSynchronize(e->st));
+  ENG_CHECK(cudaGetLastError());
+  return 0;
+}
+static int dbg_locate(lbz_engine *e, int array, uint32_t slot, void **p, size_t *cap) {
+  const LbzGeom &g = e->g;
+  if (slot >= 2 * e->max_chunks) return -1;
+  const size_t off = lbz_slot_off(g, slot), sc = lbz_slot_cap(g, slot);
+  switch (array) {
+    case LBZ_AR_TEXT: *p = e->d_T + off; *cap = sc; return 0;
+    case LBZ_AR_BWT: *p = e->d_bwt + off; *cap = sc; return 0;
+    case LBZ_AR_MTFV: *p = e->d_mtfv + off; *cap = sc * 2; return 0;
+    case LBZ_AR_FREQ: *p = e->d_freq + (size_t)slot * 260; *cap = 260 * 4; return 0;
+    case LBZ_AR_CODING: *p = e->d_coding + slot; *cap = sizeof(LbzCoding); return 0;
+    case LBZ_AR_OUT: *p = e->d_out + (size_t)slot * g.out_cap; *cap = g.out_cap; return 0;
+    case LBZ_AR_META: *p = e->d_meta + slot; *cap = sizeof(LbzBlockMeta); return 0;
+    case LBZ_AR_SA: *p = e->d_sa + off; *cap = sc * 4; return 0;
+  }
+  return -1;
+}
+extern "C" int lbz_dbg_read(lbz_engine *e, int array, uint32_t slot, void *dst, size_t bytes) {
+  void *p; size_t cap;
+  ENG_CHECK(cudaSetDevice(e->device));
+  if (dbg_locate(e, array, slot, &p, &cap) || bytes > cap) return -1;
+  ENG_CHECK(cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int lbz_dbg_write(lbz_engine *e, int array, uint32_t slot, const void *src, size_t bytes) {
+  void *p; size_t cap;
+  ENG_CHECK(cudaSetDevice(e->device));
+  if (dbg_locate(e, array, slot, &p, &cap) || bytes > cap) return -1;
+  ENG_CHECK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Reference-shaped per-block API (reference src/encode.h:29-36).
+//
+// The caller owns `struct encoder_state` (plain malloc/free, no destructor:
+// src/compress.c:89,223), so it only holds a handle; the device context is a
+// pooled single-chunk engine acquired by the first collect() and released by
+// transmit().  Calls on distinct states may come from different threads
+// concurrently (src/compress.c:81,103,113,217,222); every pooled engine has its
+// own stream, so concurrent blocks overlap on the GPU.
+struct encoder_state {
+  uint32_t magic;
+  uint32_t max_block_size;
+  uint32_t cluster_factor;
+  int32_t pool_slot;         // -1: no device context yet
+  uint32_t raw_len;          // raw bytes staged so far
+  uint32_t done;             // encode() has run
+  uint32_t out_len;
+  uint32_t crc;
+  int32_t rle_state;         // mirrors the reference's collect() state for resumed calls
+  uint32_t rle_char;
+  uint32_t staged_cap;
+  uint8_t *staged;           // pinned staging of the raw bytes of this block (lives after the struct)
+};
+
+namespace {
+#define POOL_MAX 256
+struct Pool {
+  std::mutex mu;
+  std::condition_variable cv;
+  lbz_engine *engines[POOL_MAX] = {};   // fixed array: slots are read without the lock by their owner
+  int levels[POOL_MAX] = {};
+  bool busy[POOL_MAX] = {};
+  int count = 0;
+  int max_engines = 0;
+  int device = 0;
+} g_pool;
+
+[[noreturn]] void die(const char *msg) {
+  fprintf(stderr, "lbzip2_b200: fatal: %s\n", msg);
+  abort();      // the reference API has no error channel on the encode side
+}
+
+int pool_acquire(int level) {
+  std::unique_lock<std::mutex> lk(g_pool.mu);
+  if (g_pool.max_engines == 0) {
+    const char *s = getenv("LBZIP2_B200_CONTEXTS");
+    g_pool.max_engines = s ? atoi(s) : 32;
+    if (g_pool.max_engines < 1) g_pool.max_engines = 1;
+    if (g_pool.max_engines > POOL_MAX) g_pool.max_engines = POOL_MAX;
+    const char *d = getenv("LBZIP2_B200_DEVICE");
+    g_pool.device = d ? atoi(d) : 0;
+  }
+  for (;;) {
+    for (int i = 0; i < g_pool.count; i++)
+      if (!g_pool.busy[i] && g_pool.engines[i] && g_pool.levels[i] == level) { g_pool.busy[i] = true; return i; }
+    int slot = -1;
+    lbz_engine *old = nullptr;
+    if (g_pool.count < g_pool.max_engines) {
+      slot = g_pool.count++;
+    } else {
+      for (int i = 0; i < g_pool.count; i++)       // recycle an idle context of another level
+        if (!g_pool.busy[i] && g_pool.engines[i]) { slot = i; old = g_pool.engines[i]; break; }
+    }
+    if (slot >= 0) {
+      g_pool.busy[slot] = true;
+      g_pool.engines[slot] = nullptr;
+      g_pool.levels[slot] = level;
+      lk.unlock();
+      if (old) lbz_engine_destroy(old);
+      lbz_engine *e = lbz_engine_create(g_pool.device, level, 1);
+      if (!e) die("cannot create a device context (no usable GPU?)");
+      lk.lock();
+      g_pool.engines[slot] = e;
+      return slot;
+    }
+    g_pool.cv.wait(lk);
+  }
+}
+void pool_release(int i) {
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  g_pool.busy[i] = false;
+  g_pool.cv.notify_one();
+}
+}  // namespace
+
+#define ENC_MAGIC 0xB2005A42u
+
+extern "C" size_t encoder_alloc_size(unsigned long max_block_size) {
+  // handle + host staging for the raw bytes of one block.  A block of n' <=
+  // mbs RLE1 bytes can cover up to mbs*259/5 raw bytes in theory; the
+  // scheduler never offers more than in_granul = mbs bytes per state in the
+  // default mode (src/process.c:631, src/compress.c:93-110).  collect()
+  // handles longer inputs by stopping at the staging capacity when needed.
+  return sizeof(struct encoder_state) + 64 + (size_t)max_block_size * 2 + 64;
+}
+
+extern "C" void encoder_init(struct encoder_state *s, unsigned long max_block_size, unsigned cluster_factor) {
+  if (!s || max_block_size == 0 || max_block_size > 900000 || cluster_factor == 0 || cluster_factor > 65535)
+    die("encoder_init: bad arguments (src/encode.c:121-123)");
+  if (max_block_size % 100000) die("encoder_init: block size must be a multiple of 100000 in this build");
+  memset(s, 0, sizeof(*s));
+  s->magic = ENC_MAGIC;
+  s->max_block_size = (uint32_t)max_block_size;
+  s->cluster_factor = cluster_factor;
+  s->pool_slot = -1;
+  s->staged = reinterpret_cast<uint8_t *>(s) + ((sizeof(struct encoder_state) + 63) / 64) * 64;
+  s->staged_cap = (uint32_t)max_block_size * 2;
+}
+
+// collect(): the raw bytes offered to this state are staged on the host side
+// of the handle, the RLE1 kernel runs over everything staged so far, and the
+// block record tells how many raw bytes the block takes (its cut point is a
+// prefix property, see rle1.cu).  In the scheduler's default mode there is
+// exactly one collect() per state with at most max_block_size bytes
+// (src/compress.c:93-110, src/process.c:631).  Repeated calls (the -u mode,
+// src/compress.c:160-187) are accepted as long as one block does not need more
+// than max_block_size raw bytes; beyond that this build stops loudly (row f4
+// of SURVEY.md 8 is not built yet).
+extern "C" int collect(struct encoder_state *s, const uint8_t *buf, size_t *buf_sz) {
+  if (!s || s->magic != ENC_MAGIC) die("collect: state not initialised");
+  if (s->done) die("collect: called after encode()");
+  if (s->rle_state < 0) return 1;                       // already full: nothing is consumed
+  const size_t avail = *buf_sz;
+  if (avail == 0) return 0;
+  const uint32_t mbs = s->max_block_size;
+  if (s->raw_len >= mbs) die("collect: one block would need more than max_block_size raw bytes (not supported yet)");
+  if (s->pool_slot < 0) s->pool_slot = pool_acquire((int)(mbs / 100000));
+  lbz_engine *e = g_pool.engines[s->pool_slot];
+  const size_t take = (avail < (size_t)(mbs - s->raw_len)) ? avail : (size_t)(mbs - s->raw_len);
+  memcpy(s->staged + s->raw_len, buf, take);
+  const uint32_t old_len = s->raw_len;
+  const uint32_t new_len = old_len + (uint32_t)take;
+  if (lbz_dbg_load(e, s->staged, new_len)) die("collect: H2D failed");
+  if (lbz_dbg_run(e, LBZ_ST_RLE1)) die("collect: RLE1 kernel failed");
+  LbzBlockMeta m;
+  if (lbz_dbg_read(e, LBZ_AR_META, 0, &m, sizeof m)) die("collect: meta readback failed");
+  int full = 0;
+  if (m.raw_len < new_len) {            // the block closed before the end of the staged bytes
+    s->raw_len = m.raw_len;             // >= old_len: everything before was consumed without closing
+    s->rle_state = -1;
+    full = 1;
+  } else {
+    s->raw_len = new_len;
+    if (m.n >= mbs) { s->rle_state = -1; full = 1; }   // n' == mbs is only reached by a filling write
+  }
+  *buf_sz = avail - (s->raw_len - old_len);
+  return full;
+}
+
+extern "C" size_t encode(struct encoder_state *s, uint32_t *crc) {
+  if (!s || s->magic != ENC_MAGIC) die("encode: state not initialised");
+  if (s->raw_len == 0 || s->pool_slot < 0) die("encode: empty block (src/encode.c:448)");
+  lbz_engine *e = g_pool.engines[s->pool_slot];
+  // exactly the consumed bytes form this block; run every stage on them
+  if (lbz_dbg_load(e, s->staged, s->raw_len)) die("encode: H2D failed");
+  for (int st = LBZ_ST_RLE1; st <= LBZ_ST_PACK; st++)
+    if (lbz_dbg_run(e, st)) die("encode: kernel failed");
+  LbzBlockMeta m[2];
+  if (lbz_dbg_read(e, LBZ_AR_META, 0, &m[0], sizeof m[0]) || lbz_dbg_read(e, LBZ_AR_META, 1, &m[1], sizeof m[1]))
+    die("encode: meta readback failed");
+  if (m[0].raw_len != s->raw_len || m[1].n != 0) die("encode: internal error: block split changed");
+  if (m[0].pad_[0] != 8u * m[0].out_len) die("encode: internal size mismatch");
+  s->out_len = m[0].out_len;
+  s->crc = m[0].crc;
+  s->done = 1;
+  if (crc) *crc = m[0].crc;
+  return m[0].out_len;
+}
+
+extern "C" void *transmit(struct encoder_state *s, void *buf) {
+  if (!s || s->magic != ENC_MAGIC || !s->done) die("transmit: encode() has not run");
+  if (!buf) die("transmit: NULL buffer is not supported by this build");
+  lbz_engine *e = g_pool.engines[s->pool_slot];
+  const size_t bytes = ((size_t)s->out_len + 3) / 4 * 4;
+  if (lbz_dbg_read(e, LBZ_AR_OUT, 0, buf, bytes)) die("transmit: D2H failed");
+  pool_release(s->pool_slot);
+  s->pool_slot = -1;
+  return buf;
+}
+
+extern "C" int32_t divbwt(uint8_t *T, int32_t *SA, int32_t *bucket, int32_t n) {
+  (void)bucket;
+  if (n <= 0 || n > 900000) die("divbwt: bad length");
+  const int slot = pool_acquire(9);
+  lbz_engine *e = g_pool.engines[slot];
+  // one chunk, one block: inject the text and the block record, run the BWT stage
+  e->g.nchunks = 1;
+  LbzBlockMeta m;
+  memset(&m, 0, sizeof m);
+  m.n = (uint32_t)n;
+  LbzBlockMeta z;
+  memset(&z, 0, sizeof z);
+  if (lbz_dbg_write(e, LBZ_AR_TEXT, 0, T, (size_t)n) || lbz_dbg_write(e, LBZ_AR_META, 0, &m, sizeof m) ||
+      lbz_dbg_write(e, LBZ_AR_META, 1, &z, sizeof z) || lbz_dbg_run(e, LBZ_ST_BWT))
+    die("divbwt: device error");
+  std::vector<uint8_t> bw((size_t)n);
+  if (lbz_dbg_read(e, LBZ_AR_BWT, 0, bw.data(), (size_t)n) || lbz_dbg_read(e, LBZ_AR_META, 0, &m, sizeof m))
+    die("divbwt: readback failed");
+  for (int32_t i = 0; i < n; i++) SA[i] = bw[i];
+  pool_release(slot);
+  return (int32_t)m.bwt_idx;
+}

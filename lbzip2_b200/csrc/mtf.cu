@@ -1,0 +1,306 @@
+// mtf.cu -- move-to-front + zero-run coding + symbol histogram.
+//
+// Replaces do_mtf() (reference src/encode.c:360-425) and make_map_e()
+// (src/encode.c:340-355).  Two kernels, one CTA per block:
+//
+//  k_mtf_ranks  computes the MTF rank of every BWT position.  The serial
+//     dependency (the recency list) is broken per 2048-symbol warp segment:
+//     the list in front of a segment is "all symbols ordered by their last
+//     occurrence before the segment", so each warp records the last
+//     occurrence of every symbol in its segment, a prefix-max over the 32
+//     warps (+ the carry of the previous super-tile) gives each warp its own
+//     start list (bitonic sort of 256 keys in registers), and the warp then
+//     walks its segment with the 256-entry list held as 8 bytes per lane
+//     (__vcmpeq4 + ballot to find a symbol, byte shifts + one shuffle to move
+//     it to the front).  Positions equal to their predecessor are rank 0 by
+//     construction and are skipped.
+//
+//  k_mtf_emit   turns (rank, zero-run) into the u16 symbol stream: RUNA/RUNB
+//     digits of each zero run (bijective base 2, encode.c:381-386), rank+1
+//     otherwise, EOB at the end, plus the histogram that seeds the prefix-code
+//     clustering.  Run starts are a prefix max, output offsets a prefix sum;
+//     one CTA streams the block with carried state, like rle1.cu.
+#include "lbz_common.cuh"
+#include <climits>
+
+#define MTF_THREADS 1024
+#define MTF_WARPS 32
+#define MTF_SEG 2048u                       // symbols per warp per super-tile
+#define MTF_SUPER (MTF_SEG * MTF_WARPS)
+
+__device__ __forceinline__ void cmpx_desc(uint32_t &a, uint32_t &b) {   // a >= b afterwards
+  const uint32_t hi = max(a, b), lo = min(a, b);
+  a = hi; b = lo;
+}
+
+__global__ void __launch_bounds__(MTF_THREADS, 1)
+k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ bwt,
+            uint8_t *__restrict__ mtfrank) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t n = meta[b].n;
+  if (n == 0) return;
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint8_t *src = bwt + off;
+  uint8_t *dstr = mtfrank + off;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+  __shared__ int s_tab[MTF_WARPS][256];
+  __shared__ int s_carry[256];
+  __shared__ uint8_t s_dense[256];
+
+  if (tid < 256) {
+    // dense renumbering of the used byte values (encode.c:340-355)
+    uint32_t cnt = 0;
+    for (uint32_t w = 0; w < 8; w++) {
+      const uint32_t bits = meta[b].used[w];
+      if (w < (tid >> 5)) cnt += __popc(bits);
+      else if (w == (tid >> 5)) cnt += __popc(bits & ((1u << (tid & 31u)) - 1u));
+    }
+    s_dense[tid] = (uint8_t)cnt;
+    s_carry[tid] = -1 - (int)tid;          // never seen: identity order
+  }
+
+  for (uint32_t sbase = 0; sbase < n; sbase += MTF_SUPER) {
+    __syncthreads();
+    for (uint32_t i = tid; i < MTF_WARPS * 256; i += MTF_THREADS) (&s_tab[0][0])[i] = INT_MIN;
+    __syncthreads();
+    const uint32_t segbase = sbase + warp * MTF_SEG;
+
+    // (A) last occurrence of every symbol inside this warp's segment
+    if (segbase < n) {
+      for (uint32_t q = 0; q < MTF_SEG / 32; q++) {
+        const uint32_t p = segbase + q * 32 + lane;
+        if (segbase + q * 32 >= n) break;
+        const bool valid = p < n;
+        const uint32_t c = valid ? s_dense[src[p]] : 0xFFFFu;
+        const uint32_t nc = __shfl_down_sync(0xffffffffu, c, 1);
+        if (valid && (lane == 31 || c != nc)) atomicMax(&s_tab[warp][c], (int)p);
+      }
+    }
+    __syncthreads();
+    // (B) exclusive prefix max over warps, seeded with the carry
+    if (tid < 256) {
+      int run = s_carry[tid];
+#pragma unroll 4
+      for (int w = 0; w < MTF_WARPS; w++) {
+        const int t = s_tab[w][tid];
+        s_tab[w][tid] = run;
+        run = max(run, t);
+      }
+      s_carry[tid] = run;
+    }
+    __syncthreads();
+    if (segbase >= n) continue;
+
+    // (C) start list = symbols by descending last occurrence
+    uint32_t e[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const uint32_t c = lane * 8 + r;
+      e[r] = ((uint32_t)(s_tab[warp][c] + 512) << 8) | c;
+    }
+    // bitonic sort of 256 elements, blocked layout (index = lane*8 + r), descending
+#pragma unroll
+    for (uint32_t k = 2; k <= 256; k <<= 1) {
+#pragma unroll
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        if (j >= 8) {
+          const uint32_t lj = j >> 3;
+          const bool upper = (lane & lj) != 0;                       // partner has the lower index
+          const bool desc = ((lane * 8) & k) == 0;                   // this k-block sorts descending
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, e[r], lj);
+            const bool keep_max = (desc != upper);
+            e[r] = keep_max ? max(e[r], o) : min(e[r], o);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const int pr = r ^ (int)j;
+            if (pr > r) {
+              const bool desc = (((lane * 8 + r) & k) == 0);
+              if (desc) cmpx_desc(e[r], e[pr]); else cmpx_desc(e[pr], e[r]);
+            }
+          }
+        }
+      }
+    }
+    uint32_t lo = (e[0] & 0xFFu) | ((e[1] & 0xFFu) << 8) | ((e[2] & 0xFFu) << 16) | ((e[3] & 0xFFu) << 24);
+    uint32_t hi = (e[4] & 0xFFu) | ((e[5] & 0xFFu) << 8) | ((e[6] & 0xFFu) << 16) | ((e[7] & 0xFFu) << 24);
+
+    // walk the segment
+    uint32_t prev_sym = segbase ? s_dense[src[segbase - 1]] : 0u;    // list front before the segment
+    for (uint32_t q = 0; q < MTF_SEG / 32; q++) {
+      if (segbase + q * 32 >= n) break;
+      const uint32_t p = segbase + q * 32 + lane;
+      const bool valid = p < n;
+      const uint32_t c = valid ? s_dense[src[p]] : 0xFFFFu;
+      uint32_t pc = __shfl_up_sync(0xffffffffu, c, 1);
+      if (lane == 0) pc = prev_sym;
+      const bool nz = valid && (c != pc);
+      uint32_t todo = __ballot_sync(0xffffffffu, nz);
+      uint32_t myrank = 0;
+      while (todo) {
+        const uint32_t src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t cc = __shfl_sync(0xffffffffu, c, src_lane);
+        const uint32_t rep = cc * 0x01010101u;
+        const uint32_t mlo = __vcmpeq4(lo, rep), mhi = __vcmpeq4(hi, rep);
+        const uint32_t hit = __ballot_sync(0xffffffffu, (mlo | mhi) != 0);
+        const uint32_t L = __ffs(hit) - 1;
+        uint32_t bi = mlo ? ((__ffs(mlo) - 1) >> 3) : (4 + ((__ffs(mhi) - 1) >> 3));
+        bi = __shfl_sync(0xffffffffu, bi, L);
+        if (lane == src_lane) myrank = L * 8 + bi;
+        // move to front
+        uint32_t incoming = __shfl_up_sync(0xffffffffu, hi >> 24, 1);
+        if (lane == 0) incoming = cc;
+        const uint32_t slo = (lo << 8) | incoming;
+        const uint32_t shi = (hi << 8) | (lo >> 24);
+        if (lane < L) { lo = slo; hi = shi; }
+        else if (lane == L) {
+          // bytes 0..bi take the shifted value, bytes above stay
+          if (bi < 4) {
+            const uint32_t mask = (bi == 3) ? 0xFFFFFFFFu : ((1u << (8 * (bi + 1))) - 1u);
+            lo = (slo & mask) | (lo & ~mask);
+          } else {
+            const uint32_t bj = bi - 4;
+            const uint32_t mask = (bj == 3) ? 0xFFFFFFFFu : ((1u << (8 * (bj + 1))) - 1u);
+            hi = (shi & mask) | (hi & ~mask);
+            lo = slo;
+          }
+        }
+      }
+      if (valid) dstr[p] = (uint8_t)myrank;     // 0 for positions equal to their predecessor
+      prev_sym = __shfl_sync(0xffffffffu, c, 31);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+#define EMIT_THREADS 1024
+#define EMIT_PER 8
+#define EMIT_TILE (EMIT_THREADS * EMIT_PER)
+
+__global__ void __launch_bounds__(EMIT_THREADS, 1)
+k_mtf_emit(LbzGeom g, LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ bwt,
+           const uint8_t *__restrict__ mtfrank, uint16_t *__restrict__ mtfv,
+           uint32_t *__restrict__ freq_out) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t n = meta[b].n;
+  if (n == 0) return;
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint8_t *src = bwt + off;
+  const uint8_t *rk = mtfrank + off;
+  uint16_t *out = mtfv + off;
+  const uint32_t tid = threadIdx.x;
+
+  __shared__ uint32_t s_freq[LBZ_MAX_ALPHA + 2];
+  __shared__ uint32_t ws[40];
+  __shared__ int wsi[40];
+  __shared__ uint32_t s_first_dense;
+  for (uint32_t i = tid; i < LBZ_MAX_ALPHA + 2; i += EMIT_THREADS) s_freq[i] = 0;
+  uint32_t ninuse = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) ninuse += __popc(meta[b].used[w]);
+  if (tid == 0) {
+    // dense number of the first BWT byte: position 0 is a zero iff it is 0
+    const uint32_t v = src[0];
+    uint32_t cnt = 0;
+    for (uint32_t w = 0; w < 8; w++) {
+      const uint32_t bits = meta[b].used[w];
+      if (w < (v >> 5)) cnt += __popc(bits);
+      else if (w == (v >> 5)) cnt += __popc(bits & ((1u << (v & 31u)) - 1u));
+    }
+    s_first_dense = cnt;
+  }
+  __syncthreads();
+  const bool first_is_zero = (s_first_dense == 0);
+
+  int carry_nz = -1;          // last non-zero-rank position so far
+  uint32_t m = 0;             // symbols written so far
+  for (uint32_t tb = 0; tb < n; tb += EMIT_TILE) {
+    const uint32_t p0 = tb + tid * EMIT_PER;
+    uint32_t c[EMIT_PER + 2];   // bytes p0-1 .. p0+8
+#pragma unroll
+    for (int j = 0; j < EMIT_PER + 2; j++) {
+      const int64_t p = (int64_t)p0 + j - 1;
+      c[j] = (p >= 0 && p < (int64_t)n) ? src[p] : 0x100u;
+    }
+    uint32_t zmask = 0;
+    int last = -1;
+#pragma unroll
+    for (int j = 0; j < EMIT_PER; j++) {
+      const uint32_t p = p0 + j;
+      if (p < n) {
+        const bool z = p ? (c[j + 1] == c[j]) : first_is_zero;
+        if (z) zmask |= 1u << j; else last = (int)p;
+      }
+    }
+    int tmax;
+    int lnz = cta_excl_max(last, -1, wsi, &tmax);
+    lnz = max(lnz, carry_nz);
+    uint32_t ec[EMIT_PER], kk[EMIT_PER];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < EMIT_PER; j++) {
+      const uint32_t p = p0 + j;
+      ec[j] = 0; kk[j] = 0;
+      if (p < n) {
+        if (zmask & (1u << j)) {
+          const bool runend = (p + 1 >= n) || (c[j + 2] != c[j + 1]);
+          if (runend) {
+            const uint32_t k = (uint32_t)((int)p - lnz);
+            kk[j] = k;
+            ec[j] = 31u - __clz(k + 1u);
+          }
+        } else {
+          lnz = (int)p;
+          ec[j] = 1;
+        }
+      }
+      sum += ec[j];
+    }
+    uint32_t tot;
+    uint32_t o = m + cta_excl_sum(sum, ws, &tot);
+#pragma unroll
+    for (int j = 0; j < EMIT_PER; j++) {
+      const uint32_t p = p0 + j;
+      if (p < n && ec[j]) {
+        if (zmask & (1u << j)) {
+          const uint32_t v = kk[j] + 1u, nd = ec[j];
+          for (uint32_t d = 0; d < nd; d++) out[o + d] = (uint16_t)((v >> d) & 1u);
+          const uint32_t ones = __popc(v & ((1u << nd) - 1u));
+          if (ones) atomicAdd(&s_freq[1], ones);
+          if (nd - ones) atomicAdd(&s_freq[0], nd - ones);
+        } else {
+          const uint32_t sym = (uint32_t)rk[p] + 1u;
+          out[o] = (uint16_t)sym;
+          atomicAdd(&s_freq[sym], 1u);
+        }
+        o += ec[j];
+      }
+    }
+    m += tot;
+    carry_nz = max(carry_nz, tmax);
+  }
+  __syncthreads();
+  const uint32_t eob = ninuse + 1u, as = ninuse + 2u;
+  const uint32_t nm = m + 1u;
+  const uint32_t padded = ((nm + LBZ_GROUP - 1) / LBZ_GROUP) * LBZ_GROUP;
+  if (tid == 0) { out[m] = (uint16_t)eob; s_freq[eob] = 1; }
+  if (tid >= 1 && m + tid < padded) out[m + tid] = (uint16_t)as;      // group padding (encode.c:1034)
+  __syncthreads();
+  for (uint32_t i = tid; i < 260; i += EMIT_THREADS) freq_out[b * 260 + i] = (i < LBZ_MAX_ALPHA + 1) ? s_freq[i] : 0u;
+  if (tid == 0) { meta[b].nmtf = nm; meta[b].alpha_size = as; }
+}
+
+extern "C" int lbz_launch_mtf(const LbzGeom *g, LbzBlockMeta *d_meta, const uint8_t *d_bwt, uint8_t *d_mtfrank,
+                              uint16_t *d_mtfv, uint32_t *d_freq, cudaStream_t st) {
+  const uint32_t nb = 2 * g->nchunks;
+  if (nb == 0) return 0;
+  k_mtf_ranks<<<nb, MTF_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank);
+  k_mtf_emit<<<nb, EMIT_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_mtfv, d_freq);
+  LBZ_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,91 @@
+"""Multi-GPU sharding of the block-compression path (host logic only).
+
+Blocks are independent: raw chunk i (level*100000 bytes,
+reference src/process.c:631) goes to rank i mod world; no exchange happens
+during compute; afterwards the byte-aligned block bitstreams are gathered to
+rank 0 in stream order (reference order key: (major = chunk, minor = block in
+chunk), src/compress.c:85-86,99-100) and rank 0 adds the stream header,
+trailer and combined CRC (src/compress.c:290-321, src/encode.h:38).
+
+Works with any torch.distributed backend: NCCL over NVLink on GPUs, gloo on
+CPU tensors (used by the world_size-2 CPU test)."""
+import numpy as np
+
+
+def rank_chunk_ids(n_bytes, mbs, world, rank):
+    nchunks = (n_bytes + mbs - 1) // mbs
+    return list(range(rank, nchunks, world))
+
+
+def rank_input(data, mbs, world, rank):
+    """Concatenation of this rank's chunks (a view-free copy; the short last
+    chunk of the stream, if this rank owns it, is last here as well)."""
+    a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    ids = rank_chunk_ids(a.size, mbs, world, rank)
+    if not ids:
+        return np.zeros(0, np.uint8)
+    return np.concatenate([a[i * mbs:(i + 1) * mbs] for i in ids])
+
+
+def block_table(recs, mbs):
+    """(local chunk index, out_len, crc) per block, in local stream order."""
+    t = np.zeros((len(recs), 3), dtype=np.int64)
+    for k, r in enumerate(recs):
+        t[k] = (r.raw_offset // mbs, r.out_len, r.crc)
+    return t
+
+
+def assemble_stream(level, tables, payloads, world):
+    """Rank-0 side: interleave the per-rank block payloads into stream order.
+    tables[r]: int64 [nblocks_r, 3]; payloads[r]: uint8 array of rank r's blocks
+    concatenated in its local order."""
+    offs = []
+    for r in range(world):
+        o = np.concatenate(([0], np.cumsum(tables[r][:, 1]))) if len(tables[r]) else np.zeros(1, np.int64)
+        offs.append(o)
+    cursor = [0] * world
+    parts = [b"BZh" + bytes([ord("0") + level])]
+    cc = 0
+    nchunks_total = sum((int(t[:, 0].max()) + 1) if len(t) else 0 for t in tables)
+    for i in range(nchunks_total):
+        r = i % world
+        local = i // world
+        t = tables[r]
+        while cursor[r] < len(t) and t[cursor[r], 0] == local:
+            k = cursor[r]
+            parts.append(payloads[r][offs[r][k]:offs[r][k + 1]].tobytes())
+            crc = int(t[k, 2]) & 0xFFFFFFFF
+            cc = (((cc << 1) & 0xFFFFFFFF) ^ (cc >> 31) ^ crc ^ 0xFFFFFFFF) & 0xFFFFFFFF
+            cursor[r] += 1
+    parts.append(bytes([0x17, 0x72, 0x45, 0x38, 0x50, 0x90]) + cc.to_bytes(4, "big"))
+    return b"".join(parts)
+
+
+def gather_blocks(table, payload, dist, device):
+    """Gather (table, payload) of every rank to rank 0 with torch.distributed.
+    `payload` is a uint8 torch tensor on `device` (stays on the GPU for NCCL).
+    Returns (tables, payloads) lists of numpy arrays on rank 0, else (None, None)."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = torch.tensor([table.shape[0], payload.numel()], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [s.cpu().tolist() for s in all_sizes]
+    max_rows = max(s[0] for s in all_sizes)
+    max_bytes = max(s[1] for s in all_sizes)
+    tpad = torch.zeros((max(max_rows, 1), 3), dtype=torch.int64, device=device)
+    if table.shape[0]:
+        tpad[: table.shape[0]] = torch.from_numpy(table).to(device)
+    ppad = torch.zeros(max(max_bytes, 1), dtype=torch.uint8, device=device)
+    ppad[: payload.numel()] = payload
+    if rank == 0:
+        tl = [torch.zeros_like(tpad) for _ in range(world)]
+        pl = [torch.zeros_like(ppad) for _ in range(world)]
+        dist.gather(tpad, tl, dst=0)
+        dist.gather(ppad, pl, dst=0)          # NCCL over NVLink when tensors are on GPUs
+        tables = [tl[r][: all_sizes[r][0]].cpu().numpy() for r in range(world)]
+        payloads = [pl[r][: all_sizes[r][1]].cpu().numpy() for r in range(world)]
+        return tables, payloads
+    dist.gather(tpad, None, dst=0)
+    dist.gather(ppad, None, dst=0)
+    return None, None

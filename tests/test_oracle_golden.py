@@ -1,0 +1,52 @@
+"""CPU: the oracle restatement reproduces the committed golden vectors, which
+were produced by the unmodified reference CLI (tests/golden/make_golden.py)."""
+import bz2
+import hashlib
+
+import pytest
+
+import golden_util
+import orclib
+
+MAN = golden_util.manifest()
+CASES = [(n, int(lv)) for n, e in sorted(MAN.items()) for lv in e["levels"]]
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_oracle_matches_reference_golden(chunk):
+    bad = []
+    for name, lv in CASES[chunk::8]:
+        ent = MAN[name]
+        raw = golden_util.load_input(name)
+        assert hashlib.sha256(raw).hexdigest() == ent["sha256"]
+        got, infos = orclib.orc_stream(raw, lv)
+        exp = ent["levels"][str(lv)]
+        assert len(infos) == exp["blocks"]
+        if exp["periodic"]:
+            # documented exception: ambiguous primary index of exactly periodic blocks
+            assert len(got) == exp["ref_len"]
+            assert bz2.decompress(got) == raw
+            assert any(i.tie_count > 1 for i in infos)
+        elif hashlib.sha256(got).hexdigest() != exp["ref_sha256"]:
+            bad.append((name, lv))
+    assert not bad
+
+
+def test_crc_table_known_answers():
+    # CRC-32/BZIP2 check value and the table generator rule (build-aux/make-crctab.pl:29-33)
+    import ctypes as C
+    L = orclib.oracle()
+    buf = (C.c_uint8 * 9)(*b"123456789")
+    assert (L.orc_crc_update(0xFFFFFFFF, buf, 9) ^ 0xFFFFFFFF) == 0xFC891918
+
+
+def test_single_byte_run_known_answer():
+    # SURVEY.md A.1 [validated against the reference]: 900000 x 'a' at -9
+    st = orclib.orc_block_stages(b"a" * 900000, 900000)
+    assert st["nblock"] == 17375 and st["bwt_idx"] == 3474 and st["nmtf"] == 28 and st["out_len"] == 34
+    assert bytes(st["block"][:5]) == b"aaaa\xff" and bytes(st["block"][-5:]) == b"aaaa\xe6"
+
+
+def test_empty_stream():
+    got, infos = orclib.orc_stream(b"", 9)
+    assert got == b"BZh9\x17\x72\x45\x38\x50\x90\x00\x00\x00\x00" and infos == []
