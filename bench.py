@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- input MB/s of bzip2 block compression at -9 on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (RLE1+CRC -> BWT -> MTF/RLE2 -> multi-table
+Huffman -> bit-pack) over one batch: 100 MB of enwik8-shaped synthetic text per
+GPU at -9 (BASELINE.json configs[1]; for N>1 every rank gets its own 100 MB
+stream of the same generator family = weak scaling of configs[2], and the
+byte-aligned block bitstreams are gathered to rank 0 in stream order over NCCL).
+
+  value  : whole-job input MB/s with the input already resident in HBM
+           (lbz_compress_chunks_device), timed with CUDA events, max over ranks
+  e2e    : same metric through the public host API (lbz_compress_chunks) from
+           PINNED HOST memory: H2D of the input and D2H of the .bz2 bytes are
+           inside the timed region
+  roofline / cpu_baseline / clocks : see DESIGN.md "Measurement"
+
+--impl reference times the reference's own CPU implementation (the unmodified
+lbzip2 CLI built into oracle/_ref by oracle/Makefile; the oracle port if that
+binary is absent) on the same workload with all host threads.
+"""
+import argparse
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+MB = 1_000_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--size-mb", type=int, default=100, help="raw MB per GPU per step")
+    ap.add_argument("--level", type=int, default=9)
+    ap.add_argument("--workload", default="text", choices=["text", "random", "runs_fib"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    return ap.parse_args()
+
+
+def make_input(workload, nbytes, rank):
+    import synth
+    if workload == "text":
+        return synth.text(nbytes, offset=rank)
+    if workload == "random":
+        return synth.random_bytes(nbytes, seed=1 + rank)
+    return synth.runs_and_fib(nbytes)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------- reference arm ---
+def ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "lbzip2")
+    return p if os.path.exists(p) else None
+
+
+def time_reference(data, level, steps, warmup, threads):
+    """Time the reference CPU implementation on `data` (bytes).  Returns (ms list, kind, sha256)."""
+    binp = ref_binary()
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    path = os.path.join(tmp, "lbz_bench_%d.raw" % os.getpid())
+    with open(path, "wb") as f:
+        f.write(data)
+    times, sha = [], None
+    try:
+        if binp:
+            kind = "reference"
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                if i == 0:
+                    out = subprocess.run([binp, "-%d" % level, "-n%d" % threads, "-c", path], stdout=subprocess.PIPE, check=True).stdout
+                    sha = hashlib.sha256(out).hexdigest()
+                else:
+                    with open(os.devnull, "wb") as dn:
+                        subprocess.run([binp, "-%d" % level, "-n%d" % threads, "-c", path], stdout=dn, check=True)
+                dt = (time.perf_counter() - t0) * 1e3
+                if i >= warmup:
+                    times.append(dt)
+        else:
+            import orclib
+            kind = "port"
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                out, _ = orclib.orc_stream(data, level)
+                dt = (time.perf_counter() - t0) * 1e3
+                sha = hashlib.sha256(out).hexdigest()
+                if i >= warmup:
+                    times.append(dt)
+    finally:
+        os.unlink(path)
+    return times, kind, sha
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nbytes = a.size_mb * MB
+    data = make_input(a.workload, nbytes, 0)
+    cores = os.cpu_count() or 1
+    binp = ref_binary()
+    threads = cores if binp else 1
+    # bounded sample: the whole per-GPU batch when the pthread reference is available
+    # (a fraction of a second on a many-core host), 10 MB for the scalar oracle port
+    sample = data if binp else data[: 10 * MB]
+    times, kind, _ = time_reference(sample, a.level, a.steps, a.warmup, threads)
+    ms = float(np.mean(times))
+    val = len(sample) / MB / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "input MB/s at -9 (bit-exact .bz2)", "value": round(val, 2), "unit": "MB/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%d MB enwik8-shaped synthetic text at -%d (bounded sample of the per-GPU batch)" % (len(sample) // MB, a.level)
+                   if a.workload == "text" else "%d MB %s at -%d" % (len(sample) // MB, a.workload, a.level)},
+        "cpu_baseline": {"value": round(val, 2), "unit": "MB/s", "cores": threads, "kind": kind,
+                         "sample": "%d MB of the workload per step, lbzip2 -%d -n%d from /dev/shm to /dev/null" % (len(sample) // MB, a.level, threads)
+                         if binp else "10 MB of the workload, scalar oracle port"},
+        "e2e": {"value": round(val, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------ our arm ---
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import lbzip2_b200
+    from lbzip2_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no GPU visible; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    level, mbs = a.level, a.level * 100000
+    nbytes = a.size_mb * MB
+    nchunks = (nbytes + mbs - 1) // mbs
+    data = make_input(a.workload, nbytes, rank)
+    eng = lbzip2_b200.Engine(device=local, level=level, max_chunks=nchunks)
+    L = eng.L
+    cap = L.lbz_bound(nbytes) + 64
+
+    # pinned host buffers for the e2e leg
+    h_in = L.lbz_host_alloc(nbytes)
+    h_out = L.lbz_host_alloc(cap)
+    C.memmove(h_in, data, nbytes)
+    # HBM-resident buffers for the kernel-throughput leg
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(recs, payload_dev):
+        """NCCL gather of the block bitstreams into stream order on rank 0."""
+        if world == 1:
+            return None
+        table = sharding.block_table(recs, mbs)
+        return sharding.gather_blocks(table, payload_dev, dist, dev)
+
+    def step_device():
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        n_out, recs = eng.compress_chunks_ptr(d_in.data_ptr(), nbytes, d_out.data_ptr(), cap, device=True)
+        g = gather(recs, d_out[:n_out])
+        ev1.record()
+        ev1.synchronize()
+        return ev0.elapsed_time(ev1), eng.last_ms, n_out, recs, g
+
+    def step_host():
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        n_out, recs = eng.compress_chunks_ptr(h_in, nbytes, h_out, cap, device=False)
+        g = None
+        if world > 1:
+            pay = torch.frombuffer((C.c_uint8 * n_out).from_address(h_out), dtype=torch.uint8).to(dev, non_blocking=True)
+            g = gather(recs, pay)
+        ev1.record()
+        ev1.synchronize()
+        return ev0.elapsed_time(ev1), eng.last_ms, n_out, recs, g
+
+    def timed(fn):
+        for _ in range(a.warmup):
+            fn()
+        sampler = ClockSampler(local)
+        barrier()
+        l0 = eng.launches
+        if rank == 0:
+            sampler.start()
+        t0 = time.perf_counter()
+        ms, eng_ms, stage, k0 = [], [], {}, [0.0, 0, 0]
+        last = None
+        for _ in range(a.steps):
+            last = fn()
+            ms.append(last[0])
+            eng_ms.append(last[1])
+            for k, v in eng.stage_ms().items():
+                stage[k] = stage.get(k, 0.0) + v
+            s = eng.k0_stats()
+            k0[0] += s[0]; k0[1] += s[1]; k0[2] = s[2]
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop() if rank == 0 else None
+        tot = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return dict(total_ms=float(tot.item()), wall_ms=wall, launches=eng.launches - l0, stage=stage, k0=k0,
+                    clocks=clocks, last=last, eng_ms=sum(eng_ms))
+
+    rd = timed(step_device)
+    rh = timed(step_host)
+
+    # ---- correctness of what was timed (outside the timed region) -------------------
+    n_out, recs = rd["last"][2], rd["last"][3]
+    verified = {}
+    if rank == 0 and not a.no_verify:
+        import bz2
+        if world == 1:
+            body = d_out[:n_out].cpu().numpy().tobytes()
+            cc = 0
+            for r in recs:
+                cc = (((cc << 1) & 0xFFFFFFFF) ^ (cc >> 31) ^ r.crc ^ 0xFFFFFFFF) & 0xFFFFFFFF
+            stream = b"BZh" + bytes([48 + level]) + body + bytes([0x17, 0x72, 0x45, 0x38, 0x50, 0x90]) + cc.to_bytes(4, "big")
+            host_body = bytes((C.c_uint8 * rh["last"][2]).from_address(h_out))
+            verified["host_equals_device_path"] = host_body == body
+            verified["roundtrip"] = bz2.decompress(stream) == data
+            verified["sha256"] = hashlib.sha256(stream).hexdigest()
+        else:
+            tables, payloads = rd["last"][4]
+            stream = sharding.assemble_stream(level, tables, payloads, world)
+            verified["gathered_stream_decodes"] = len(bz2.decompress(stream)) == world * nbytes
+        verified["periodic_blocks"] = sum(1 for r in recs if r.tie_count > 1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = rd["total_ms"] / a.steps
+    value = world * nbytes / MB / (ms_step / 1e3)
+    ms_e2e = rh["total_ms"] / a.steps
+    e2e = world * nbytes / MB / (ms_e2e / 1e3)
+    hbm_peak, peak_kind = peaks()
+
+    # dominant kernel: one LSD pass of the initial rotation sort (k_scatter<text digit>):
+    # per element it reads a 4-byte index, gathers 1 text byte, writes a 4-byte index
+    k0_ms, k0_n, k0_elems = rd["k0"]
+    k0_avg_ms = k0_ms / max(k0_n, 1)
+    k0_bytes = 9.0 * k0_elems
+    k0_gbs = k0_bytes / (k0_avg_ms / 1e3) / 1e9 if k0_avg_ms > 0 else 0.0
+    # whole path: stage-interface model of SURVEY.md 8d: n + 13 n' + 20 nm + z per block
+    path_bytes = sum(r.raw_len + 13 * r.nblock + 20 * r.nmtf + r.out_len for r in recs)
+    path_gbs = path_bytes / (rd["eng_ms"] / a.steps / 1e3) / 1e9
+
+    stage = {k: round(v / a.steps, 3) for k, v in rd["stage"].items()}
+    line = {
+        "metric": "input MB/s at -9 (bit-exact .bz2)", "value": round(value, 2), "unit": "MB/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": ("%d MB enwik8-shaped synthetic text per GPU at -%d" % (a.size_mb, level)) if a.workload == "text"
+                   else "%d MB %s per GPU at -%d" % (a.size_mb, a.workload, level),
+                   "chunks_per_gpu": nchunks, "blocks": len(recs), "l2": "inputs (100 MB) and working set (>7 GB) larger than L2",
+                   "generator": "tests/synth.py seed 0x5EED, stream offset = rank",
+                   "gather": "NCCL gather of block bitstreams to rank 0" if world > 1 else "none (single GPU)"},
+        "e2e": {"value": round(e2e, 2), "unit": "MB/s", "ms_per_step": round(ms_e2e, 3),
+                "h2d_bytes_per_step": world * nbytes, "d2h_bytes_per_step": int(world * rh["last"][2]),
+                "api": "lbz_compress_chunks (pinned host in/out)"},
+        "gpu_launches": int(rd["launches"]),
+        "clocks": rd["clocks"],
+        "roofline": {"bound": "hbm", "kernel": "k_scatter<0> (one LSD pass of the rotation sort)",
+                     "achieved": round(k0_gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(k0_gbs / hbm_peak, 4),
+                     "traffic": None, "peak_kind": peak_kind,
+                     "bytes_per_launch": int(k0_bytes), "avg_launch_ms": round(k0_avg_ms, 4)},
+        "path_roofline": {"model": "n + 13n' + 20nm + z per block (SURVEY.md 8d)", "bytes_per_step": int(path_bytes),
+                          "achieved": round(path_gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(path_gbs / hbm_peak, 5)},
+        "stage_ms": stage, "sort_rounds": eng.last_rounds,
+        "wall_ms_per_step": round(rd["wall_ms"] / a.steps, 3), "verified": verified,
+        "compressed_ratio": round(nbytes / max(n_out, 1), 3),
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        binp = ref_binary()
+        sample = data if binp else data[: 10 * MB]
+        times, kind, sha = time_reference(sample, level, 3, 1, cores if binp else 1)
+        v = len(sample) / MB / (min(times) / 1e3)
+        line["cpu_baseline"] = {"value": round(v, 2), "unit": "MB/s", "cores": cores if binp else 1, "kind": kind,
+                                "sample": ("%d MB (the whole batch), lbzip2 -%d -n%d, /dev/shm -> /dev/null, best of 3" % (len(sample) // MB, level, cores))
+                                if binp else "10 MB of the batch, scalar oracle port"}
+        if binp and "sha256" in verified:
+            line["verified"]["bit_exact_vs_reference_cli"] = (sha == verified["sha256"])
+    print(json.dumps(line))
+    L.lbz_host_free(h_in)
+    L.lbz_host_free(h_out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -129,6 +129,14 @@ uint32_t lbz_engine_last_rounds(const lbz_engine *e);
 /* Bytes of device memory held by the engine. */
 size_t lbz_engine_device_bytes(const lbz_engine *e);
 const char *lbz_version(void);
+/* Device timing of the last lbz_compress_* call, from CUDA events recorded on the
+   engine's own stream: whole call; per stage {rle1, initial radix sort, doubling
+   rounds, last-column gather, mtf, huffman, pack+gather}; and the dominant kernel
+   (one LSD pass of the initial sort, k_scatter): summed launch time, launch count,
+   elements moved per launch. */
+double lbz_engine_last_ms(const lbz_engine *e);
+void lbz_engine_stage_ms(const lbz_engine *e, double *out7);
+void lbz_engine_k0_stats(const lbz_engine *e, double *sum_ms, uint32_t *launches, uint64_t *elements);
 
 /* ------------------------------------------------------------------------
  * 3. Stage hooks for the parity tests.  Slots: chunk c owns block slots 2c

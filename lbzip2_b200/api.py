@@ -46,6 +46,7 @@ EXPORTS = [
     "lbz_engine_create", "lbz_engine_destroy", "lbz_bound", "lbz_compress_chunks",
     "lbz_compress_chunks_device", "lbz_compress_stream", "lbz_host_alloc", "lbz_host_free",
     "lbz_engine_launches", "lbz_engine_last_rounds", "lbz_engine_device_bytes", "lbz_version",
+    "lbz_engine_last_ms", "lbz_engine_stage_ms", "lbz_engine_k0_stats",
     # stage hooks
     "lbz_dbg_load", "lbz_dbg_run", "lbz_dbg_read", "lbz_dbg_write", "lbz_dbg_num_slots",
     "lbz_dbg_set_chunks",
@@ -86,6 +87,12 @@ def load_library():
     L.lbz_engine_device_bytes.restype = C.c_size_t
     L.lbz_engine_device_bytes.argtypes = [vp]
     L.lbz_version.restype = C.c_char_p
+    L.lbz_engine_last_ms.restype = C.c_double
+    L.lbz_engine_last_ms.argtypes = [vp]
+    L.lbz_engine_stage_ms.restype = None
+    L.lbz_engine_stage_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    L.lbz_engine_k0_stats.restype = None
+    L.lbz_engine_k0_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.lbz_dbg_load.restype = C.c_int
     L.lbz_dbg_load.argtypes = [vp, vp, C.c_size_t]
     L.lbz_dbg_run.restype = C.c_int
@@ -184,6 +191,20 @@ class Engine:
     @property
     def launches(self):
         return self.L.lbz_engine_launches(self.h)
+
+    @property
+    def last_ms(self):
+        return self.L.lbz_engine_last_ms(self.h)
+
+    def stage_ms(self):
+        a = (C.c_double * 7)()
+        self.L.lbz_engine_stage_ms(self.h, a)
+        return dict(zip(("rle1", "sort_initial", "sort_refine", "bwt_gather", "mtf", "huffman", "pack"), list(a)))
+
+    def k0_stats(self):
+        ms, nl, ne = C.c_double(0), C.c_uint32(0), C.c_uint64(0)
+        self.L.lbz_engine_k0_stats(self.h, C.byref(ms), C.byref(nl), C.byref(ne))
+        return ms.value, nl.value, ne.value
 
     @property
     def last_rounds(self):

@@ -420,7 +420,8 @@ __global__ void k_zero2(uint32_t *c) { c[0] = 0; c[1] = 0; }
 // ---------------------------------------------------------------------------
 // Host driver.  `h_counters` is pinned host memory for the per-round readback.
 extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B,
-                           uint32_t *h_counters, uint32_t *rounds_out, uint64_t *launches, cudaStream_t st) {
+                           uint32_t *h_counters, uint32_t *rounds_out, uint64_t *launches,
+                           const LbzTimers *tm, cudaStream_t st) {
   uint64_t nl = 0;
   const LbzGeom g = *gp;
   const uint32_t nb = 2 * g.nchunks;
@@ -435,8 +436,10 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   for (int d = (int)BWT_K - 1; d >= 0; d--) {
     k_hist<0><<<grid_full, SORT_THREADS, 0, st>>>(g, d_meta, B.T, src, nullptr, B.hist, (uint32_t)d);
     k_scan<0><<<nb, 256, 0, st>>>(g, d_meta, B.hist, B.digit_base);
+    if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * d], st);
     k_scatter<0><<<grid_full, SORT_THREADS, 0, st>>>(g, d_meta, B.T, src, dst, nullptr, nullptr,
                                                        B.hist, B.digit_base, (uint32_t)d);
+    if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * d + 1], st);
     uint32_t *t = src; src = dst; dst = t;
   }
   // BWT_K is even, so the order is back in B.sa
@@ -444,6 +447,7 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   k_heads_initial<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.head);
   k_block_ranks<<<nb, STREAM_THREADS, 0, st>>>(g, d_meta, B);
   LBZ_CUDA_CHECK(cudaGetLastError());
+  if (tm && tm->enabled) cudaEventRecord(tm->stage[2], st);
 
   uint32_t rounds = 0;
   uint32_t h = BWT_K;
@@ -477,6 +481,7 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     h *= 2;
     LBZ_CUDA_CHECK(cudaGetLastError());
   }
+  if (tm && tm->enabled) cudaEventRecord(tm->stage[3], st);
   k_bwt_final<<<grid_full, 256, 0, st>>>(g, d_meta, B);
   LBZ_CUDA_CHECK(cudaGetLastError());
   nl += 1;

@@ -31,7 +31,7 @@ extern "C" {
 int lbz_launch_rle1(const LbzGeom *g, const uint8_t *d_in, const uint32_t *d_chunk_len, uint8_t *d_T,
                     LbzBlockMeta *d_meta, cudaStream_t st);
 int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B, uint32_t *h_counters,
-                uint32_t *rounds_out, uint64_t *launches, cudaStream_t st);
+                uint32_t *rounds_out, uint64_t *launches, const LbzTimers *tm, cudaStream_t st);
 int lbz_launch_mtf(const LbzGeom *g, LbzBlockMeta *d_meta, const uint8_t *d_bwt, uint8_t *d_mtfrank,
                    uint16_t *d_mtfv, uint32_t *d_freq, cudaStream_t st);
 int lbz_launch_huffman(const LbzGeom *g, LbzBlockMeta *d_meta, uint16_t *d_mtfv, const uint32_t *d_freq,
@@ -49,6 +49,13 @@ struct lbz_engine {
   size_t dev_bytes = 0;
   uint64_t launches = 0;
   uint32_t last_rounds = 0;
+  LbzTimers tm{};
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};
+  double last_ms = 0.0;                 // device time of the last compress call (all batches)
+  double stage_ms[LBZ_NSTAGE] = {};     // accumulated over the last call
+  double k0_ms = 0.0;                   // dominant kernel: summed launch time, last call
+  uint32_t k0_launches = 0;
+  uint64_t k0_elements = 0;             // elements sorted per launch (sum over blocks), last batch
   // device
   uint8_t *d_in = nullptr;     // max_chunks * mbs raw bytes
   uint32_t *d_chunk_len = nullptr;
@@ -137,6 +144,11 @@ extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) 
   const size_t NB = 2 * (size_t)e->max_chunks;
   int rc = 0;
   rc |= cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess;
+  for (int i = 0; i <= LBZ_NSTAGE; i++) rc |= cudaEventCreate(&e->tm.stage[i]) != cudaSuccess;
+  for (int i = 0; i < 2 * LBZ_NK0; i++) rc |= cudaEventCreate(&e->tm.k0[i]) != cudaSuccess;
+  rc |= cudaEventCreate(&e->ev_call[0]) != cudaSuccess;
+  rc |= cudaEventCreate(&e->ev_call[1]) != cudaSuccess;
+  e->tm.enabled = 1;
   rc |= dev_alloc(e, &e->d_in, (size_t)e->max_chunks * g.mbs);
   rc |= dev_alloc(e, &e->d_chunk_len, e->max_chunks);
   rc |= dev_alloc(e, &e->d_T, E);
@@ -182,6 +194,9 @@ extern "C" void lbz_engine_destroy(lbz_engine *e) {
   cudaSetDevice(e->device);
   if (e->st) { cudaStreamSynchronize(e->st); cudaStreamDestroy(e->st); }
   for (void *p : e->allocs) cudaFree(p);
+  for (int i = 0; i <= LBZ_NSTAGE; i++) if (e->tm.stage[i]) cudaEventDestroy(e->tm.stage[i]);
+  for (int i = 0; i < 2 * LBZ_NK0; i++) if (e->tm.k0[i]) cudaEventDestroy(e->tm.k0[i]);
+  for (int i = 0; i < 2; i++) if (e->ev_call[i]) cudaEventDestroy(e->ev_call[i]);
   if (e->h_chunk_len) cudaFreeHost(e->h_chunk_len);
   if (e->h_meta) cudaFreeHost(e->h_meta);
   if (e->h_counters) cudaFreeHost(e->h_counters);
@@ -196,6 +211,11 @@ extern "C" void *lbz_host_alloc(size_t bytes) {
 extern "C" void lbz_host_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" uint64_t lbz_engine_launches(const lbz_engine *e) { return e->launches; }
 extern "C" uint32_t lbz_engine_last_rounds(const lbz_engine *e) { return e->last_rounds; }
+extern "C" double lbz_engine_last_ms(const lbz_engine *e) { return e->last_ms; }
+extern "C" void lbz_engine_stage_ms(const lbz_engine *e, double *out7) { for (int i = 0; i < 7; i++) out7[i] = e->stage_ms[i]; }
+extern "C" void lbz_engine_k0_stats(const lbz_engine *e, double *sum_ms, uint32_t *launches, uint64_t *elements) {
+  *sum_ms = e->k0_ms; *launches = e->k0_launches; *elements = e->k0_elements;
+}
 extern "C" size_t lbz_engine_device_bytes(const lbz_engine *e) { return e->dev_bytes; }
 extern "C" uint32_t lbz_dbg_num_slots(const lbz_engine *e) { return 2 * e->g.nchunks; }
 extern "C" int lbz_dbg_set_chunks(lbz_engine *e, uint32_t nchunks) {
@@ -235,7 +255,7 @@ static int run_stage(lbz_engine *e, int stage, const uint8_t *d_in, uint8_t *d_p
       e->launches += 1;
       return lbz_launch_rle1(g, d_in, e->d_chunk_len, e->d_T, e->d_meta, e->st);
     case LBZ_ST_BWT:
-      return lbz_run_bwt(g, e->d_meta, bwt_buffers(e), e->h_counters, &e->last_rounds, &e->launches, e->st);
+      return lbz_run_bwt(g, e->d_meta, bwt_buffers(e), e->h_counters, &e->last_rounds, &e->launches, &e->tm, e->st);
     case LBZ_ST_MTF:
       e->launches += 2;
       return lbz_launch_mtf(g, e->d_meta, e->d_bwt, e->d_mtfrank, e->d_mtfv, e->d_freq, e->st);
@@ -257,11 +277,27 @@ static int run_pipeline(lbz_engine *e, const uint8_t *d_in, uint8_t *d_packed, s
   const uint32_t nb = 2 * e->g.nchunks;
   *total = 0;
   if (nb == 0) return 0;
-  for (int s = LBZ_ST_RLE1; s <= LBZ_ST_PACK; s++)
+  // stage boundaries: [0] start, [1] after rle1, [2] after initial sort, [3] after refinement,
+  // [4] after last-column gather, [5] after mtf, [6] after huffman, [7] after pack+gather
+  static const int after[5] = {1, 4, 5, 6, 7};
+  cudaEventRecord(e->tm.stage[0], e->st);
+  for (int s = LBZ_ST_RLE1; s <= LBZ_ST_PACK; s++) {
     if (run_stage(e, s, d_in, d_packed)) return -1;
+    cudaEventRecord(e->tm.stage[after[s]], e->st);
+  }
   ENG_CHECK(cudaMemcpyAsync(e->h_meta, e->d_meta, nb * sizeof(LbzBlockMeta), cudaMemcpyDeviceToHost, e->st));
   ENG_CHECK(cudaMemcpyAsync(e->h_counters + 2, e->d_counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->st));
   ENG_CHECK(cudaStreamSynchronize(e->st));
+  for (int i = 0; i < 7; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->tm.stage[i], e->tm.stage[i + 1]) == cudaSuccess) e->stage_ms[i] += ms;
+  }
+  for (int i = 0; i < LBZ_NK0; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->tm.k0[2 * i], e->tm.k0[2 * i + 1]) == cudaSuccess) { e->k0_ms += ms; e->k0_launches++; }
+  }
+  e->k0_elements = 0;
+  for (uint32_t b = 0; b < nb; b++) e->k0_elements += e->h_meta[b].n;
   size_t sum = 0;
   for (uint32_t b = 0; b < nb; b++) {
     const LbzBlockMeta &m = e->h_meta[b];
@@ -279,6 +315,19 @@ static int run_pipeline(lbz_engine *e, const uint8_t *d_in, uint8_t *d_packed, s
   }
   *total = sum;
   return 0;
+}
+
+static void call_begin(lbz_engine *e) {
+  for (int i = 0; i < LBZ_NSTAGE; i++) e->stage_ms[i] = 0.0;
+  e->k0_ms = 0.0; e->k0_launches = 0;
+  cudaEventRecord(e->ev_call[0], e->st);
+}
+static void call_end(lbz_engine *e) {
+  cudaEventRecord(e->ev_call[1], e->st);
+  cudaEventSynchronize(e->ev_call[1]);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e->ev_call[0], e->ev_call[1]);
+  e->last_ms = ms;
 }
 
 static size_t fill_recs(lbz_engine *e, uint64_t raw_base, lbz_block_rec *recs, size_t max_recs, size_t have) {
@@ -306,6 +355,7 @@ extern "C" int lbz_compress_chunks(lbz_engine *e, const uint8_t *in, size_t n, u
   ENG_CHECK(cudaSetDevice(e->device));
   const size_t batch_bytes = (size_t)e->max_chunks * e->g.mbs;
   size_t o = 0, nrec = 0;
+  call_begin(e);
   for (size_t pos = 0; pos < n; pos += batch_bytes) {
     const size_t len = (n - pos < batch_bytes) ? n - pos : batch_bytes;
     if (set_chunks(e, len)) return -1;
@@ -318,6 +368,7 @@ extern "C" int lbz_compress_chunks(lbz_engine *e, const uint8_t *in, size_t n, u
     nrec = fill_recs(e, pos, recs, max_recs, nrec);
     o += total;
   }
+  call_end(e);
   if (out_len) *out_len = o;
   if (num_recs) *num_recs = nrec;
   return 0;
@@ -330,7 +381,9 @@ extern "C" int lbz_compress_chunks_device(lbz_engine *e, const void *d_in, size_
   if (set_chunks(e, n)) return -1;
   if (out_cap < lbz_bound(n)) { fprintf(stderr, "lbzip2_b200: device output buffer too small\n"); return -2; }
   size_t total;
+  call_begin(e);
   if (run_pipeline(e, reinterpret_cast<const uint8_t *>(d_in), reinterpret_cast<uint8_t *>(d_out), &total)) return -1;
+  call_end(e);
   const size_t nrec = fill_recs(e, 0, recs, max_recs, 0);
   if (out_len) *out_len = total;
   if (num_recs) *num_recs = nrec;

@@ -66,6 +66,15 @@ struct LbzCoding {
   uint8_t selector_mtf[18008];             // incl. the optional padding selector
 };
 
+// Device-side timers (CUDA events on the engine's stream).
+#define LBZ_NSTAGE 8     // rle1, sort8 (initial radix), refine (doubling rounds), bwt_final, mtf, huffman, pack, copy
+#define LBZ_NK0 8        // launches of the dominant kernel (k_scatter<0>) per batch
+struct LbzTimers {
+  cudaEvent_t stage[LBZ_NSTAGE + 1];
+  cudaEvent_t k0[2 * LBZ_NK0];
+  int enabled;
+};
+
 #define LBZ_CUDA_CHECK(x)                                                        \
   do {                                                                           \
     cudaError_t e_ = (x);                                                        \
