@@ -343,3 +343,24 @@ def test_divbwt_entry_point():
     idx = L.divbwt(t2, sa, None, blk.size)
     assert idx == st["bwt_idx"]
     assert np.array_equal(np.array(sa[: blk.size], dtype=np.uint8), st["bwt"])
+
+
+# ------------------------------------------- the unmodified reference CLI as driver ---
+def test_reference_cli_drives_the_gpu_engine():
+    """oracle/_ref/lbzip2_gpu = the reference's main.c/process.c/compress.c/... linked
+    against libbz2b200.so instead of src/encode.c + src/divbwt.c (oracle/Makefile).
+    Its output must be byte-identical to the all-CPU reference binary's."""
+    import os
+    import subprocess
+    gpu_cli = os.path.join(orclib.REF_DIR, "lbzip2_gpu")
+    cpu_cli = os.path.join(orclib.REF_DIR, "lbzip2")
+    if not (os.path.exists(gpu_cli) and os.path.exists(cpu_cli)):
+        pytest.skip("oracle/_ref binaries not present")
+    data = synth.text(2_300_000, offset=12) + b"\0" * 1_000_000 + synth.random_bytes(400_000, seed=12)
+    for lv, nthreads in ((9, 6), (1, 12)):
+        env = dict(os.environ, LBZIP2_B200_CONTEXTS="16")
+        got = subprocess.run([gpu_cli, "-%d" % lv, "-n%d" % nthreads], input=data, stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, env=env, timeout=300)
+        assert got.returncode == 0 and got.stderr == b"", got.stderr[-500:]
+        want = subprocess.run([cpu_cli, "-%d" % lv], input=data, stdout=subprocess.PIPE, check=True).stdout
+        assert got.stdout == want
