@@ -80,16 +80,21 @@ k_hist(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restri
   sh[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uint32_t dg[SORT_ITEMS];
 #pragma unroll
   for (int it = 0; it < SORT_ITEMS; it++) {
     const uint32_t idx = tbase + warp * (32 * SORT_ITEMS) + it * 32 + lane;
-    if (idx < cnt) {
-      uint32_t digit;
-      if (MODE == 0) digit = T[off + wrap_add(src_val[off + idx], dsh, n)];
-      else digit = (uint32_t)(src_key[off + idx] >> dsh) & 0xFFu;
-      atomicAdd(&sh[digit], 1u);
-    }
+    dg[it] = 0xFFFFFFFFu;
+    if (idx < cnt) dg[it] = (MODE == 0) ? src_val[off + idx] : ((uint32_t)(src_key[off + idx] >> dsh) & 0xFFu);
   }
+  if (MODE == 0) {
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; it++)
+      if (dg[it] != 0xFFFFFFFFu) dg[it] = T[off + wrap_add(dg[it], dsh, n)];
+  }
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; it++)
+    if (dg[it] != 0xFFFFFFFFu) atomicAdd(&sh[dg[it]], 1u);
   __syncthreads();
   hist[((size_t)b * g.tiles1 + tile) * 256 + threadIdx.x] = sh[threadIdx.x];
 }
@@ -141,24 +146,37 @@ k_scatter(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__res
   uint32_t rd[SORT_ITEMS];     // rank within warp strip | digit << 16 | valid << 31
   uint64_t key[MODE == 1 ? SORT_ITEMS : 1];
 
+  // Phase 1: all independent loads first (16 in flight per thread), then all
+  // dependent text gathers, and only then the shared-memory ranking, so that
+  // the two global latencies are paid once per tile instead of once per item.
 #pragma unroll
   for (int it = 0; it < SORT_ITEMS; it++) {
     const uint32_t idx = tbase + warp * (32 * SORT_ITEMS) + it * 32 + lane;
     const bool valid = idx < cnt;
+    val[it] = valid ? src_val[off + idx] : 0u;
+    if (MODE == 1) key[it] = valid ? src_key[off + idx] : 0ull;
+    rd[it] = valid ? 0x80000000u : 0u;
+  }
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; it++) {
     uint32_t digit = 0x100u;                   // invalid lanes form their own match group
-    val[it] = 0;
-    if (valid) {
-      val[it] = src_val[off + idx];
+    if (rd[it]) {
       if (MODE == 0) digit = T[off + wrap_add(val[it], dsh, n)];
-      else { key[it] = src_key[off + idx]; digit = (uint32_t)(key[it] >> dsh) & 0xFFu; }
+      else digit = (uint32_t)(key[it] >> dsh) & 0xFFu;
     }
+    rd[it] |= digit << 16;
+  }
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; it++) {
+    const bool valid = (rd[it] & 0x80000000u) != 0;
+    const uint32_t digit = (rd[it] >> 16) & 0x1FFu;
     const uint32_t mask = __match_any_sync(0xffffffffu, digit);
     uint32_t base = 0;
     if (valid) base = wcnt[warp][digit];
     __syncwarp();
     if (valid && (mask & lt) == 0) wcnt[warp][digit] = base + __popc(mask);   // group leader
     __syncwarp();
-    rd[it] = (base + __popc(mask & lt)) | (digit << 16) | (valid ? 0x80000000u : 0u);
+    rd[it] |= base + __popc(mask & lt);
   }
   __syncthreads();
   {
@@ -185,103 +203,157 @@ k_scatter(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__res
 
 // ---------------------------------------------------------------------------
 // Group heads after the initial sort: head[p] = first BWT_K bytes of rotation
-// sa[p] differ from those of sa[p-1].
+// sa[p] differ from those of sa[p-1].  Keys are only compared for equality, so
+// the 8 bytes are fetched as three aligned words and funnel-shifted.
 __device__ __forceinline__ uint64_t text_key(const uint8_t *__restrict__ Tb, uint32_t v, uint32_t n) {
-  uint64_t k = 0;
   if (v + BWT_K <= n) {
-#pragma unroll
-    for (uint32_t d = 0; d < BWT_K; d++) k = (k << 8) | Tb[v + d];
-  } else {
-    uint32_t j = v;
-#pragma unroll
-    for (uint32_t d = 0; d < BWT_K; d++) { k = (k << 8) | Tb[j]; if (++j >= n) j = 0; }
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(Tb + (v & ~3u));
+    const uint32_t sh = 8u * (v & 3u);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];      // slot capacity >= n + 64: in bounds
+    const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+    return ((uint64_t)x1 << 32) | x0;
   }
+  uint64_t k = 0;
+  uint32_t j = v;
+#pragma unroll
+  for (uint32_t d = 0; d < BWT_K; d++) { k |= (uint64_t)Tb[j] << (8 * d); if (++j >= n) j = 0; }
   return k;
 }
 
+struct TileAgg { uint32_t count; int last; };
+
+// Tile-parallel pass A: head flags of a tile, number of rotations still tied,
+// last head position.  Per-tile aggregates replace a serial scan: pass B sums
+// the (<= 220) aggregates of the preceding tiles of its block itself.
 __global__ void __launch_bounds__(256)
-k_heads_initial(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
-                const uint32_t *__restrict__ sa, uint8_t *__restrict__ head) {
-  const uint32_t b = blockIdx.y;
+k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+            const uint32_t *__restrict__ sa, uint8_t *__restrict__ head, TileAgg *__restrict__ agg) {
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
   const uint32_t n = meta[b].n;
-  const uint32_t tbase = blockIdx.x * LBZ_TILE;
+  const uint32_t tbase = tile * LBZ_TILE;
   if (tbase >= n) return;
   const uint32_t off = lbz_slot_off(g, b);
   const uint8_t *Tb = T + off;
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  __shared__ __align__(16) uint8_t sflag[LBZ_TILE + 32];
+  __shared__ uint32_t ws[40];
+  __shared__ int wsi[40];
 #pragma unroll 2
-  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {   // uniform trip count: shuffles stay converged
-    const uint32_t p = tbase + it * 256 + threadIdx.x;
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {     // uniform trip count: shuffles stay converged
+    const uint32_t p = tbase + it * 256 + tid;
     const bool valid = p < n;
     uint64_t k = 0;
     if (valid) k = text_key(Tb, sa[off + p], n);
     uint64_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
     if (valid) {
       if (lane == 0) kprev = p ? text_key(Tb, sa[off + p - 1], n) : ~k;
-      head[off + p] = (p == 0) || (k != kprev);
+      sflag[p - tbase] = (p == 0) || (k != kprev);
+    } else if (p - tbase <= LBZ_TILE) {
+      sflag[p - tbase] = 1;                              // end of block acts as a head
     }
   }
+  if (tid == 0) {
+    const uint32_t pn = tbase + LBZ_TILE;
+    sflag[LBZ_TILE] = (pn < n) ? (text_key(Tb, sa[off + pn], n) != text_key(Tb, sa[off + pn - 1], n)) : 1;
+  }
+  __syncthreads();
+  const bool tracking = BWT_K < n;
+  const uint32_t q0 = tid * 16;
+  const uint4 fv = *reinterpret_cast<const uint4 *>(&sflag[q0]);
+  *reinterpret_cast<uint4 *>(&head[off + tbase + q0]) = fv;
+  uint32_t uns = 0;
+  int last = -1;
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const uint32_t p = tbase + q0 + j;
+    if (p < n) {
+      const bool f = sflag[q0 + j], f1 = sflag[q0 + j + 1];
+      if (f) last = (int)p;
+      uns += !(f && f1);
+    }
+  }
+  uint32_t tot;
+  int tmax;
+  (void)cta_excl_sum(uns, ws, &tot);
+  (void)cta_excl_max(last, -1, wsi, &tmax);
+  if (tid == 0) { TileAgg a; a.count = tracking ? tot : 0u; a.last = tmax; agg[(size_t)b * g.tiles1 + tile] = a; }
 }
 
-// ---------------------------------------------------------------------------
-// One CTA per block: turn head flags into ranks (rank[i] = first position of
-// i's group) and compact the members of tied groups into the round lists.
-__global__ void __launch_bounds__(STREAM_THREADS, 1)
-k_block_ranks(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B) {
-  const uint32_t b = blockIdx.x;
+// Tile-parallel pass B: ranks (rank[i] = first position of i's group) and
+// compaction of the members of tied groups into the round lists.
+__global__ void __launch_bounds__(256)
+k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const TileAgg *__restrict__ agg) {
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
   const uint32_t n = meta[b].n;
-  if (n == 0) { return; }
+  const uint32_t tbase = tile * LBZ_TILE;
+  if (tbase >= n) return;
   const uint32_t off = lbz_slot_off(g, b);
   const uint32_t tid = threadIdx.x;
-  const uint8_t *head = B.head + off;
-  const uint32_t *sa = B.sa + off;
-  const bool tracking = BWT_K < n;        // otherwise the order is already final
+  const bool tracking = BWT_K < n;
   __shared__ uint32_t ws[40];
   __shared__ int wsi[40];
-  int carry_start = 0;
-  uint32_t U = 0;
-  for (uint32_t base = 0; base < n; base += STREAM_THREADS * 4) {
-    const uint32_t p0 = base + tid * 4;
-    uint32_t h[5];
+  // carry from the preceding tiles of this block
+  uint32_t c = 0;
+  int l = -1;
+  for (uint32_t t = tid; t < tile; t += 256) {
+    const TileAgg a = agg[(size_t)b * g.tiles1 + t];
+    c += a.count; l = max(l, a.last);
+  }
+  uint32_t carry_cnt;
+  int carry_last;
+  (void)cta_excl_sum(c, ws, &carry_cnt);
+  (void)cta_excl_max(l, -1, wsi, &carry_last);
+
+  const uint32_t p0 = tbase + tid * 16;
+  uint8_t f[17];
+  {
+    const uint4 fv = *reinterpret_cast<const uint4 *>(&B.head[off + p0]);
+    const uint32_t wv[4] = {fv.x, fv.y, fv.z, fv.w};
 #pragma unroll
-    for (int j = 0; j < 5; j++) h[j] = (p0 + j < n) ? head[p0 + j] : 1u;
-    int last = -1;
+    for (int j = 0; j < 16; j++) f[j] = (p0 + j < n) ? (uint8_t)((wv[j >> 2] >> (8 * (j & 3))) & 0xFFu) : (uint8_t)1;
+    f[16] = (p0 + 16 < n) ? B.head[off + p0 + 16] : (uint8_t)1;
+  }
+  int last = -1;
 #pragma unroll
-    for (int j = 0; j < 4; j++) if (p0 + j < n && h[j]) last = (int)(p0 + j);
-    int tmax;
-    int st = cta_excl_max(last, -1, wsi, &tmax);
-    st = max(st, carry_start);
-    uint32_t starts[4];
-    uint32_t uns = 0;
+  for (int j = 0; j < 16; j++) if (p0 + j < n && f[j]) last = (int)(p0 + j);
+  int tmax;
+  int st = cta_excl_max(last, -1, wsi, &tmax);
+  st = max(st, carry_last);
+  uint32_t unsmask = 0;
+  uint32_t starts[16];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (p0 + j < n) {
-        if (h[j]) st = (int)(p0 + j);
-        starts[j] = (uint32_t)st;
-        const bool single = h[j] && h[j + 1];
-        if (tracking && !single) uns |= 1u << j;
-      }
+  for (int j = 0; j < 16; j++) {
+    if (p0 + j < n) {
+      if (f[j]) st = (int)(p0 + j);
+      starts[j] = (uint32_t)st;
+      if (tracking && !(f[j] && f[j + 1])) unsmask |= 1u << j;
     }
-    uint32_t tot;
-    uint32_t o = U + cta_excl_sum(__popc(uns), ws, &tot);
+  }
+  uint32_t tot;
+  uint32_t o = carry_cnt + cta_excl_sum(__popc(unsmask), ws, &tot);
+  if (p0 < n) {
+    uint32_t v[16];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int q = 0; q < 4; q++) {
+      const uint4 x = *reinterpret_cast<const uint4 *>(&B.sa[off + p0 + 4 * q]);   // slot capacity covers the overread
+      v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
       if (p0 + j < n) {
-        const uint32_t v = sa[p0 + j];
-        B.rank[off + v] = starts[j];
-        if (uns & (1u << j)) {
+        B.rank[off + v[j]] = starts[j];
+        if (unsmask & (1u << j)) {
           B.pos[off + o] = p0 + j;
-          B.val[off + o] = v;
+          B.val[off + o] = v[j];
           B.gs[off + o] = starts[j];
           o++;
         }
       }
     }
-    U += tot;
-    carry_start = max(carry_start, tmax);
   }
-  if (tid == 0) {
-    meta[b].unsorted = U;
+  if (tid == 0 && tbase + LBZ_TILE >= n) {               // last tile of the block
+    const uint32_t U = carry_cnt + tot;
+    meta[b].pad_[1] = U;                                  // committed by k_round_commit
     meta[b].depth = BWT_K;
     atomicMax(&B.counters[0], U);
     atomicAdd(&B.counters[1], U);
@@ -307,84 +379,130 @@ k_round_keys(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint32_t *_
   }
 }
 
-// One CTA per block: after the round sort, refine groups, write the order and
-// the new ranks back, and compact what is still tied for the next round.
-__global__ void __launch_bounds__(STREAM_THREADS, 1)
-k_round_update(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
-               const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval,
-               const uint32_t *__restrict__ pos, uint32_t *__restrict__ nval,
-               uint32_t *__restrict__ npos, uint32_t *__restrict__ ngs, uint32_t h) {
-  const uint32_t b = blockIdx.x;
+// After the round sort (tile-parallel, two passes like the initial ranks):
+// pass A counts, per tile of the sorted list, the elements that stay tied and
+// finds the last group head; pass B refines groups, writes order and ranks
+// back and compacts the survivors for the next round.
+__device__ __forceinline__ void load_round_keys(const uint64_t *__restrict__ skey, uint32_t off, uint32_t j0,
+                                                uint32_t U, uint64_t k[18]) {
+  // k[q] = key of list index j0 - 1 + q ; out of range = ~0 (never a real key: 40 bits)
+#pragma unroll
+  for (int q = 0; q < 18; q++) {
+    const int64_t j = (int64_t)j0 + q - 1;
+    k[q] = (j >= 0 && j < (int64_t)U) ? skey[off + j] : ~0ull;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_round_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__restrict__ skey,
+            TileAgg *__restrict__ agg, uint32_t h) {
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
   const uint32_t U = meta[b].unsorted;
-  if (U == 0) return;
+  const uint32_t tbase = tile * LBZ_TILE;
+  if (tbase >= U) return;
   const uint32_t n = meta[b].n;
   const uint32_t off = lbz_slot_off(g, b);
   const uint32_t tid = threadIdx.x;
-  const bool more = (2u * h < n);     // after this round the order is valid for 2h symbols
+  const bool more = (2u * h < n);
   __shared__ uint32_t ws[40];
   __shared__ int wsi[40];
-  int carry_j = -1;                   // list index of the last head seen so far
-  uint32_t carry_gs = 0;              // its SA position
-  uint32_t U2 = 0;
-  __shared__ uint32_t s_gs;
-  for (uint32_t base = 0; base < U; base += STREAM_THREADS * 2) {
-    const uint32_t j0 = base + tid * 2;
-    uint64_t k[4];                    // keys j0-1 .. j0+2
+  const uint32_t j0 = tbase + tid * 16;
+  uint64_t k[18];
+  load_round_keys(skey, off, j0, U, k);
+  uint32_t uns = 0;
+  int last = -1;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int64_t j = (int64_t)j0 + q - 1;
-      k[q] = (j >= 0 && j < (int64_t)U) ? skey[off + j] : ~0ull;
+  for (int q = 0; q < 16; q++) {
+    const uint32_t j = j0 + q;
+    if (j < U) {
+      const bool hd = (j == 0) || (k[q + 1] != k[q]);
+      const bool hn = (j + 1 >= U) || (k[q + 2] != k[q + 1]);
+      if (hd) last = (int)j;
+      uns += (more && !(hd && hn));
     }
-    bool hd[3];                       // head flags of j0, j0+1, j0+2
-    hd[0] = (j0 == 0) || (k[1] != k[0]);
-    hd[1] = (k[2] != k[1]);
-    hd[2] = (j0 + 2 >= U) || (k[3] != k[2]);
-    int last = -1;
-    if (j0 < U && hd[0]) last = (int)j0;
-    if (j0 + 1 < U && hd[1]) last = (int)(j0 + 1);
-    int tmax;
-    int st = cta_excl_max(last, -1, wsi, &tmax);
-    st = max(st, carry_j);
-    uint32_t myp[2], myv[2], mygs[2];
-    uint32_t uns = 0;
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const uint32_t j = j0 + q;
-      if (j < U) {
-        myp[q] = pos[off + j];
-        myv[q] = sval[off + j];
-        if (hd[q]) st = (int)j;
-        // group start = SA position of the group's head element
-        mygs[q] = ((uint32_t)st >= base) ? pos[off + (uint32_t)st] : carry_gs;
-        const bool single = hd[q] && hd[q + 1];
-        if (more && !single) uns |= 1u << q;
-      }
-    }
-    uint32_t tot;
-    uint32_t o = U2 + cta_excl_sum(__popc(uns), ws, &tot);
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const uint32_t j = j0 + q;
-      if (j < U) {
-        B.sa[off + myp[q]] = myv[q];
-        B.rank[off + myv[q]] = mygs[q];
-        if (uns & (1u << q)) {
-          npos[off + o] = myp[q];
-          nval[off + o] = myv[q];
-          ngs[off + o] = mygs[q];
-          o++;
-        }
-      }
-    }
-    U2 += tot;
-    // carry: SA position of the last head of this tile
-    __syncthreads();
-    if (tmax >= 0 && (uint32_t)tmax >= j0 && (uint32_t)tmax < j0 + 2) s_gs = pos[off + (uint32_t)tmax];
-    __syncthreads();
-    if (tmax >= (int)base) { carry_gs = s_gs; carry_j = tmax; }
   }
-  if (tid == 0) {
-    meta[b].unsorted = U2;
+  uint32_t tot;
+  int tmax;
+  (void)cta_excl_sum(uns, ws, &tot);
+  (void)cta_excl_max(last, -1, wsi, &tmax);
+  if (tid == 0) { TileAgg a; a.count = tot; a.last = tmax; agg[(size_t)b * g.tiles1 + tile] = a; }
+}
+
+__global__ void __launch_bounds__(256)
+k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
+              const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval,
+              const uint32_t *__restrict__ pos, uint32_t *__restrict__ nval,
+              uint32_t *__restrict__ npos, uint32_t *__restrict__ ngs,
+              const TileAgg *__restrict__ agg, uint32_t h) {
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
+  const uint32_t U = meta[b].unsorted;
+  const uint32_t tbase = tile * LBZ_TILE;
+  if (tbase >= U) return;
+  const uint32_t n = meta[b].n;
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint32_t tid = threadIdx.x;
+  const bool more = (2u * h < n);
+  __shared__ uint32_t ws[40];
+  __shared__ int wsi[40];
+  uint32_t c = 0;
+  int l = -1;
+  for (uint32_t t = tid; t < tile; t += 256) {
+    const TileAgg a = agg[(size_t)b * g.tiles1 + t];
+    c += a.count; l = max(l, a.last);
+  }
+  uint32_t carry_cnt;
+  int carry_last;
+  (void)cta_excl_sum(c, ws, &carry_cnt);
+  (void)cta_excl_max(l, -1, wsi, &carry_last);
+
+  const uint32_t j0 = tbase + tid * 16;
+  uint64_t k[18];
+  load_round_keys(skey, off, j0, U, k);
+  int last = -1;
+  uint32_t hdmask = 0;
+#pragma unroll
+  for (int q = 0; q < 17; q++) {
+    const uint32_t j = j0 + q;
+    const bool hd = (j >= U) || (j == 0) || (k[q + 1] != k[q]);
+    if (hd) hdmask |= 1u << q;
+    if (q < 16 && j < U && hd) last = (int)j;
+  }
+  int tmax;
+  int st = cta_excl_max(last, -1, wsi, &tmax);
+  st = max(st, carry_last);
+  uint32_t unsmask = 0;
+  uint32_t mygs[16], myp[16], myv[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const uint32_t j = j0 + q;
+    if (j < U) {
+      if (hdmask & (1u << q)) st = (int)j;
+      myp[q] = pos[off + j];
+      myv[q] = sval[off + j];
+      mygs[q] = pos[off + (uint32_t)st];                  // SA position of the group's head element
+      const bool single = (hdmask & (1u << q)) && (hdmask & (2u << q));
+      if (more && !single) unsmask |= 1u << q;
+    }
+  }
+  uint32_t tot;
+  uint32_t o = carry_cnt + cta_excl_sum(__popc(unsmask), ws, &tot);
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const uint32_t j = j0 + q;
+    if (j < U) {
+      B.sa[off + myp[q]] = myv[q];
+      B.rank[off + myv[q]] = mygs[q];
+      if (unsmask & (1u << q)) {
+        npos[off + o] = myp[q];
+        nval[off + o] = myv[q];
+        ngs[off + o] = mygs[q];
+        o++;
+      }
+    }
+  }
+  if (tid == 0 && tbase + LBZ_TILE >= U) {                // last tile of this block's list
+    const uint32_t U2 = carry_cnt + tot;
+    meta[b].pad_[1] = U2;                                  // committed by k_round_commit
     meta[b].depth = 2u * h;
     atomicMax(&B.counters[0], U2);
     atomicAdd(&B.counters[1], U2);
@@ -412,10 +530,17 @@ k_bwt_final(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B) {
 
 __global__ void k_bwt_prep(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, uint32_t *__restrict__ counters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nblocks) { meta[i].tie_count = 0; meta[i].unsorted = 0; }
+  if (i < nblocks) { meta[i].tie_count = 0; meta[i].unsorted = 0; meta[i].pad_[1] = 0; }
   if (i == 0) { counters[0] = 0; counters[1] = 0; }
 }
-__global__ void k_zero2(uint32_t *c) { c[0] = 0; c[1] = 0; }
+// Between rounds: the tied-set size written by the last tile of a block becomes
+// the segment size of the next round (kept apart so that no kernel reads and
+// writes meta.unsorted at the same time).
+__global__ void k_round_commit(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, uint32_t *__restrict__ counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nblocks) meta[i].unsorted = meta[i].pad_[1];
+  if (i == 0) { counters[0] = 0; counters[1] = 0; }
+}
 
 // ---------------------------------------------------------------------------
 // Host driver.  `h_counters` is pinned host memory for the per-round readback.
@@ -444,8 +569,9 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   }
   // BWT_K is even, so the order is back in B.sa
   B.sa = src; B.sa2 = dst;
-  k_heads_initial<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.head);
-  k_block_ranks<<<nb, STREAM_THREADS, 0, st>>>(g, d_meta, B);
+  TileAgg *agg = reinterpret_cast<TileAgg *>(B.hist);     // hist is free between radix passes
+  k_heads_agg<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.head, agg);
+  k_ranks_compact<<<grid_full, 256, 0, st>>>(g, d_meta, B, agg);
   LBZ_CUDA_CHECK(cudaGetLastError());
   if (tm && tm->enabled) cudaEventRecord(tm->stage[2], st);
 
@@ -461,9 +587,9 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     const uint32_t maxU = h_counters[0];
     if (maxU == 0) break;
     rounds++;
-    nl += 2 + 15 + 1;
+    nl += 2 + 15 + 2;
     const dim3 grid_u((maxU + LBZ_TILE - 1) / LBZ_TILE, nb);
-    k_zero2<<<1, 1, 0, st>>>(B.counters);
+    k_round_commit<<<(nb + 255) / 256, 256, 0, st>>>(d_meta, nb, B.counters);
     k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, h);
     for (uint32_t sh = 0; sh < 40; sh += 8) {
       k_hist<1><<<grid_u, SORT_THREADS, 0, st>>>(g, d_meta, nullptr, vsrc, ksrc, B.hist, sh);
@@ -474,7 +600,8 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
       uint32_t *tv = vsrc; vsrc = vdst; vdst = tv;
     }
     // sorted (key,val) now in ksrc/vsrc; compacted survivors go to vdst/pdst/gdst
-    k_round_update<<<nb, STREAM_THREADS, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, h);
+    k_round_agg<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h);
+    k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h);
     { uint32_t *t = vsrc; vsrc = vdst; vdst = t; }
     { uint32_t *t = psrc; psrc = pdst; pdst = t; }
     { uint32_t *t = gsrc; gsrc = gdst; gdst = t; }

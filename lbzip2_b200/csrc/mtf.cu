@@ -25,7 +25,8 @@
 
 #define MTF_THREADS 1024
 #define MTF_WARPS 32
-#define MTF_SEG 2048u                       // symbols per warp per super-tile
+#define MTF_SEG 1024u                       // symbols per warp per super-tile
+#define MTF_PARTS 8u                        // CTAs per block (each walks a contiguous range of super-tiles)
 #define MTF_SUPER (MTF_SEG * MTF_WARPS)
 
 __device__ __forceinline__ void cmpx_desc(uint32_t &a, uint32_t &b) {   // a >= b afterwards
@@ -33,12 +34,59 @@ __device__ __forceinline__ void cmpx_desc(uint32_t &a, uint32_t &b) {   // a >= 
   a = hi; b = lo;
 }
 
-__global__ void __launch_bounds__(MTF_THREADS, 1)
-k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ bwt,
-            uint8_t *__restrict__ mtfrank) {
-  const uint32_t b = blockIdx.x;
+__device__ __forceinline__ void mtf_part_range(uint32_t n, uint32_t part, uint32_t &lo, uint32_t &hi) {
+  const uint32_t nsuper = (n + MTF_SUPER - 1) / MTF_SUPER;
+  const uint32_t spp = (nsuper + MTF_PARTS - 1) / MTF_PARTS;
+  lo = min(part * spp * MTF_SUPER, n);
+  hi = min((part + 1) * spp * MTF_SUPER, n);
+}
+
+__device__ __forceinline__ uint32_t dense_of(const uint32_t *used, uint32_t v) {
+  uint32_t cnt = 0;
+  for (uint32_t w = 0; w < 8; w++) {
+    const uint32_t bits = used[w];
+    if (w < (v >> 5)) cnt += __popc(bits);
+    else if (w == (v >> 5)) cnt += __popc(bits & ((1u << (v & 31u)) - 1u));
+  }
+  return cnt;
+}
+
+// Last occurrence of every (dense) symbol inside each part of a block, so that
+// the MTF walk of part p can start from the recency order left by parts < p.
+__global__ void __launch_bounds__(MTF_THREADS)
+k_mtf_parttab(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ bwt,
+              int *__restrict__ parttab) {
+  const uint32_t b = blockIdx.y, part = blockIdx.x;
   const uint32_t n = meta[b].n;
   if (n == 0) return;
+  uint32_t lo, hi;
+  mtf_part_range(n, part, lo, hi);
+  const uint8_t *src = bwt + lbz_slot_off(g, b);
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  __shared__ int s_tab[256];
+  __shared__ uint8_t s_dense[256];
+  if (tid < 256) { s_tab[tid] = INT_MIN; s_dense[tid] = (uint8_t)dense_of(meta[b].used, tid); }
+  __syncthreads();
+  for (uint32_t base = lo; base < hi; base += MTF_THREADS) {      // uniform trip count per warp
+    const uint32_t p = base + tid;
+    const bool valid = p < hi;
+    const uint32_t c = valid ? s_dense[src[p]] : 0xFFFFu;
+    const uint32_t nc = __shfl_down_sync(0xffffffffu, c, 1);
+    if (valid && (lane == 31 || c != nc)) atomicMax(&s_tab[c], (int)p);
+  }
+  __syncthreads();
+  if (tid < 256) parttab[((size_t)b * MTF_PARTS + part) * 256 + tid] = s_tab[tid];
+}
+
+__global__ void __launch_bounds__(MTF_THREADS, 2)
+k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ bwt,
+            uint8_t *__restrict__ mtfrank, const int *__restrict__ parttab) {
+  const uint32_t b = blockIdx.y, part = blockIdx.x;
+  const uint32_t n = meta[b].n;
+  if (n == 0) return;
+  uint32_t part_lo, part_hi;
+  mtf_part_range(n, part, part_lo, part_hi);
+  if (part_lo >= part_hi) return;
   const uint32_t off = lbz_slot_off(g, b);
   const uint8_t *src = bwt + off;
   uint8_t *dstr = mtfrank + off;
@@ -57,21 +105,23 @@ k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
       else if (w == (tid >> 5)) cnt += __popc(bits & ((1u << (tid & 31u)) - 1u));
     }
     s_dense[tid] = (uint8_t)cnt;
-    s_carry[tid] = -1 - (int)tid;          // never seen: identity order
+    int cr = -1 - (int)tid;                // never seen: identity order
+    for (uint32_t q = 0; q < part; q++) cr = max(cr, parttab[((size_t)b * MTF_PARTS + q) * 256 + tid]);
+    s_carry[tid] = cr;
   }
 
-  for (uint32_t sbase = 0; sbase < n; sbase += MTF_SUPER) {
+  for (uint32_t sbase = part_lo; sbase < part_hi; sbase += MTF_SUPER) {
     __syncthreads();
     for (uint32_t i = tid; i < MTF_WARPS * 256; i += MTF_THREADS) (&s_tab[0][0])[i] = INT_MIN;
     __syncthreads();
     const uint32_t segbase = sbase + warp * MTF_SEG;
 
     // (A) last occurrence of every symbol inside this warp's segment
-    if (segbase < n) {
+    if (segbase < part_hi) {
       for (uint32_t q = 0; q < MTF_SEG / 32; q++) {
         const uint32_t p = segbase + q * 32 + lane;
-        if (segbase + q * 32 >= n) break;
-        const bool valid = p < n;
+        if (segbase + q * 32 >= part_hi) break;
+        const bool valid = p < part_hi;
         const uint32_t c = valid ? s_dense[src[p]] : 0xFFFFu;
         const uint32_t nc = __shfl_down_sync(0xffffffffu, c, 1);
         if (valid && (lane == 31 || c != nc)) atomicMax(&s_tab[warp][c], (int)p);
@@ -90,7 +140,7 @@ k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
       s_carry[tid] = run;
     }
     __syncthreads();
-    if (segbase >= n) continue;
+    if (segbase >= part_hi) continue;
 
     // (C) start list = symbols by descending last occurrence
     uint32_t e[8];
@@ -132,9 +182,9 @@ k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
     // walk the segment
     uint32_t prev_sym = segbase ? s_dense[src[segbase - 1]] : 0u;    // list front before the segment
     for (uint32_t q = 0; q < MTF_SEG / 32; q++) {
-      if (segbase + q * 32 >= n) break;
+      if (segbase + q * 32 >= part_hi) break;
       const uint32_t p = segbase + q * 32 + lane;
-      const bool valid = p < n;
+      const bool valid = p < part_hi;
       const uint32_t c = valid ? s_dense[src[p]] : 0xFFFFu;
       uint32_t pc = __shfl_up_sync(0xffffffffu, c, 1);
       if (lane == 0) pc = prev_sym;
@@ -295,11 +345,14 @@ k_mtf_emit(LbzGeom g, LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict
   if (tid == 0) { meta[b].nmtf = nm; meta[b].alpha_size = as; }
 }
 
+extern "C" uint32_t lbz_mtf_parts() { return MTF_PARTS; }
+
 extern "C" int lbz_launch_mtf(const LbzGeom *g, LbzBlockMeta *d_meta, const uint8_t *d_bwt, uint8_t *d_mtfrank,
-                              uint16_t *d_mtfv, uint32_t *d_freq, cudaStream_t st) {
+                              uint16_t *d_mtfv, uint32_t *d_freq, int *d_parttab, cudaStream_t st) {
   const uint32_t nb = 2 * g->nchunks;
   if (nb == 0) return 0;
-  k_mtf_ranks<<<nb, MTF_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank);
+  k_mtf_parttab<<<dim3(MTF_PARTS, nb), MTF_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_parttab);
+  k_mtf_ranks<<<dim3(MTF_PARTS, nb), MTF_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_parttab);
   k_mtf_emit<<<nb, EMIT_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_mtfv, d_freq);
   LBZ_CUDA_CHECK(cudaGetLastError());
   return 0;
