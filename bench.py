@@ -311,11 +311,11 @@ def run_ours(a):
     e2e = world * nbytes / MB / (ms_e2e / 1e3)
     hbm_peak, peak_kind = peaks()
 
-    # dominant kernel: one LSD pass of the initial rotation sort (k_scatter<text digit>):
-    # per element it reads a 4-byte index, gathers 1 text byte, writes a 4-byte index
+    # dominant kernel: one LSD pass of the initial rotation sort (k_radix_pass<u32>):
+    # per element it reads (4-byte index, 4-byte key) and writes them to their sorted place
     k0_ms, k0_n, k0_elems = rd["k0"]
     k0_avg_ms = k0_ms / max(k0_n, 1)
-    k0_bytes = 9.0 * k0_elems
+    k0_bytes = 16.0 * k0_elems
     k0_gbs = k0_bytes / (k0_avg_ms / 1e3) / 1e9 if k0_avg_ms > 0 else 0.0
     # whole path: stage-interface model of SURVEY.md 8d: n + 13 n' + 20 nm + z per block
     path_bytes = sum(r.raw_len + 13 * r.nblock + 20 * r.nmtf + r.out_len for r in recs)
@@ -336,7 +336,7 @@ def run_ours(a):
                 "api": "lbz_compress_chunks (pinned host in/out)"},
         "gpu_launches": int(rd["launches"]),
         "clocks": rd["clocks"],
-        "roofline": {"bound": "hbm", "kernel": "k_scatter<0> (one LSD pass of the rotation sort)",
+        "roofline": {"bound": "hbm", "kernel": "k_radix_pass<u32> (one LSD pass of the rotation sort, 8 per batch)",
                      "achieved": round(k0_gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(k0_gbs / hbm_peak, 4),
                      "traffic": None, "peak_kind": peak_kind,
                      "bytes_per_launch": int(k0_bytes), "avg_launch_ms": round(k0_avg_ms, 4)},

@@ -36,9 +36,12 @@ struct BwtBuffers {
   uint32_t *val, *val2;   // round payload = rotation index (ping/pong)
   uint32_t *pos, *pos2;   // SA position of each tied element (ping/pong)
   uint32_t *gs, *gs2;     // group start of each tied element (ping/pong)
-  uint32_t *hist;         // [(b*tiles1 + tile)*256 + digit]
-  uint32_t *digit_base;   // [b*256 + digit]
-  uint32_t *counters;     // [0] = max unsorted over blocks, [1] = total unsorted
+  uint32_t *tstat;        // chained-scan status words [(b*tiles1 + tile)*256 + digit]
+  uint32_t *gbase;        // digit bases: [b*256 + d] text passes, then [nb*256 + (b*5 + pass)*256 + d] key passes
+  uint32_t *khist;        // key-pass digit histograms [(b*5 + pass)*256 + d]
+  void *agg;              // per-tile aggregates of the rank/refine passes
+  uint32_t *counters;     // [0] = max unsorted over blocks, [1] = total unsorted, [3] = error flag
+  uint32_t *epoch;        // host-side pass counter (status-word epoch)
   uint8_t *bwt;           // output last column
 };
 
@@ -49,13 +52,28 @@ __device__ __forceinline__ uint32_t wrap_add(uint32_t v, uint32_t d, uint32_t n)
 }
 
 // ---------------------------------------------------------------------------
-__global__ void k_sa_init(LbzGeom g, const LbzBlockMeta *__restrict__ meta, uint32_t *__restrict__ sa) {
+// Identity order plus the key word of the first four passes: text bytes 4..7 of
+// every rotation (contiguous reads -- the order is still the identity).
+__global__ void k_sa_init(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+                          uint32_t *__restrict__ sa, uint32_t *__restrict__ key32) {
   const uint32_t b = blockIdx.y;
   const uint32_t n = meta[b].n;
   const uint32_t base = blockIdx.x * LBZ_TILE;
   if (base >= n) return;
-  uint32_t *p = sa + lbz_slot_off(g, b);
-  for (uint32_t i = base + threadIdx.x; i < min(base + LBZ_TILE, n); i += blockDim.x) p[i] = i;
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint8_t *Tb = T + off;
+  for (uint32_t i = base + threadIdx.x; i < min(base + LBZ_TILE, n); i += blockDim.x) {
+    sa[off + i] = i;
+    uint32_t k = 0;
+    if (i + 8 <= n) {
+      k = ((uint32_t)Tb[i + 4] << 24) | ((uint32_t)Tb[i + 5] << 16) | ((uint32_t)Tb[i + 6] << 8) | Tb[i + 7];
+    } else {
+      uint32_t j = (i + 4) % n;
+#pragma unroll
+      for (int d = 0; d < 4; d++) { k = (k << 8) | Tb[j]; if (++j >= n) j = 0; }
+    }
+    key32[off + i] = k;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -65,139 +83,207 @@ __global__ void k_sa_init(LbzGeom g, const LbzBlockMeta *__restrict__ meta, uint
 template <int MODE>
 __device__ __forceinline__ uint32_t seg_count(const LbzBlockMeta &m) { return MODE == 0 ? m.n : m.unsorted; }
 
-template <int MODE>
+// One counting-sort pass in ONE launch ("onesweep"): every tile ranks its items
+// per digit, publishes its per-digit counts and obtains its per-digit offset by
+// a decoupled look-back over the preceding tiles of the same block (chained
+// scan).  A status word carries flag (2 bits: 1 = tile aggregate, 2 = inclusive
+// prefix), a 10-bit epoch (pass counter, so the array never needs clearing
+// between passes) and a 20-bit count.  Tiles are dispatched in blockIdx.x order,
+// so a tile only ever waits for tiles that are already resident or finished.
+#define TS_FLAG_AGG 0x40000000u
+#define TS_FLAG_PREFIX 0x80000000u
+#define TS_EPOCH_MASK 0x3FF00000u
+#define TS_VALUE_MASK 0x000FFFFFu
+#define TS_SPIN_LIMIT (1u << 27)
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// K = key type carried with the rotation index (u32: four text bytes, u64: round
+// key).  COUNT_U: segment size = tied-set size (round passes) instead of n.
+// GATHER: the key is not read from src_key but fetched from the text: the four
+// leading bytes of rotation `val` (used once, by the 5th pass of the initial sort).
+template <typename K>
+struct RadixSmem {
+  K skey[LBZ_TILE];
+  uint32_t sval[LBZ_TILE];
+  uint32_t wcnt[SORT_WARPS][256];
+  uint32_t dstart[256];
+  uint32_t delta[256];
+  uint32_t ws[40];
+};
+
+__device__ __forceinline__ uint32_t text_key4(const uint8_t *__restrict__ Tb, uint32_t v, uint32_t n) {
+  if (v + 4 <= n) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(Tb + (v & ~3u));
+    const uint32_t x = __funnelshift_r(w[0], w[1], 8u * (v & 3u));   // bytes v..v+3, little endian
+    return __byte_perm(x, 0, 0x0123);                                // first byte most significant
+  }
+  uint32_t k = 0, j = v;
+#pragma unroll
+  for (int d = 0; d < 4; d++) { k = (k << 8) | Tb[j]; if (++j >= n) j = 0; }
+  return k;
+}
+
+template <typename K, int COUNT_U, int GATHER>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_hist(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
-       const uint32_t *__restrict__ src_val, const uint64_t *__restrict__ src_key,
-       uint32_t *__restrict__ hist, uint32_t dsh) {
+k_radix_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+             const uint32_t *__restrict__ src_val, uint32_t *__restrict__ dst_val,
+             const K *__restrict__ src_key, K *__restrict__ dst_key,
+             uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase, uint32_t gstride,
+             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err) {
+  extern __shared__ __align__(16) unsigned char radix_smem_raw[];
+  RadixSmem<K> &S = *reinterpret_cast<RadixSmem<K> *>(radix_smem_raw);
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
-  const uint32_t cnt = seg_count<MODE>(meta[b]);
+  const uint32_t cnt = COUNT_U ? meta[b].unsorted : meta[b].n;
   const uint32_t tbase = tile * LBZ_TILE;
   if (tbase >= cnt) return;
   const uint32_t n = meta[b].n;
   const uint32_t off = lbz_slot_off(g, b);
-  __shared__ uint32_t sh[256];
-  sh[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  uint32_t dg[SORT_ITEMS];
-#pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++) {
-    const uint32_t idx = tbase + warp * (32 * SORT_ITEMS) + it * 32 + lane;
-    dg[it] = 0xFFFFFFFFu;
-    if (idx < cnt) dg[it] = (MODE == 0) ? src_val[off + idx] : ((uint32_t)(src_key[off + idx] >> dsh) & 0xFFu);
-  }
-  if (MODE == 0) {
-#pragma unroll
-    for (int it = 0; it < SORT_ITEMS; it++)
-      if (dg[it] != 0xFFFFFFFFu) dg[it] = T[off + wrap_add(dg[it], dsh, n)];
-  }
-#pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++)
-    if (dg[it] != 0xFFFFFFFFu) atomicAdd(&sh[dg[it]], 1u);
-  __syncthreads();
-  hist[((size_t)b * g.tiles1 + tile) * 256 + threadIdx.x] = sh[threadIdx.x];
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256)
-k_scan(LbzGeom g, const LbzBlockMeta *__restrict__ meta, uint32_t *__restrict__ hist,
-       uint32_t *__restrict__ digit_base) {
-  const uint32_t b = blockIdx.x;
-  const uint32_t cnt = seg_count<MODE>(meta[b]);
-  if (cnt == 0) return;
-  const uint32_t ntiles = (cnt + LBZ_TILE - 1) / LBZ_TILE;
-  uint32_t *h = hist + (size_t)b * g.tiles1 * 256 + threadIdx.x;
-  uint32_t run = 0;
-  uint32_t t = 0;
-  for (; t + 4 <= ntiles; t += 4) {
-    const uint32_t a0 = h[(t + 0) * 256], a1 = h[(t + 1) * 256], a2 = h[(t + 2) * 256], a3 = h[(t + 3) * 256];
-    h[(t + 0) * 256] = run; run += a0;
-    h[(t + 1) * 256] = run; run += a1;
-    h[(t + 2) * 256] = run; run += a2;
-    h[(t + 3) * 256] = run; run += a3;
-  }
-  for (; t < ntiles; t++) { const uint32_t a = h[t * 256]; h[t * 256] = run; run += a; }
-  __shared__ uint32_t ws[40];
-  uint32_t total;
-  const uint32_t ex = cta_excl_sum(run, ws, &total);
-  digit_base[b * 256 + threadIdx.x] = ex;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(SORT_THREADS)
-k_scatter(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
-          const uint32_t *__restrict__ src_val, uint32_t *__restrict__ dst_val,
-          const uint64_t *__restrict__ src_key, uint64_t *__restrict__ dst_key,
-          const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_base, uint32_t dsh) {
-  const uint32_t b = blockIdx.y, tile = blockIdx.x;
-  const uint32_t cnt = seg_count<MODE>(meta[b]);
-  const uint32_t tbase = tile * LBZ_TILE;
-  if (tbase >= cnt) return;
-  const uint32_t n = meta[b].n;
-  const uint32_t off = lbz_slot_off(g, b);
-  __shared__ uint32_t wcnt[SORT_WARPS][256];
-  for (uint32_t i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+  const uint32_t tile_cnt = min(LBZ_TILE, cnt - tbase);
+  for (uint32_t i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&S.wcnt[0][0])[i] = 0;
   __syncthreads();
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t lt = lanemask_lt();
   uint32_t val[SORT_ITEMS];
   uint32_t rd[SORT_ITEMS];     // rank within warp strip | digit << 16 | valid << 31
-  uint64_t key[MODE == 1 ? SORT_ITEMS : 1];
+  K key[SORT_ITEMS];
 
-  // Phase 1: all independent loads first (16 in flight per thread), then all
-  // dependent text gathers, and only then the shared-memory ranking, so that
-  // the two global latencies are paid once per tile instead of once per item.
 #pragma unroll
   for (int it = 0; it < SORT_ITEMS; it++) {
     const uint32_t idx = tbase + warp * (32 * SORT_ITEMS) + it * 32 + lane;
     const bool valid = idx < cnt;
     val[it] = valid ? src_val[off + idx] : 0u;
-    if (MODE == 1) key[it] = valid ? src_key[off + idx] : 0ull;
+    if (!GATHER) key[it] = valid ? src_key[off + idx] : (K)0;
     rd[it] = valid ? 0x80000000u : 0u;
   }
+  if (GATHER) {
 #pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++) {
-    uint32_t digit = 0x100u;                   // invalid lanes form their own match group
-    if (rd[it]) {
-      if (MODE == 0) digit = T[off + wrap_add(val[it], dsh, n)];
-      else digit = (uint32_t)(key[it] >> dsh) & 0xFFu;
-    }
-    rd[it] |= digit << 16;
+    for (int it = 0; it < SORT_ITEMS; it++) key[it] = rd[it] ? (K)text_key4(T + off, val[it], n) : (K)0;
   }
 #pragma unroll
   for (int it = 0; it < SORT_ITEMS; it++) {
-    const bool valid = (rd[it] & 0x80000000u) != 0;
-    const uint32_t digit = (rd[it] >> 16) & 0x1FFu;
+    const bool valid = rd[it] != 0;
+    const uint32_t digit = valid ? ((uint32_t)(key[it] >> shift) & 0xFFu) : 0x100u;   // invalid lanes: own match group
     const uint32_t mask = __match_any_sync(0xffffffffu, digit);
     uint32_t base = 0;
-    if (valid) base = wcnt[warp][digit];
+    if (valid) base = S.wcnt[warp][digit];
     __syncwarp();
-    if (valid && (mask & lt) == 0) wcnt[warp][digit] = base + __popc(mask);   // group leader
+    if (valid && (mask & lt) == 0) S.wcnt[warp][digit] = base + __popc(mask);   // group leader
     __syncwarp();
-    rd[it] |= base + __popc(mask & lt);
+    rd[it] |= (digit << 16) | (base + __popc(mask & lt));
   }
   __syncthreads();
   {
     const uint32_t d = threadIdx.x;
-    uint32_t run = hist[((size_t)b * g.tiles1 + tile) * 256 + d] + digit_base[b * 256 + d];
+    uint32_t total = 0;
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; w++) {
-      const uint32_t c = wcnt[w][d];
-      wcnt[w][d] = run;
-      run += c;
+      const uint32_t c = S.wcnt[w][d];
+      S.wcnt[w][d] = total;
+      total += c;
     }
+    uint32_t *mine = tstat + ((size_t)b * g.tiles1 + tile) * 256 + d;
+    const uint32_t ep = (epoch << 20) & TS_EPOCH_MASK;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      st_volatile_u32(mine, TS_FLAG_PREFIX | ep | total);
+    } else {
+      st_volatile_u32(mine, TS_FLAG_AGG | ep | total);
+    }
+    uint32_t tsum;
+    const uint32_t dst0 = cta_excl_sum(total, S.ws, &tsum);      // start of digit d inside the tile
+    if (tile != 0) {
+      const uint32_t *look = mine - 256;
+      uint32_t spins = 0;
+      for (;;) {
+        const uint32_t sw = ld_volatile_u32(look);
+        if ((sw & TS_EPOCH_MASK) != ep || (sw >> 30) == 0u) {
+          if (++spins > TS_SPIN_LIMIT) { *err = 1u; break; }     // never expected: fail loudly on the host
+          continue;
+        }
+        excl += sw & TS_VALUE_MASK;
+        if (sw & TS_FLAG_PREFIX) break;
+        look -= 256;
+      }
+      st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total) & TS_VALUE_MASK));
+    }
+    S.dstart[d] = dst0;
+    S.delta[d] = gbase[(size_t)b * gstride + d] + excl - dst0;   // global index = delta[digit] + tile-local slot
   }
   __syncthreads();
+  // stage the tile in digit order, then write it out with consecutive threads
+  // on consecutive slots (runs of equal digits are contiguous in global memory)
 #pragma unroll
   for (int it = 0; it < SORT_ITEMS; it++) {
     if (rd[it] & 0x80000000u) {
       const uint32_t digit = (rd[it] >> 16) & 0xFFu;
-      const uint32_t dst = wcnt[warp][digit] + (rd[it] & 0xFFFFu);
-      dst_val[off + dst] = val[it];
-      if (MODE == 1) dst_key[off + dst] = key[it];
+      const uint32_t slot = S.dstart[digit] + S.wcnt[warp][digit] + (rd[it] & 0xFFFFu);
+      S.skey[slot] = key[it];
+      S.sval[slot] = val[it];
     }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < tile_cnt; i += SORT_THREADS) {
+    const K k = S.skey[i];
+    const uint32_t dst = S.delta[(uint32_t)(k >> shift) & 0xFFu] + i;
+    dst_key[off + dst] = k;
+    dst_val[off + dst] = S.sval[i];
+  }
+}
+
+// Digit bases of the text passes: every pass of the initial sort sees the same
+// multiset of digits (each rotation index occurs once, so the digits at any
+// depth are the bytes of the block), hence one byte histogram per block serves
+// all BWT_K passes.  One CTA per block.
+__global__ void __launch_bounds__(1024)
+k_text_bases(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+             uint32_t *__restrict__ gbase) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t n = meta[b].n;
+  if (n == 0) return;
+  const uint8_t *Tb = T + lbz_slot_off(g, b);
+  __shared__ uint32_t sh[256];
+  __shared__ uint32_t ws[40];
+  if (threadIdx.x < 256) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t nvec = n / 16;
+  for (uint32_t i = threadIdx.x; i < nvec; i += 1024) {
+    const uint4 v = reinterpret_cast<const uint4 *>(Tb)[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      atomicAdd(&sh[w[q] & 0xFFu], 1u); atomicAdd(&sh[(w[q] >> 8) & 0xFFu], 1u);
+      atomicAdd(&sh[(w[q] >> 16) & 0xFFu], 1u); atomicAdd(&sh[w[q] >> 24], 1u);
+    }
+  }
+  for (uint32_t i = nvec * 16 + threadIdx.x; i < n; i += 1024) atomicAdd(&sh[Tb[i]], 1u);
+  __syncthreads();
+  const uint32_t v = threadIdx.x < 256 ? sh[threadIdx.x] : 0u;
+  uint32_t tot;
+  const uint32_t ex = cta_excl_sum(v, ws, &tot);
+  if (threadIdx.x < 256) gbase[b * 256 + threadIdx.x] = ex;
+}
+
+// Digit bases of the five key passes of a round from the histograms that
+// k_round_keys accumulated.
+__global__ void __launch_bounds__(256)
+k_key_bases(const LbzBlockMeta *__restrict__ meta, const uint32_t *__restrict__ khist, uint32_t *__restrict__ gbase1) {
+  const uint32_t b = blockIdx.x;
+  if (meta[b].unsorted == 0) return;
+  __shared__ uint32_t ws[40];
+  for (uint32_t p = 0; p < 5; p++) {
+    const uint32_t v = khist[(b * 5 + p) * 256 + threadIdx.x];
+    uint32_t tot;
+    const uint32_t ex = cta_excl_sum(v, ws, &tot);
+    gbase1[(b * 5 + p) * 256 + threadIdx.x] = ex;
   }
 }
 
@@ -361,21 +447,46 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
 }
 
 // ---------------------------------------------------------------------------
-// Round key: (group start << 20) | rank of rotation (i + h).
+// Round key: (group start << 20) | rank of rotation (i + h); also accumulates
+// the digit histograms of the five radix passes that follow.
 __global__ void __launch_bounds__(256)
 k_round_keys(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint32_t *__restrict__ val,
              const uint32_t *__restrict__ gs, const uint32_t *__restrict__ rank,
-             uint64_t *__restrict__ key, uint32_t h) {
+             uint64_t *__restrict__ key, uint32_t *__restrict__ khist, uint32_t h) {
   const uint32_t b = blockIdx.y;
   const uint32_t U = meta[b].unsorted;
   const uint32_t tbase = blockIdx.x * LBZ_TILE;
   if (tbase >= U) return;
   const uint32_t n = meta[b].n;
   const uint32_t off = lbz_slot_off(g, b);
-  for (uint32_t j = tbase + threadIdx.x; j < min(tbase + LBZ_TILE, U); j += 256) {
-    const uint32_t v = val[off + j];
-    const uint32_t r = rank[off + wrap_add(v, h, n)];
-    key[off + j] = ((uint64_t)gs[off + j] << 20) | r;
+  __shared__ uint32_t sh[5][256];
+  for (uint32_t i = threadIdx.x; i < 5 * 256; i += 256) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  uint32_t v[LBZ_TILE / 256], gg[LBZ_TILE / 256];
+#pragma unroll
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
+    const uint32_t j = tbase + it * 256 + threadIdx.x;
+    v[it] = (j < U) ? val[off + j] : 0xFFFFFFFFu;
+    gg[it] = (j < U) ? gs[off + j] : 0u;
+  }
+#pragma unroll
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
+    if (v[it] != 0xFFFFFFFFu) v[it] = rank[off + wrap_add(v[it], h, n)];
+  }
+#pragma unroll
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
+    const uint32_t j = tbase + it * 256 + threadIdx.x;
+    if (j < U) {
+      const uint64_t k = ((uint64_t)gg[it] << 20) | v[it];
+      key[off + j] = k;
+#pragma unroll
+      for (int p = 0; p < 5; p++) atomicAdd(&sh[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < 5 * 256; i += 256) {
+    const uint32_t c = (&sh[0][0])[i];
+    if (c) atomicAdd(&khist[(size_t)b * 5 * 256 + i], c);
   }
 }
 
@@ -531,15 +642,28 @@ k_bwt_final(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B) {
 __global__ void k_bwt_prep(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, uint32_t *__restrict__ counters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nblocks) { meta[i].tie_count = 0; meta[i].unsorted = 0; meta[i].pad_[1] = 0; }
-  if (i == 0) { counters[0] = 0; counters[1] = 0; }
+  if (i == 0) { counters[0] = 0; counters[1] = 0; counters[3] = 0; }
 }
 // Between rounds: the tied-set size written by the last tile of a block becomes
 // the segment size of the next round (kept apart so that no kernel reads and
 // writes meta.unsorted at the same time).
-__global__ void k_round_commit(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, uint32_t *__restrict__ counters) {
+__global__ void k_round_commit(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, uint32_t *__restrict__ counters,
+                               uint32_t *__restrict__ khist) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nblocks) meta[i].unsorted = meta[i].pad_[1];
+  if (i < nblocks * 5 * 256) khist[i] = 0;
   if (i == 0) { counters[0] = 0; counters[1] = 0; }
+}
+
+// Status-word epoch: 1..1023, the status array is cleared when it wraps.
+static uint32_t next_epoch(const BwtBuffers &B, uint32_t nb, const LbzGeom &g, cudaStream_t st) {
+  uint32_t e = *B.epoch + 1;
+  if (e >= 1024) {
+    cudaMemsetAsync(B.tstat, 0, (size_t)nb * g.tiles1 * 256 * sizeof(uint32_t), st);
+    e = 1;
+  }
+  *B.epoch = e;
+  return e;
 }
 
 // ---------------------------------------------------------------------------
@@ -554,22 +678,34 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   const dim3 grid_full(g.tiles1, nb);
 
   k_bwt_prep<<<(nb + 255) / 256, 256, 0, st>>>(d_meta, nb, B.counters);
-  k_sa_init<<<grid_full, 256, 0, st>>>(g, d_meta, B.sa);
-  nl += 2 + 3 * BWT_K + 2;
+  uint32_t *k32a = reinterpret_cast<uint32_t *>(B.key), *k32b = reinterpret_cast<uint32_t *>(B.key2);
+  k_sa_init<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, k32a);
+  nl += 3 + BWT_K + 2;
+  const size_t smem32 = sizeof(RadixSmem<uint32_t>), smem64 = sizeof(RadixSmem<uint64_t>);
+  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<uint32_t, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<uint32_t, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<uint64_t, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
 
   uint32_t *src = B.sa, *dst = B.sa2;
-  for (int d = (int)BWT_K - 1; d >= 0; d--) {
-    k_hist<0><<<grid_full, SORT_THREADS, 0, st>>>(g, d_meta, B.T, src, nullptr, B.hist, (uint32_t)d);
-    k_scan<0><<<nb, 256, 0, st>>>(g, d_meta, B.hist, B.digit_base);
-    if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * d], st);
-    k_scatter<0><<<grid_full, SORT_THREADS, 0, st>>>(g, d_meta, B.T, src, dst, nullptr, nullptr,
-                                                       B.hist, B.digit_base, (uint32_t)d);
-    if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * d + 1], st);
-    uint32_t *t = src; src = dst; dst = t;
+  k_text_bases<<<nb, 1024, 0, st>>>(g, d_meta, B.T, B.gbase);
+  // LSD over text bytes 7..0 of every rotation: bytes 4..7 travel as a 32-bit key
+  // for the first four passes, bytes 0..3 are fetched once by the fifth pass.
+  for (uint32_t p = 0; p < BWT_K; p++) {
+    if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * p], st);
+    const uint32_t ep = next_epoch(B, nb, g, st);
+    if (p == 4)
+      k_radix_pass<uint32_t, 0, 1><<<grid_full, SORT_THREADS, smem32, st>>>(g, d_meta, B.T, src, dst, k32a, k32b, B.tstat,
+                                                                            B.gbase, 256u, 0u, ep, B.counters + 3);
+    else
+      k_radix_pass<uint32_t, 0, 0><<<grid_full, SORT_THREADS, smem32, st>>>(g, d_meta, B.T, src, dst, k32a, k32b, B.tstat,
+                                                                            B.gbase, 256u, 8u * (p & 3u), ep, B.counters + 3);
+    if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * p + 1], st);
+    { uint32_t *t = src; src = dst; dst = t; }
+    { uint32_t *t = k32a; k32a = k32b; k32b = t; }
   }
   // BWT_K is even, so the order is back in B.sa
   B.sa = src; B.sa2 = dst;
-  TileAgg *agg = reinterpret_cast<TileAgg *>(B.hist);     // hist is free between radix passes
+  TileAgg *agg = reinterpret_cast<TileAgg *>(B.agg);
   k_heads_agg<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.head, agg);
   k_ranks_compact<<<grid_full, 256, 0, st>>>(g, d_meta, B, agg);
   LBZ_CUDA_CHECK(cudaGetLastError());
@@ -582,20 +718,24 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   uint32_t *psrc = B.pos, *pdst = B.pos2;
   uint32_t *gsrc = B.gs, *gdst = B.gs2;
   for (;;) {
-    LBZ_CUDA_CHECK(cudaMemcpyAsync(h_counters, B.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    LBZ_CUDA_CHECK(cudaMemcpyAsync(h_counters, B.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     LBZ_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_counters[3]) {
+      fprintf(stderr, "lbzip2_b200: chained scan timed out (tile scheduling assumption violated)\n");
+      return -1;
+    }
     const uint32_t maxU = h_counters[0];
     if (maxU == 0) break;
     rounds++;
-    nl += 2 + 15 + 2;
+    nl += 3 + 5 + 2;
     const dim3 grid_u((maxU + LBZ_TILE - 1) / LBZ_TILE, nb);
-    k_round_commit<<<(nb + 255) / 256, 256, 0, st>>>(d_meta, nb, B.counters);
-    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, h);
-    for (uint32_t sh = 0; sh < 40; sh += 8) {
-      k_hist<1><<<grid_u, SORT_THREADS, 0, st>>>(g, d_meta, nullptr, vsrc, ksrc, B.hist, sh);
-      k_scan<1><<<nb, 256, 0, st>>>(g, d_meta, B.hist, B.digit_base);
-      k_scatter<1><<<grid_u, SORT_THREADS, 0, st>>>(g, d_meta, nullptr, vsrc, vdst, ksrc, kdst,
-                                                      B.hist, B.digit_base, sh);
+    k_round_commit<<<(nb * 5 * 256 + 255) / 256, 256, 0, st>>>(d_meta, nb, B.counters, B.khist);
+    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h);
+    k_key_bases<<<nb, 256, 0, st>>>(d_meta, B.khist, B.gbase + (size_t)nb * 256);
+    for (uint32_t p = 0; p < 5; p++) {
+      k_radix_pass<uint64_t, 1, 0><<<grid_u, SORT_THREADS, smem64, st>>>(g, d_meta, nullptr, vsrc, vdst, ksrc, kdst, B.tstat,
+                                                                         B.gbase + (size_t)nb * 256 + p * 256, 5u * 256u, 8u * p,
+                                                                         next_epoch(B, nb, g, st), B.counters + 3);
       uint64_t *tk = ksrc; ksrc = kdst; kdst = tk;
       uint32_t *tv = vsrc; vsrc = vdst; vdst = tv;
     }

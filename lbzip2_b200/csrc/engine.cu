@@ -23,7 +23,10 @@ struct BwtBuffers {           // must match bwt.cu
   uint8_t *head;
   uint64_t *key, *key2;
   uint32_t *val, *val2, *pos, *pos2, *gs, *gs2;
-  uint32_t *hist, *digit_base, *counters;
+  uint32_t *tstat, *gbase, *khist;
+  void *agg;
+  uint32_t *counters;
+  uint32_t *epoch;
   uint8_t *bwt;
 };
 
@@ -64,7 +67,9 @@ struct lbz_engine {
   uint32_t *d_sa = nullptr, *d_sa2 = nullptr, *d_rank = nullptr;
   uint64_t *d_key = nullptr, *d_key2 = nullptr;
   uint32_t *d_val = nullptr, *d_val2 = nullptr, *d_pos = nullptr, *d_pos2 = nullptr, *d_gs = nullptr, *d_gs2 = nullptr;
-  uint32_t *d_hist = nullptr, *d_digit_base = nullptr, *d_counters = nullptr;
+  uint32_t *d_tstat = nullptr, *d_gbase = nullptr, *d_khist = nullptr, *d_counters = nullptr;
+  uint64_t *d_agg = nullptr;
+  uint32_t epoch = 0;
   uint16_t *d_mtfv = nullptr;
   uint32_t *d_freq = nullptr;
   int *d_parttab = nullptr;
@@ -168,8 +173,10 @@ extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) 
   rc |= dev_alloc(e, &e->d_pos2, E);
   rc |= dev_alloc(e, &e->d_gs, E);
   rc |= dev_alloc(e, &e->d_gs2, E);
-  rc |= dev_alloc(e, &e->d_hist, NB * g.tiles1 * 256);
-  rc |= dev_alloc(e, &e->d_digit_base, NB * 256);
+  rc |= dev_alloc(e, &e->d_tstat, NB * g.tiles1 * 256);
+  rc |= dev_alloc(e, &e->d_gbase, NB * 256 * 6);
+  rc |= dev_alloc(e, &e->d_khist, NB * 256 * 5);
+  rc |= dev_alloc(e, &e->d_agg, NB * g.tiles1);
   rc |= dev_alloc(e, &e->d_counters, 8);
   rc |= dev_alloc(e, &e->d_mtfv, E);
   rc |= dev_alloc(e, &e->d_freq, NB * 260);
@@ -188,6 +195,8 @@ extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) 
     return nullptr;
   }
   cudaMemsetAsync(e->d_meta, 0, NB * sizeof(LbzBlockMeta), e->st);
+  cudaMemsetAsync(e->d_tstat, 0, NB * g.tiles1 * 256 * sizeof(uint32_t), e->st);
+  cudaMemsetAsync(e->d_counters, 0, 8 * sizeof(uint32_t), e->st);
   cudaStreamSynchronize(e->st);
   return e;
 }
@@ -232,7 +241,8 @@ static BwtBuffers bwt_buffers(lbz_engine *e) {
   B.T = e->d_T; B.sa = e->d_sa; B.sa2 = e->d_sa2; B.rank = e->d_rank; B.head = e->d_head;
   B.key = e->d_key; B.key2 = e->d_key2; B.val = e->d_val; B.val2 = e->d_val2;
   B.pos = e->d_pos; B.pos2 = e->d_pos2; B.gs = e->d_gs; B.gs2 = e->d_gs2;
-  B.hist = e->d_hist; B.digit_base = e->d_digit_base; B.counters = e->d_counters; B.bwt = e->d_bwt;
+  B.tstat = e->d_tstat; B.gbase = e->d_gbase; B.khist = e->d_khist; B.agg = e->d_agg;
+  B.counters = e->d_counters; B.epoch = &e->epoch; B.bwt = e->d_bwt;
   return B;
 }
 

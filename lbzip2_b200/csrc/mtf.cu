@@ -95,6 +95,8 @@ k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
   __shared__ int s_tab[MTF_WARPS][256];
   __shared__ int s_carry[256];
   __shared__ uint8_t s_dense[256];
+  __shared__ __align__(8) uint8_t s_P[MTF_WARPS][256];
+  __shared__ uint32_t s_B[MTF_WARPS][16];
 
   if (tid < 256) {
     // dense renumbering of the used byte values (encode.c:340-355)
@@ -176,53 +178,104 @@ k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
         }
       }
     }
-    uint32_t lo = (e[0] & 0xFFu) | ((e[1] & 0xFFu) << 8) | ((e[2] & 0xFFu) << 16) | ((e[3] & 0xFFu) << 24);
-    uint32_t hi = (e[4] & 0xFFu) | ((e[5] & 0xFFu) << 8) | ((e[6] & 0xFFu) << 16) | ((e[7] & 0xFFu) << 24);
+    // position table P[sym] = place of sym in the recency list at the segment start
+    uint8_t *P = s_P[warp];
+#pragma unroll
+    for (int r = 0; r < 8; r++) P[e[r] & 0xFFu] = (uint8_t)(lane * 8 + r);
+    __syncwarp();
 
-    // walk the segment
+    // Walk the segment 32 positions at a time; all 32 ranks of a chunk are
+    // computed together from the chunk-local occurrence structure:
+    //   * symbol seen earlier in the chunk (at lane j): rank = number of distinct
+    //     symbols in lanes (j, i) = lanes there that are the last occurrence
+    //     before i of their symbol ("alive" mask, a prefix-OR of predecessor bits);
+    //   * first occurrence in the chunk: rank = P[sym] + number of distinct chunk
+    //     symbols seen earlier whose old place was behind it;
+    // then the table is advanced past the chunk in one step (symbols outside the
+    // chunk slide back by the number of chunk symbols that were behind them).
+    const uint32_t ltm = lanemask_lt();
+    const uint32_t gtm = ~ltm & ~(1u << lane);
     uint32_t prev_sym = segbase ? s_dense[src[segbase - 1]] : 0u;    // list front before the segment
     for (uint32_t q = 0; q < MTF_SEG / 32; q++) {
       if (segbase + q * 32 >= part_hi) break;
       const uint32_t p = segbase + q * 32 + lane;
       const bool valid = p < part_hi;
-      const uint32_t c = valid ? s_dense[src[p]] : 0xFFFFu;
+      const uint32_t c = valid ? s_dense[src[p]] : (0x100u + lane);  // invalid lanes: unique dummies
       uint32_t pc = __shfl_up_sync(0xffffffffu, c, 1);
       if (lane == 0) pc = prev_sym;
-      const bool nz = valid && (c != pc);
-      uint32_t todo = __ballot_sync(0xffffffffu, nz);
-      uint32_t myrank = 0;
-      while (todo) {
-        const uint32_t src_lane = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t cc = __shfl_sync(0xffffffffu, c, src_lane);
-        const uint32_t rep = cc * 0x01010101u;
-        const uint32_t mlo = __vcmpeq4(lo, rep), mhi = __vcmpeq4(hi, rep);
-        const uint32_t hit = __ballot_sync(0xffffffffu, (mlo | mhi) != 0);
-        const uint32_t L = __ffs(hit) - 1;
-        uint32_t bi = mlo ? ((__ffs(mlo) - 1) >> 3) : (4 + ((__ffs(mhi) - 1) >> 3));
-        bi = __shfl_sync(0xffffffffu, bi, L);
-        if (lane == src_lane) myrank = L * 8 + bi;
-        // move to front
-        uint32_t incoming = __shfl_up_sync(0xffffffffu, hi >> 24, 1);
-        if (lane == 0) incoming = cc;
-        const uint32_t slo = (lo << 8) | incoming;
-        const uint32_t shi = (hi << 8) | (lo >> 24);
-        if (lane < L) { lo = slo; hi = shi; }
-        else if (lane == L) {
-          // bytes 0..bi take the shifted value, bytes above stay
-          if (bi < 4) {
-            const uint32_t mask = (bi == 3) ? 0xFFFFFFFFu : ((1u << (8 * (bi + 1))) - 1u);
-            lo = (slo & mask) | (lo & ~mask);
-          } else {
-            const uint32_t bj = bi - 4;
-            const uint32_t mask = (bj == 3) ? 0xFFFFFFFFu : ((1u << (8 * (bj + 1))) - 1u);
-            hi = (shi & mask) | (hi & ~mask);
-            lo = slo;
-          }
-        }
-      }
-      if (valid) dstr[p] = (uint8_t)myrank;     // 0 for positions equal to their predecessor
+      const bool ev = valid && (c != pc);
+      const uint32_t evmask = __ballot_sync(0xffffffffu, ev);
       prev_sym = __shfl_sync(0xffffffffu, c, 31);
+      if (evmask == 0) {                                             // pure run: ranks 0, list unchanged
+        if (valid) dstr[p] = 0;
+        continue;
+      }
+      const uint32_t m = __match_any_sync(0xffffffffu, c);
+      const uint32_t prevm = m & ltm;
+      const bool hasprev = prevm != 0;
+      const uint32_t j = hasprev ? (31u - __clz(prevm)) : 0u;
+      const bool isfirst = valid && !hasprev;
+      const bool islast = valid && ((m & gtm) == 0);
+      const uint32_t Pc = valid ? (uint32_t)P[c] : 0u;
+      // dead = lanes whose symbol occurs again at or before this lane
+      uint32_t dead = hasprev ? (1u << j) : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, dead, o);
+        if (lane >= (uint32_t)o) dead |= t;
+      }
+      const uint32_t alive = ltm & ~dead;
+      const uint32_t fm = __ballot_sync(0xffffffffu, isfirst);
+      uint32_t cnt = 0;
+      for (uint32_t mm = fm; mm; mm &= mm - 1) {
+        const uint32_t t = __ffs(mm) - 1;
+        const uint32_t pt = __shfl_sync(0xffffffffu, Pc, t);
+        cnt += (t < lane) && (pt > Pc);
+      }
+      const uint32_t rank = hasprev ? __popc((alive >> j) >> 1) : (Pc + cnt);
+      if (valid) dstr[p] = ev ? (uint8_t)rank : (uint8_t)0;
+
+      // ---- advance the table past the chunk ----
+      const uint32_t lastm = __ballot_sync(0xffffffffu, islast);
+      uint32_t Bw[8];
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        const uint32_t contrib = (isfirst && (Pc >> 5) == (uint32_t)w) ? (1u << (Pc & 31u)) : 0u;
+        Bw[w] = __reduce_or_sync(0xffffffffu, contrib);
+      }
+      uint32_t *SB = s_B[warp];
+      if (lane < 8) {
+        uint32_t mine = 0, suffix = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+          if ((uint32_t)w == lane) mine = Bw[w];
+          if ((uint32_t)w > lane) suffix += __popc(Bw[w]);
+        }
+        SB[lane] = mine;
+        SB[8 + lane] = suffix;
+      }
+      __syncwarp();
+      {
+        uint2 pv = *reinterpret_cast<uint2 *>(&P[lane * 8]);
+        uint32_t wv[2] = {pv.x, pv.y};
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+          uint32_t out = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t pk = (wv[h2] >> (8 * k)) & 0xFFu;
+            const uint32_t w = pk >> 5;
+            const uint32_t above = __popc((SB[w] >> (pk & 31u)) >> 1) + SB[8 + w];
+            out |= ((pk + above) & 0xFFu) << (8 * k);
+          }
+          wv[h2] = out;
+        }
+        pv.x = wv[0]; pv.y = wv[1];
+        *reinterpret_cast<uint2 *>(&P[lane * 8]) = pv;
+      }
+      __syncwarp();
+      if (islast) P[c] = (uint8_t)__popc(lastm & gtm);
+      __syncwarp();
     }
   }
 }
