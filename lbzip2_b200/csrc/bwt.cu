@@ -109,11 +109,11 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
 // key).  COUNT_U: segment size = tied-set size (round passes) instead of n.
 // GATHER: the key is not read from src_key but fetched from the text: the four
 // leading bytes of rotation `val` (used once, by the 5th pass of the initial sort).
-template <typename K>
+template <typename K, int THREADS, int ITEMS>
 struct RadixSmem {
-  K skey[LBZ_TILE];
-  uint32_t sval[LBZ_TILE];
-  uint32_t wcnt[SORT_WARPS][256];
+  K skey[THREADS * ITEMS];
+  uint32_t sval[THREADS * ITEMS];
+  uint32_t wcnt[THREADS / 32][256];
   uint32_t dstart[256];
   uint32_t delta[256];
   uint32_t ws[40];
@@ -131,34 +131,37 @@ __device__ __forceinline__ uint32_t text_key4(const uint8_t *__restrict__ Tb, ui
   return k;
 }
 
-template <typename K, int COUNT_U, int GATHER>
-__global__ void __launch_bounds__(SORT_THREADS)
+template <typename K, int COUNT_U, int GATHER, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS, (THREADS * ITEMS <= 2048 ? 4 : 2))
 k_radix_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
              const uint32_t *__restrict__ src_val, uint32_t *__restrict__ dst_val,
              const K *__restrict__ src_key, K *__restrict__ dst_key,
              uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase, uint32_t gstride,
              uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err) {
   extern __shared__ __align__(16) unsigned char radix_smem_raw[];
-  RadixSmem<K> &S = *reinterpret_cast<RadixSmem<K> *>(radix_smem_raw);
+  RadixSmem<K, THREADS, ITEMS> &S = *reinterpret_cast<RadixSmem<K, THREADS, ITEMS> *>(radix_smem_raw);
+  constexpr uint32_t RTILE = THREADS * ITEMS;
+  constexpr int NW = THREADS / 32;
+  const uint32_t rtiles = g.S1 / RTILE;            // status rows per block slot
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
   const uint32_t cnt = COUNT_U ? meta[b].unsorted : meta[b].n;
-  const uint32_t tbase = tile * LBZ_TILE;
+  const uint32_t tbase = tile * RTILE;
   if (tbase >= cnt) return;
   const uint32_t n = meta[b].n;
   const uint32_t off = lbz_slot_off(g, b);
-  const uint32_t tile_cnt = min(LBZ_TILE, cnt - tbase);
-  for (uint32_t i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&S.wcnt[0][0])[i] = 0;
+  const uint32_t tile_cnt = min(RTILE, cnt - tbase);
+  for (uint32_t i = threadIdx.x; i < NW * 256; i += THREADS) (&S.wcnt[0][0])[i] = 0;
   __syncthreads();
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t lt = lanemask_lt();
-  uint32_t val[SORT_ITEMS];
-  uint32_t rd[SORT_ITEMS];     // rank within warp strip | digit << 16 | valid << 31
-  K key[SORT_ITEMS];
+  uint32_t val[ITEMS];
+  uint32_t rd[ITEMS];     // rank within warp strip | digit << 16 | valid << 31
+  K key[ITEMS];
 
 #pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++) {
-    const uint32_t idx = tbase + warp * (32 * SORT_ITEMS) + it * 32 + lane;
+  for (int it = 0; it < ITEMS; it++) {
+    const uint32_t idx = tbase + warp * (32 * ITEMS) + it * 32 + lane;
     const bool valid = idx < cnt;
     val[it] = valid ? src_val[off + idx] : 0u;
     if (!GATHER) key[it] = valid ? src_key[off + idx] : (K)0;
@@ -166,10 +169,10 @@ k_radix_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   }
   if (GATHER) {
 #pragma unroll
-    for (int it = 0; it < SORT_ITEMS; it++) key[it] = rd[it] ? (K)text_key4(T + off, val[it], n) : (K)0;
+    for (int it = 0; it < ITEMS; it++) key[it] = rd[it] ? (K)text_key4(T + off, val[it], n) : (K)0;
   }
 #pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++) {
+  for (int it = 0; it < ITEMS; it++) {
     const bool valid = rd[it] != 0;
     const uint32_t digit = valid ? ((uint32_t)(key[it] >> shift) & 0xFFu) : 0x100u;   // invalid lanes: own match group
     const uint32_t mask = __match_any_sync(0xffffffffu, digit);
@@ -181,25 +184,38 @@ k_radix_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
     rd[it] |= (digit << 16) | (base + __popc(mask & lt));
   }
   __syncthreads();
-  {
-    const uint32_t d = threadIdx.x;
-    uint32_t total = 0;
+  // per-digit totals of the tile; publish them at once so that successors can proceed
+  const uint32_t d = threadIdx.x;
+  uint32_t total = 0;
+  uint32_t *mine = tstat + ((size_t)b * rtiles + tile) * 256 + (d & 255u);
+  const uint32_t ep = (epoch << 20) & TS_EPOCH_MASK;
+  if (d < 256) {
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) {
+    for (int w = 0; w < NW; w++) {
       const uint32_t c = S.wcnt[w][d];
       S.wcnt[w][d] = total;
       total += c;
     }
-    uint32_t *mine = tstat + ((size_t)b * g.tiles1 + tile) * 256 + d;
-    const uint32_t ep = (epoch << 20) & TS_EPOCH_MASK;
-    uint32_t excl = 0;
-    if (tile == 0) {
-      st_volatile_u32(mine, TS_FLAG_PREFIX | ep | total);
-    } else {
-      st_volatile_u32(mine, TS_FLAG_AGG | ep | total);
+    st_volatile_u32(mine, (tile == 0 ? TS_FLAG_PREFIX : TS_FLAG_AGG) | ep | total);
+  }
+  uint32_t tsum;
+  const uint32_t dst0 = cta_excl_sum(total, S.ws, &tsum);      // start of digit d inside the tile
+  if (d < 256) S.dstart[d] = dst0;
+  __syncthreads();
+  // stage the tile in digit order (needs only tile-local offsets) ...
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
+    if (rd[it] & 0x80000000u) {
+      const uint32_t digit = (rd[it] >> 16) & 0xFFu;
+      const uint32_t slot = S.dstart[digit] + S.wcnt[warp][digit] + (rd[it] & 0xFFFFu);
+      S.skey[slot] = key[it];
+      S.sval[slot] = val[it];
     }
-    uint32_t tsum;
-    const uint32_t dst0 = cta_excl_sum(total, S.ws, &tsum);      // start of digit d inside the tile
+  }
+  // ... then resolve the global offset of every digit by looking back over the
+  // preceding tiles of this block (by now they have usually published)
+  if (d < 256) {
+    uint32_t excl = 0;
     if (tile != 0) {
       const uint32_t *look = mine - 256;
       uint32_t spins = 0;
@@ -207,6 +223,7 @@ k_radix_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
         const uint32_t sw = ld_volatile_u32(look);
         if ((sw & TS_EPOCH_MASK) != ep || (sw >> 30) == 0u) {
           if (++spins > TS_SPIN_LIMIT) { *err = 1u; break; }     // never expected: fail loudly on the host
+          __nanosleep(40);
           continue;
         }
         excl += sw & TS_VALUE_MASK;
@@ -215,23 +232,12 @@ k_radix_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
       }
       st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total) & TS_VALUE_MASK));
     }
-    S.dstart[d] = dst0;
     S.delta[d] = gbase[(size_t)b * gstride + d] + excl - dst0;   // global index = delta[digit] + tile-local slot
   }
   __syncthreads();
-  // stage the tile in digit order, then write it out with consecutive threads
-  // on consecutive slots (runs of equal digits are contiguous in global memory)
-#pragma unroll
-  for (int it = 0; it < SORT_ITEMS; it++) {
-    if (rd[it] & 0x80000000u) {
-      const uint32_t digit = (rd[it] >> 16) & 0xFFu;
-      const uint32_t slot = S.dstart[digit] + S.wcnt[warp][digit] + (rd[it] & 0xFFFFu);
-      S.skey[slot] = key[it];
-      S.sval[slot] = val[it];
-    }
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < tile_cnt; i += SORT_THREADS) {
+  // write out with consecutive threads on consecutive slots (runs of equal
+  // digits are contiguous in global memory)
+  for (uint32_t i = threadIdx.x; i < tile_cnt; i += THREADS) {
     const K k = S.skey[i];
     const uint32_t dst = S.delta[(uint32_t)(k >> shift) & 0xFFu] + i;
     dst_key[off + dst] = k;
@@ -655,11 +661,38 @@ __global__ void k_round_commit(LbzBlockMeta *__restrict__ meta, uint32_t nblocks
   if (i == 0) { counters[0] = 0; counters[1] = 0; }
 }
 
+template <typename K, int COUNT_U, int GATHER, int THREADS, int ITEMS>
+static int launch_radix_t(dim3 grid, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
+                          const uint32_t *sv, uint32_t *dv, const K *sk, K *dk, uint32_t *tstat, const uint32_t *gbase,
+                          uint32_t gstride, uint32_t shift, uint32_t epoch, uint32_t *err) {
+  const size_t smem = sizeof(RadixSmem<K, THREADS, ITEMS>);
+  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<K, COUNT_U, GATHER, THREADS, ITEMS>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_radix_pass<K, COUNT_U, GATHER, THREADS, ITEMS><<<grid, THREADS, smem, st>>>(g, meta, T, sv, dv, sk, dk, tstat, gbase,
+                                                                                 gstride, shift, epoch, err);
+  return 0;
+}
+// cfg 0: 256 threads x 8 items (tile 2048); cfg 1: 512 threads x 8 items (tile 4096)
+template <typename K, int COUNT_U>
+static int launch_radix(int cfg, bool gather, uint32_t max_count, uint32_t nb, cudaStream_t st, const LbzGeom &g,
+                        const LbzBlockMeta *meta, const uint8_t *T, const uint32_t *sv, uint32_t *dv, const K *sk, K *dk,
+                        uint32_t *tstat, const uint32_t *gbase, uint32_t gstride, uint32_t shift, uint32_t epoch,
+                        uint32_t *err) {
+  const uint32_t rtile = cfg ? 4096u : 2048u;
+  const dim3 grid((max_count + rtile - 1) / rtile, nb);
+  if (cfg) {
+    if (gather) return launch_radix_t<K, COUNT_U, 1, 512, 8>(grid, st, g, meta, T, sv, dv, sk, dk, tstat, gbase, gstride, shift, epoch, err);
+    return launch_radix_t<K, COUNT_U, 0, 512, 8>(grid, st, g, meta, T, sv, dv, sk, dk, tstat, gbase, gstride, shift, epoch, err);
+  }
+  if (gather) return launch_radix_t<K, COUNT_U, 1, 256, 8>(grid, st, g, meta, T, sv, dv, sk, dk, tstat, gbase, gstride, shift, epoch, err);
+  return launch_radix_t<K, COUNT_U, 0, 256, 8>(grid, st, g, meta, T, sv, dv, sk, dk, tstat, gbase, gstride, shift, epoch, err);
+}
+
 // Status-word epoch: 1..1023, the status array is cleared when it wraps.
 static uint32_t next_epoch(const BwtBuffers &B, uint32_t nb, const LbzGeom &g, cudaStream_t st) {
   uint32_t e = *B.epoch + 1;
   if (e >= 1024) {
-    cudaMemsetAsync(B.tstat, 0, (size_t)nb * g.tiles1 * 256 * sizeof(uint32_t), st);
+    cudaMemsetAsync(B.tstat, 0, (size_t)nb * (g.S1 / 2048u) * 256 * sizeof(uint32_t), st);
     e = 1;
   }
   *B.epoch = e;
@@ -681,10 +714,8 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   uint32_t *k32a = reinterpret_cast<uint32_t *>(B.key), *k32b = reinterpret_cast<uint32_t *>(B.key2);
   k_sa_init<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, k32a);
   nl += 3 + BWT_K + 2;
-  const size_t smem32 = sizeof(RadixSmem<uint32_t>), smem64 = sizeof(RadixSmem<uint64_t>);
-  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<uint32_t, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<uint32_t, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass<uint64_t, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+  static int cfg = -1;
+  if (cfg < 0) { const char *ev = getenv("LBZ_RADIX_CFG"); cfg = ev ? (atoi(ev) != 0) : 1; }
 
   uint32_t *src = B.sa, *dst = B.sa2;
   k_text_bases<<<nb, 1024, 0, st>>>(g, d_meta, B.T, B.gbase);
@@ -693,12 +724,8 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   for (uint32_t p = 0; p < BWT_K; p++) {
     if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * p], st);
     const uint32_t ep = next_epoch(B, nb, g, st);
-    if (p == 4)
-      k_radix_pass<uint32_t, 0, 1><<<grid_full, SORT_THREADS, smem32, st>>>(g, d_meta, B.T, src, dst, k32a, k32b, B.tstat,
-                                                                            B.gbase, 256u, 0u, ep, B.counters + 3);
-    else
-      k_radix_pass<uint32_t, 0, 0><<<grid_full, SORT_THREADS, smem32, st>>>(g, d_meta, B.T, src, dst, k32a, k32b, B.tstat,
-                                                                            B.gbase, 256u, 8u * (p & 3u), ep, B.counters + 3);
+    if (launch_radix<uint32_t, 0>(cfg, p == 4, g.S1, nb, st, g, d_meta, B.T, src, dst, k32a, k32b, B.tstat,
+                                  B.gbase, 256u, (p == 4) ? 0u : 8u * (p & 3u), ep, B.counters + 3)) return -1;
     if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * p + 1], st);
     { uint32_t *t = src; src = dst; dst = t; }
     { uint32_t *t = k32a; k32a = k32b; k32b = t; }
@@ -733,9 +760,9 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h);
     k_key_bases<<<nb, 256, 0, st>>>(d_meta, B.khist, B.gbase + (size_t)nb * 256);
     for (uint32_t p = 0; p < 5; p++) {
-      k_radix_pass<uint64_t, 1, 0><<<grid_u, SORT_THREADS, smem64, st>>>(g, d_meta, nullptr, vsrc, vdst, ksrc, kdst, B.tstat,
-                                                                         B.gbase + (size_t)nb * 256 + p * 256, 5u * 256u, 8u * p,
-                                                                         next_epoch(B, nb, g, st), B.counters + 3);
+      if (launch_radix<uint64_t, 1>(cfg, false, maxU, nb, st, g, d_meta, nullptr, vsrc, vdst,
+                                    ksrc, kdst, B.tstat, B.gbase + (size_t)nb * 256 + p * 256, 5u * 256u, 8u * p,
+                                    next_epoch(B, nb, g, st), B.counters + 3)) return -1;
       uint64_t *tk = ksrc; ksrc = kdst; kdst = tk;
       uint32_t *tv = vsrc; vsrc = vdst; vdst = tv;
     }

@@ -16,6 +16,8 @@
 #include <mutex>
 #include <condition_variable>
 #include <vector>
+#include <thread>
+#include <future>
 
 struct BwtBuffers {           // must match bwt.cu
   const uint8_t *T;
@@ -82,6 +84,14 @@ struct lbz_engine {
   LbzBlockMeta *h_meta = nullptr;
   uint32_t *h_counters = nullptr;   // [0..1] sort counters, [2] packed total
   std::vector<void *> allocs;
+  // Two-lane mode: large engines are split into two half-capacity lanes (this
+  // object + `sib`) that work on disjoint chunk ranges of a batch on their own
+  // streams, driven by two host threads, so that the latency-bound kernels of one
+  // lane (rle1, huffman, round bookkeeping, host round trips) overlap with the
+  // bandwidth-bound sort passes of the other, and H2D/D2H overlap with compute.
+  lbz_engine *sib = nullptr;
+  uint32_t total_chunks = 0;           // capacity of the whole engine (both lanes)
+  cudaEvent_t ev_done = nullptr;
 };
 
 #define ENG_CHECK(x)                                                              \
@@ -118,7 +128,7 @@ extern "C" size_t lbz_bound(size_t n) {
   return n + n / 32 + 8192 * (n / 100000 + 2) + 64;
 }
 
-extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) {
+static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   if (level < 1 || level > 9 || max_chunks < 1 || max_chunks > 16384) {
     fprintf(stderr, "lbzip2_b200: bad engine parameters (level %d, max_chunks %d)\n", level, max_chunks);
     return nullptr;
@@ -139,6 +149,7 @@ extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) 
   e->device = device;
   e->level = level;
   e->max_chunks = (uint32_t)max_chunks;
+  e->total_chunks = (uint32_t)max_chunks;
   LbzGeom &g = e->g;
   g.mbs = (uint32_t)level * 100000u;
   g.S1 = round_up(g.mbs + 64, LBZ_TILE);
@@ -153,6 +164,7 @@ extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) 
   rc |= cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess;
   for (int i = 0; i <= LBZ_NSTAGE; i++) rc |= cudaEventCreate(&e->tm.stage[i]) != cudaSuccess;
   for (int i = 0; i < 2 * LBZ_NK0; i++) rc |= cudaEventCreate(&e->tm.k0[i]) != cudaSuccess;
+  rc |= cudaEventCreate(&e->ev_done) != cudaSuccess;
   rc |= cudaEventCreate(&e->ev_call[0]) != cudaSuccess;
   rc |= cudaEventCreate(&e->ev_call[1]) != cudaSuccess;
   e->tm.enabled = 1;
@@ -173,7 +185,7 @@ extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) 
   rc |= dev_alloc(e, &e->d_pos2, E);
   rc |= dev_alloc(e, &e->d_gs, E);
   rc |= dev_alloc(e, &e->d_gs2, E);
-  rc |= dev_alloc(e, &e->d_tstat, NB * g.tiles1 * 256);
+  rc |= dev_alloc(e, &e->d_tstat, NB * (g.S1 / 2048u) * 256);
   rc |= dev_alloc(e, &e->d_gbase, NB * 256 * 6);
   rc |= dev_alloc(e, &e->d_khist, NB * 256 * 5);
   rc |= dev_alloc(e, &e->d_agg, NB * g.tiles1);
@@ -195,14 +207,31 @@ extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) 
     return nullptr;
   }
   cudaMemsetAsync(e->d_meta, 0, NB * sizeof(LbzBlockMeta), e->st);
-  cudaMemsetAsync(e->d_tstat, 0, NB * g.tiles1 * 256 * sizeof(uint32_t), e->st);
+  cudaMemsetAsync(e->d_tstat, 0, NB * (g.S1 / 2048u) * 256 * sizeof(uint32_t), e->st);
   cudaMemsetAsync(e->d_counters, 0, 8 * sizeof(uint32_t), e->st);
   cudaStreamSynchronize(e->st);
   return e;
 }
 
+extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) {
+  const char *ev = getenv("LBZ_LANES");
+  const int lanes = (max_chunks >= 32 && !(ev && atoi(ev) == 1)) ? 2 : 1;
+  const int per = (max_chunks + lanes - 1) / lanes;
+  lbz_engine *e = engine_create_one(device, level, per);
+  if (!e) return nullptr;
+  e->total_chunks = (uint32_t)(per * lanes);
+  if (lanes == 2) {
+    e->sib = engine_create_one(device, level, per);
+    if (!e->sib) { lbz_engine_destroy(e); return nullptr; }
+    e->sib->total_chunks = (uint32_t)per;
+  }
+  return e;
+}
+
 extern "C" void lbz_engine_destroy(lbz_engine *e) {
   if (!e) return;
+  if (e->sib) { lbz_engine_destroy(e->sib); e->sib = nullptr; }
+  if (e->ev_done) cudaEventDestroy(e->ev_done);
   cudaSetDevice(e->device);
   if (e->st) { cudaStreamSynchronize(e->st); cudaStreamDestroy(e->st); }
   for (void *p : e->allocs) cudaFree(p);
@@ -221,14 +250,22 @@ extern "C" void *lbz_host_alloc(size_t bytes) {
   return p;
 }
 extern "C" void lbz_host_free(void *p) { if (p) cudaFreeHost(p); }
-extern "C" uint64_t lbz_engine_launches(const lbz_engine *e) { return e->launches; }
-extern "C" uint32_t lbz_engine_last_rounds(const lbz_engine *e) { return e->last_rounds; }
-extern "C" double lbz_engine_last_ms(const lbz_engine *e) { return e->last_ms; }
-extern "C" void lbz_engine_stage_ms(const lbz_engine *e, double *out7) { for (int i = 0; i < 7; i++) out7[i] = e->stage_ms[i]; }
-extern "C" void lbz_engine_k0_stats(const lbz_engine *e, double *sum_ms, uint32_t *launches, uint64_t *elements) {
-  *sum_ms = e->k0_ms; *launches = e->k0_launches; *elements = e->k0_elements;
+extern "C" uint64_t lbz_engine_launches(const lbz_engine *e) { return e->launches + (e->sib ? e->sib->launches : 0); }
+extern "C" uint32_t lbz_engine_last_rounds(const lbz_engine *e) {
+  return (e->sib && e->sib->last_rounds > e->last_rounds) ? e->sib->last_rounds : e->last_rounds;
 }
-extern "C" size_t lbz_engine_device_bytes(const lbz_engine *e) { return e->dev_bytes; }
+extern "C" double lbz_engine_last_ms(const lbz_engine *e) { return e->last_ms; }
+// stage times are summed over the lanes (the lanes overlap, so the sum exceeds the call time)
+extern "C" void lbz_engine_stage_ms(const lbz_engine *e, double *out7) {
+  for (int i = 0; i < 7; i++) out7[i] = e->stage_ms[i] + (e->sib ? e->sib->stage_ms[i] : 0.0);
+}
+// dominant kernel: summed launch time, launches, average elements per launch
+extern "C" void lbz_engine_k0_stats(const lbz_engine *e, double *sum_ms, uint32_t *launches, uint64_t *elements) {
+  double ms = e->k0_ms; uint64_t nl = e->k0_launches; double el = (double)e->k0_elements * e->k0_launches;
+  if (e->sib) { ms += e->sib->k0_ms; nl += e->sib->k0_launches; el += (double)e->sib->k0_elements * e->sib->k0_launches; }
+  *sum_ms = ms; *launches = (uint32_t)nl; *elements = nl ? (uint64_t)(el / (double)nl) : 0;
+}
+extern "C" size_t lbz_engine_device_bytes(const lbz_engine *e) { return e->dev_bytes + (e->sib ? e->sib->dev_bytes : 0); }
 extern "C" uint32_t lbz_dbg_num_slots(const lbz_engine *e) { return 2 * e->g.nchunks; }
 extern "C" int lbz_dbg_set_chunks(lbz_engine *e, uint32_t nchunks) {
   if (nchunks > e->max_chunks) return -1;
@@ -330,11 +367,6 @@ static int run_pipeline(lbz_engine *e, const uint8_t *d_in, uint8_t *d_packed, s
   return 0;
 }
 
-static void call_begin(lbz_engine *e) {
-  for (int i = 0; i < LBZ_NSTAGE; i++) e->stage_ms[i] = 0.0;
-  e->k0_ms = 0.0; e->k0_launches = 0;
-  cudaEventRecord(e->ev_call[0], e->st);
-}
 static void call_end(lbz_engine *e) {
   cudaEventRecord(e->ev_call[1], e->st);
   cudaEventSynchronize(e->ev_call[1]);
@@ -362,24 +394,95 @@ static size_t fill_recs(lbz_engine *e, uint64_t raw_base, lbz_block_rec *recs, s
   return k;
 }
 
-extern "C" int lbz_compress_chunks(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
-                                   size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
+static void reset_call_stats(lbz_engine *e) {
+  for (int i = 0; i < LBZ_NSTAGE; i++) e->stage_ms[i] = 0.0;
+  e->k0_ms = 0.0; e->k0_launches = 0;
+}
+
+// One lane: chunk table, (H2D,) all stages.  Leaves the packed blocks in
+// e->d_packed (or dst_dev if given) and the block records in e->h_meta.
+static int lane_run(lbz_engine *e, const uint8_t *src, bool src_on_device, size_t len, uint8_t *dst_dev, size_t *total) {
+  if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+  if (set_chunks(e, len)) return -1;
+  const uint8_t *d_in = src;
+  if (!src_on_device) {
+    ENG_CHECK(cudaMemcpyAsync(e->d_in, src, len, cudaMemcpyHostToDevice, e->st));
+    d_in = e->d_in;
+  }
+  return run_pipeline(e, d_in, dst_dev ? dst_dev : e->d_packed, total);
+}
+
+// Compress up to total_chunks chunks (one "super batch") from `src` into `dst`
+// (host or device memory, `on_device`).  Two lanes split the chunk range.
+static int super_batch(lbz_engine *e, const uint8_t *src, size_t len, uint8_t *dst, size_t dst_cap, bool on_device,
+                       uint64_t raw_base, size_t *written, lbz_block_rec *recs, size_t max_recs, size_t *nrec) {
+  const size_t mbs = e->g.mbs;
+  const size_t nc = (len + mbs - 1) / mbs;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (!e->sib || nc < 2) {
+    size_t total;
+    if (lane_run(e, src, on_device, len, nullptr, &total)) return -1;
+    if (total > dst_cap) { fprintf(stderr, "lbzip2_b200: output buffer too small\n"); return -2; }
+    ENG_CHECK(cudaMemcpyAsync(dst, e->d_packed, total, kind, e->st));
+    ENG_CHECK(cudaStreamSynchronize(e->st));
+    *nrec = fill_recs(e, raw_base, recs, max_recs, *nrec);
+    *written = total;
+    return 0;
+  }
+  const size_t ncA = (nc + 1) / 2;
+  const size_t lenA = ncA * mbs, lenB = len - lenA;
+  lbz_engine *A = e, *B = e->sib;
+  std::promise<long long> totA_p;
+  std::future<long long> totA_f = totA_p.get_future();
+  int rcA = 0, rcB = 0;
+  size_t totA = 0, totB = 0;
+  std::thread tb([&]() {
+    rcB = lane_run(B, src + lenA, on_device, lenB, nullptr, &totB);
+    const long long ta = totA_f.get();
+    if (rcB == 0 && ta >= 0) {
+      if ((size_t)ta + totB > dst_cap) { rcB = -2; return; }
+      if (cudaMemcpyAsync(dst + ta, B->d_packed, totB, kind, B->st) != cudaSuccess) { rcB = -1; return; }
+      cudaEventRecord(B->ev_done, B->st);
+      if (cudaStreamSynchronize(B->st) != cudaSuccess) rcB = -1;
+    }
+  });
+  rcA = lane_run(A, src, on_device, lenA, nullptr, &totA);
+  totA_p.set_value(rcA == 0 ? (long long)totA : -1LL);
+  if (rcA == 0) {
+    if (totA > dst_cap) rcA = -2;
+    else if (cudaMemcpyAsync(dst, A->d_packed, totA, kind, A->st) != cudaSuccess) rcA = -1;
+  }
+  tb.join();
+  if (rcA == 0) {
+    cudaStreamWaitEvent(A->st, B->ev_done, 0);          // the call-level end event covers both lanes
+    if (cudaStreamSynchronize(A->st) != cudaSuccess) rcA = -1;
+  }
+  if (rcA || rcB) {
+    if (rcA == -2 || rcB == -2) fprintf(stderr, "lbzip2_b200: output buffer too small\n");
+    return rcA ? rcA : rcB;
+  }
+  *nrec = fill_recs(A, raw_base, recs, max_recs, *nrec);
+  *nrec = fill_recs(B, raw_base + lenA, recs, max_recs, *nrec);
+  *written = totA + totB;
+  return 0;
+}
+
+static int compress_any(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, bool on_device,
+                        size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
   if (!e) return -1;
   ENG_CHECK(cudaSetDevice(e->device));
-  const size_t batch_bytes = (size_t)e->max_chunks * e->g.mbs;
+  const size_t batch_bytes = (size_t)e->total_chunks * e->g.mbs;
+  if (on_device && n > batch_bytes) { fprintf(stderr, "lbzip2_b200: device input exceeds one batch\n"); return -1; }
   size_t o = 0, nrec = 0;
-  call_begin(e);
+  reset_call_stats(e);
+  if (e->sib) reset_call_stats(e->sib);
+  cudaEventRecord(e->ev_call[0], e->st);
   for (size_t pos = 0; pos < n; pos += batch_bytes) {
     const size_t len = (n - pos < batch_bytes) ? n - pos : batch_bytes;
-    if (set_chunks(e, len)) return -1;
-    ENG_CHECK(cudaMemcpyAsync(e->d_in, in + pos, len, cudaMemcpyHostToDevice, e->st));
-    size_t total;
-    if (run_pipeline(e, e->d_in, e->d_packed, &total)) return -1;
-    if (o + total > out_cap) { fprintf(stderr, "lbzip2_b200: output buffer too small\n"); return -2; }
-    ENG_CHECK(cudaMemcpyAsync(out + o, e->d_packed, total, cudaMemcpyDeviceToHost, e->st));
-    ENG_CHECK(cudaStreamSynchronize(e->st));
-    nrec = fill_recs(e, pos, recs, max_recs, nrec);
-    o += total;
+    size_t written = 0;
+    const int rc = super_batch(e, in + pos, len, out + o, out_cap - o, on_device, pos, &written, recs, max_recs, &nrec);
+    if (rc) return rc;
+    o += written;
   }
   call_end(e);
   if (out_len) *out_len = o;
@@ -387,20 +490,16 @@ extern "C" int lbz_compress_chunks(lbz_engine *e, const uint8_t *in, size_t n, u
   return 0;
 }
 
+extern "C" int lbz_compress_chunks(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
+                                   size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
+  return compress_any(e, in, n, out, out_cap, false, out_len, recs, max_recs, num_recs);
+}
+
 extern "C" int lbz_compress_chunks_device(lbz_engine *e, const void *d_in, size_t n, void *d_out, size_t out_cap,
                                           size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
-  if (!e) return -1;
-  ENG_CHECK(cudaSetDevice(e->device));
-  if (set_chunks(e, n)) return -1;
-  if (out_cap < lbz_bound(n)) { fprintf(stderr, "lbzip2_b200: device output buffer too small\n"); return -2; }
-  size_t total;
-  call_begin(e);
-  if (run_pipeline(e, reinterpret_cast<const uint8_t *>(d_in), reinterpret_cast<uint8_t *>(d_out), &total)) return -1;
-  call_end(e);
-  const size_t nrec = fill_recs(e, 0, recs, max_recs, 0);
-  if (out_len) *out_len = total;
-  if (num_recs) *num_recs = nrec;
-  return 0;
+  if (e && out_cap < lbz_bound(n)) { fprintf(stderr, "lbzip2_b200: device output buffer too small\n"); return -2; }
+  return compress_any(e, reinterpret_cast<const uint8_t *>(d_in), n, reinterpret_cast<uint8_t *>(d_out), out_cap, true,
+                      out_len, recs, max_recs, num_recs);
 }
 
 extern "C" int lbz_compress_stream(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
