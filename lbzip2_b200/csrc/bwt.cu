@@ -80,8 +80,6 @@ __global__ void k_sa_init(LbzGeom g, const LbzBlockMeta *__restrict__ meta, cons
 // Counting sort pass, segmented by block.  MODE 0: digit = text byte
 // T[(v + d) mod n], payload = rotation index only.  MODE 1: digit = byte
 // `shift/8` of a 64-bit key that travels with the payload.
-template <int MODE>
-__device__ __forceinline__ uint32_t seg_count(const LbzBlockMeta &m) { return MODE == 0 ? m.n : m.unsorted; }
 
 // One counting-sort pass in ONE launch ("onesweep"): every tile ranks its items
 // per digit, publishes its per-digit counts and obtains its per-digit offset by
@@ -144,11 +142,11 @@ k_radix_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   constexpr int NW = THREADS / 32;
   const uint32_t rtiles = g.S1 / RTILE;            // status rows per block slot
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
-  const uint32_t cnt = COUNT_U ? meta[b].unsorted : meta[b].n;
+  const uint32_t cnt = COUNT_U ? meta[b].ul : meta[b].n;     // round passes sort list L only
   const uint32_t tbase = tile * RTILE;
   if (tbase >= cnt) return;
   const uint32_t n = meta[b].n;
-  const uint32_t off = lbz_slot_off(g, b);
+  const uint32_t off = lbz_slot_off(g, b) + (COUNT_U ? meta[b].lbase : 0u);
   const uint32_t tile_cnt = min(RTILE, cnt - tbase);
   for (uint32_t i = threadIdx.x; i < NW * 256; i += THREADS) (&S.wcnt[0][0])[i] = 0;
   __syncthreads();
@@ -283,7 +281,7 @@ k_text_bases(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
 __global__ void __launch_bounds__(256)
 k_key_bases(const LbzBlockMeta *__restrict__ meta, const uint32_t *__restrict__ khist, uint32_t *__restrict__ gbase1) {
   const uint32_t b = blockIdx.x;
-  if (meta[b].unsorted == 0) return;
+  if (meta[b].ul == 0) return;
   __shared__ uint32_t ws[40];
   for (uint32_t p = 0; p < 5; p++) {
     const uint32_t v = khist[(b * 5 + p) * 256 + threadIdx.x];
@@ -312,11 +310,19 @@ __device__ __forceinline__ uint64_t text_key(const uint8_t *__restrict__ Tb, uin
   return k;
 }
 
-struct TileAgg { uint32_t count; int last; };
+#define SMALL_GROUP 32u      // groups up to this size are refined by the local sort
 
-// Tile-parallel pass A: head flags of a tile, number of rotations still tied,
-// last head position.  Per-tile aggregates replace a serial scan: pass B sums
-// the (<= 220) aggregates of the preceding tiles of its block itself.
+struct TileAgg { uint32_t small; uint32_t large; int last; uint32_t pad; };
+
+__device__ __forceinline__ void list_sel(const LbzBlockMeta &m, uint32_t sel, uint32_t &base, uint32_t &cnt) {
+  if (sel == 0) { base = 0; cnt = m.us; } else { base = m.lbase; cnt = m.ul; }
+}
+
+// Tile-parallel pass A: head flags of a tile (bit 0) plus the size class of every
+// tied rotation's group (bit 1: the group has <= SMALL_GROUP members), numbers of
+// small/large tied rotations, last head position.  Per-tile aggregates replace a
+// serial scan: pass B sums the (<= 220) aggregates of its block itself.
+#define HALO 32u
 __global__ void __launch_bounds__(256)
 k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
             const uint32_t *__restrict__ sa, uint8_t *__restrict__ head, TileAgg *__restrict__ agg) {
@@ -327,7 +333,8 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
   const uint32_t off = lbz_slot_off(g, b);
   const uint8_t *Tb = T + off;
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  __shared__ __align__(16) uint8_t sflag[LBZ_TILE + 32];
+  // flags of positions tbase-HALO .. tbase+LBZ_TILE+HALO ; index = p - tbase + HALO
+  __shared__ __align__(16) uint8_t sflag[HALO + LBZ_TILE + HALO + 16];
   __shared__ uint32_t ws[40];
   __shared__ int wsi[40];
 #pragma unroll 2
@@ -339,40 +346,56 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
     uint64_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
     if (valid) {
       if (lane == 0) kprev = p ? text_key(Tb, sa[off + p - 1], n) : ~k;
-      sflag[p - tbase] = (p == 0) || (k != kprev);
-    } else if (p - tbase <= LBZ_TILE) {
-      sflag[p - tbase] = 1;                              // end of block acts as a head
+      sflag[HALO + p - tbase] = (p == 0) || (k != kprev);
+    } else {
+      sflag[HALO + p - tbase] = 1;                       // end of block acts as a head
     }
   }
-  if (tid == 0) {
-    const uint32_t pn = tbase + LBZ_TILE;
-    sflag[LBZ_TILE] = (pn < n) ? (text_key(Tb, sa[off + pn], n) != text_key(Tb, sa[off + pn - 1], n)) : 1;
+  if (tid < 2 * HALO + 1) {                              // halo flags on both sides (+ the tile's end flag)
+    const int64_t p = (tid < HALO) ? (int64_t)tbase - HALO + tid : (int64_t)tbase + LBZ_TILE + (tid - HALO);
+    const uint32_t x = (tid < HALO) ? tid : HALO + LBZ_TILE + (tid - HALO);
+    uint8_t f = 1;
+    if (p > 0 && p < (int64_t)n)
+      f = text_key(Tb, sa[off + (uint32_t)p], n) != text_key(Tb, sa[off + (uint32_t)p - 1], n);
+    sflag[x] = f;
   }
   __syncthreads();
   const bool tracking = BWT_K < n;
   const uint32_t q0 = tid * 16;
-  const uint4 fv = *reinterpret_cast<const uint4 *>(&sflag[q0]);
-  *reinterpret_cast<uint4 *>(&head[off + tbase + q0]) = fv;
-  uint32_t uns = 0;
+  uint32_t small = 0, large = 0;
   int last = -1;
+  uint32_t outw[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int j = 0; j < 16; j++) {
     const uint32_t p = tbase + q0 + j;
+    const uint32_t x = HALO + q0 + j;
+    uint32_t fb = sflag[x] & 1u;
     if (p < n) {
-      const bool f = sflag[q0 + j], f1 = sflag[q0 + j + 1];
+      const bool f = fb, f1 = sflag[x + 1] & 1u;
       if (f) last = (int)p;
-      uns += !(f && f1);
+      if (tracking && !(f && f1)) {
+        uint32_t back = 0, fwd = 1;
+        while (back < SMALL_GROUP && !(sflag[x - back] & 1u)) back++;
+        while (fwd <= SMALL_GROUP && !(sflag[x + fwd] & 1u)) fwd++;
+        const bool is_small = (back < SMALL_GROUP) && (fwd <= SMALL_GROUP) && (back + fwd <= SMALL_GROUP);
+        if (is_small) { small++; fb |= 2u; } else large++;
+      }
+    } else {
+      fb = 1;
     }
+    outw[j >> 2] |= fb << (8 * (j & 3));
   }
-  uint32_t tot;
+  *reinterpret_cast<uint4 *>(&head[off + tbase + q0]) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+  uint32_t tots, totl;
   int tmax;
-  (void)cta_excl_sum(uns, ws, &tot);
+  (void)cta_excl_sum(small, ws, &tots);
+  (void)cta_excl_sum(large, ws, &totl);
   (void)cta_excl_max(last, -1, wsi, &tmax);
-  if (tid == 0) { TileAgg a; a.count = tracking ? tot : 0u; a.last = tmax; agg[(size_t)b * g.tiles1 + tile] = a; }
+  if (tid == 0) { TileAgg a; a.small = tots; a.large = totl; a.last = tmax; a.pad = 0; agg[(size_t)b * g.tiles1 + tile] = a; }
 }
 
 // Tile-parallel pass B: ranks (rank[i] = first position of i's group) and
-// compaction of the members of tied groups into the round lists.
+// compaction of the members of tied groups into the two round lists.
 __global__ void __launch_bounds__(256)
 k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const TileAgg *__restrict__ agg) {
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
@@ -381,20 +404,25 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
   if (tbase >= n) return;
   const uint32_t off = lbz_slot_off(g, b);
   const uint32_t tid = threadIdx.x;
-  const bool tracking = BWT_K < n;
   __shared__ uint32_t ws[40];
   __shared__ int wsi[40];
-  // carry from the preceding tiles of this block
-  uint32_t c = 0;
+  // carries from the preceding tiles of this block; list L starts where S ends
+  const uint32_t ntiles = (n + LBZ_TILE - 1) / LBZ_TILE;
+  uint32_t cs = 0, cl = 0, alls = 0, alll = 0;
   int l = -1;
-  for (uint32_t t = tid; t < tile; t += 256) {
+  for (uint32_t t = tid; t < ntiles; t += 256) {
     const TileAgg a = agg[(size_t)b * g.tiles1 + t];
-    c += a.count; l = max(l, a.last);
+    alls += a.small; alll += a.large;
+    if (t < tile) { cs += a.small; cl += a.large; l = max(l, a.last); }
   }
-  uint32_t carry_cnt;
+  uint32_t carry_s, carry_l, total_s, total_l;
   int carry_last;
-  (void)cta_excl_sum(c, ws, &carry_cnt);
+  (void)cta_excl_sum(cs, ws, &carry_s);
+  (void)cta_excl_sum(cl, ws, &carry_l);
+  (void)cta_excl_sum(alls, ws, &total_s);
+  (void)cta_excl_sum(alll, ws, &total_l);
   (void)cta_excl_max(l, -1, wsi, &carry_last);
+  const uint32_t lbase = total_s;
 
   const uint32_t p0 = tbase + tid * 16;
   uint8_t f[17];
@@ -407,22 +435,26 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
   }
   int last = -1;
 #pragma unroll
-  for (int j = 0; j < 16; j++) if (p0 + j < n && f[j]) last = (int)(p0 + j);
+  for (int j = 0; j < 16; j++) if (p0 + j < n && (f[j] & 1u)) last = (int)(p0 + j);
   int tmax;
   int st = cta_excl_max(last, -1, wsi, &tmax);
   st = max(st, carry_last);
-  uint32_t unsmask = 0;
+  const bool tracking = BWT_K < n;
+  uint32_t smask = 0, lmask = 0;
   uint32_t starts[16];
 #pragma unroll
   for (int j = 0; j < 16; j++) {
     if (p0 + j < n) {
-      if (f[j]) st = (int)(p0 + j);
+      if (f[j] & 1u) st = (int)(p0 + j);
       starts[j] = (uint32_t)st;
-      if (tracking && !(f[j] && f[j + 1])) unsmask |= 1u << j;
+      if (tracking && !((f[j] & 1u) && (f[j + 1] & 1u))) {
+        if (f[j] & 2u) smask |= 1u << j; else lmask |= 1u << j;
+      }
     }
   }
-  uint32_t tot;
-  uint32_t o = carry_cnt + cta_excl_sum(__popc(unsmask), ws, &tot);
+  uint32_t tots, totl;
+  uint32_t os = carry_s + cta_excl_sum(__popc(smask), ws, &tots);
+  uint32_t ol = lbase + carry_l + cta_excl_sum(__popc(lmask), ws, &totl);
   if (p0 < n) {
     uint32_t v[16];
 #pragma unroll
@@ -434,46 +466,52 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
     for (int j = 0; j < 16; j++) {
       if (p0 + j < n) {
         B.rank[off + v[j]] = starts[j];
-        if (unsmask & (1u << j)) {
+        if ((smask | lmask) & (1u << j)) {
+          const uint32_t o = (smask & (1u << j)) ? os++ : ol++;
           B.pos[off + o] = p0 + j;
           B.val[off + o] = v[j];
           B.gs[off + o] = starts[j];
-          o++;
         }
       }
     }
   }
   if (tid == 0 && tbase + LBZ_TILE >= n) {               // last tile of the block
-    const uint32_t U = carry_cnt + tot;
-    meta[b].pad_[1] = U;                                  // committed by k_round_commit
+    meta[b].us_next = total_s;                            // committed by k_round_commit
+    meta[b].ul_next = total_l;
+    meta[b].lbase = lbase;
     meta[b].depth = BWT_K;
-    atomicMax(&B.counters[0], U);
-    atomicAdd(&B.counters[1], U);
+    atomicMax(&B.counters[0], max(total_s, total_l));
+    atomicAdd(&B.counters[1], total_s + total_l);
   }
 }
 
 // ---------------------------------------------------------------------------
-// Round key: (group start << 20) | rank of rotation (i + h); also accumulates
-// the digit histograms of the five radix passes that follow.
+// Round key: (group start << 20) | rank of rotation (i + h) for one of the two
+// lists; for list L it also accumulates the digit histograms of the five radix
+// passes that follow.
 __global__ void __launch_bounds__(256)
 k_round_keys(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint32_t *__restrict__ val,
              const uint32_t *__restrict__ gs, const uint32_t *__restrict__ rank,
-             uint64_t *__restrict__ key, uint32_t *__restrict__ khist, uint32_t h) {
+             uint64_t *__restrict__ key, uint32_t *__restrict__ khist, uint32_t h, uint32_t sel) {
   const uint32_t b = blockIdx.y;
-  const uint32_t U = meta[b].unsorted;
+  uint32_t lb, U;
+  list_sel(meta[b], sel, lb, U);
   const uint32_t tbase = blockIdx.x * LBZ_TILE;
   if (tbase >= U) return;
   const uint32_t n = meta[b].n;
   const uint32_t off = lbz_slot_off(g, b);
+  const uint32_t lo = off + lb;
   __shared__ uint32_t sh[5][256];
-  for (uint32_t i = threadIdx.x; i < 5 * 256; i += 256) (&sh[0][0])[i] = 0;
-  __syncthreads();
+  if (sel) {
+    for (uint32_t i = threadIdx.x; i < 5 * 256; i += 256) (&sh[0][0])[i] = 0;
+    __syncthreads();
+  }
   uint32_t v[LBZ_TILE / 256], gg[LBZ_TILE / 256];
 #pragma unroll
   for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
     const uint32_t j = tbase + it * 256 + threadIdx.x;
-    v[it] = (j < U) ? val[off + j] : 0xFFFFFFFFu;
-    gg[it] = (j < U) ? gs[off + j] : 0u;
+    v[it] = (j < U) ? val[lo + j] : 0xFFFFFFFFu;
+    gg[it] = (j < U) ? gs[lo + j] : 0u;
   }
 #pragma unroll
   for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
@@ -484,15 +522,55 @@ k_round_keys(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint32_t *_
     const uint32_t j = tbase + it * 256 + threadIdx.x;
     if (j < U) {
       const uint64_t k = ((uint64_t)gg[it] << 20) | v[it];
-      key[off + j] = k;
+      key[lo + j] = k;
+      if (sel) {
 #pragma unroll
-      for (int p = 0; p < 5; p++) atomicAdd(&sh[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
+        for (int p = 0; p < 5; p++) atomicAdd(&sh[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
+      }
     }
   }
+  if (sel) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 5 * 256; i += 256) {
+      const uint32_t c = (&sh[0][0])[i];
+      if (c) atomicAdd(&khist[(size_t)b * 5 * 256 + i], c);
+    }
+  }
+}
+
+// Local refinement of list S: every group has at most SMALL_GROUP members, so a
+// member's place inside its group is found by counting the members with a smaller
+// key (ties by list index: stable).  One tile of 4096 list entries per CTA with a
+// halo of SMALL_GROUP entries on both sides staged in shared memory.
+__global__ void __launch_bounds__(256)
+k_small_sort(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__restrict__ kin,
+             const uint32_t *__restrict__ vin, uint64_t *__restrict__ kout, uint32_t *__restrict__ vout) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t U = meta[b].us;
+  const uint32_t tbase = blockIdx.x * LBZ_TILE;
+  if (tbase >= U) return;
+  const uint32_t off = lbz_slot_off(g, b);
+  __shared__ uint64_t sk[SMALL_GROUP + LBZ_TILE + SMALL_GROUP];
+  const int64_t lo = (int64_t)tbase - SMALL_GROUP;
+  for (uint32_t x = threadIdx.x; x < SMALL_GROUP + LBZ_TILE + SMALL_GROUP; x += 256) {
+    const int64_t j = lo + x;
+    sk[x] = (j >= 0 && j < (int64_t)U) ? kin[off + j] : ~0ull;       // ~0: belongs to no group
+  }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < 5 * 256; i += 256) {
-    const uint32_t c = (&sh[0][0])[i];
-    if (c) atomicAdd(&khist[(size_t)b * 5 * 256 + i], c);
+  for (uint32_t q = threadIdx.x; q < LBZ_TILE; q += 256) {
+    const uint32_t j = tbase + q;
+    if (j >= U) break;
+    const uint32_t x = SMALL_GROUP + q;
+    const uint64_t k = sk[x];
+    const uint64_t grp = k >> 20;
+    uint32_t hs = x, he = x + 1;
+    while (hs > 0 && (sk[hs - 1] >> 20) == grp) hs--;                   // group extent (<= SMALL_GROUP members)
+    while (he < SMALL_GROUP + LBZ_TILE + SMALL_GROUP && (sk[he] >> 20) == grp) he++;
+    uint32_t r = 0;
+    for (uint32_t y = hs; y < he; y++) r += (sk[y] < k) || (sk[y] == k && y < x);
+    const uint32_t dst = (uint32_t)(lo + hs) + r;                       // list index of the sorted place
+    kout[off + dst] = k;
+    vout[off + dst] = vin[off + j];
   }
 }
 
@@ -512,13 +590,14 @@ __device__ __forceinline__ void load_round_keys(const uint64_t *__restrict__ ske
 
 __global__ void __launch_bounds__(256)
 k_round_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__restrict__ skey,
-            TileAgg *__restrict__ agg, uint32_t h) {
+            TileAgg *__restrict__ agg, uint32_t h, uint32_t sel) {
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
-  const uint32_t U = meta[b].unsorted;
+  uint32_t lb, U;
+  list_sel(meta[b], sel, lb, U);
   const uint32_t tbase = tile * LBZ_TILE;
   if (tbase >= U) return;
   const uint32_t n = meta[b].n;
-  const uint32_t off = lbz_slot_off(g, b);
+  const uint32_t off = lbz_slot_off(g, b) + lb;
   const uint32_t tid = threadIdx.x;
   const bool more = (2u * h < n);
   __shared__ uint32_t ws[40];
@@ -542,7 +621,10 @@ k_round_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__
   int tmax;
   (void)cta_excl_sum(uns, ws, &tot);
   (void)cta_excl_max(last, -1, wsi, &tmax);
-  if (tid == 0) { TileAgg a; a.count = tot; a.last = tmax; agg[(size_t)b * g.tiles1 + tile] = a; }
+  if (tid == 0) {
+    TileAgg a; a.small = tot; a.large = 0; a.last = tmax; a.pad = 0;
+    agg[((size_t)sel * gridDim.y + b) * g.tiles1 + tile] = a;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -550,13 +632,15 @@ k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
               const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval,
               const uint32_t *__restrict__ pos, uint32_t *__restrict__ nval,
               uint32_t *__restrict__ npos, uint32_t *__restrict__ ngs,
-              const TileAgg *__restrict__ agg, uint32_t h) {
+              const TileAgg *__restrict__ agg, uint32_t h, uint32_t sel) {
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
-  const uint32_t U = meta[b].unsorted;
+  uint32_t lb, U;
+  list_sel(meta[b], sel, lb, U);
   const uint32_t tbase = tile * LBZ_TILE;
   if (tbase >= U) return;
   const uint32_t n = meta[b].n;
-  const uint32_t off = lbz_slot_off(g, b);
+  const uint32_t sa_off = lbz_slot_off(g, b);       // order / rank arrays
+  const uint32_t off = sa_off + lb;                  // list arrays
   const uint32_t tid = threadIdx.x;
   const bool more = (2u * h < n);
   __shared__ uint32_t ws[40];
@@ -564,8 +648,8 @@ k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
   uint32_t c = 0;
   int l = -1;
   for (uint32_t t = tid; t < tile; t += 256) {
-    const TileAgg a = agg[(size_t)b * g.tiles1 + t];
-    c += a.count; l = max(l, a.last);
+    const TileAgg a = agg[((size_t)sel * gridDim.y + b) * g.tiles1 + t];
+    c += a.small; l = max(l, a.last);
   }
   uint32_t carry_cnt;
   int carry_last;
@@ -607,8 +691,8 @@ k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
   for (int q = 0; q < 16; q++) {
     const uint32_t j = j0 + q;
     if (j < U) {
-      B.sa[off + myp[q]] = myv[q];
-      B.rank[off + myv[q]] = mygs[q];
+      B.sa[sa_off + myp[q]] = myv[q];
+      B.rank[sa_off + myv[q]] = mygs[q];
       if (unsmask & (1u << q)) {
         npos[off + o] = myp[q];
         nval[off + o] = myv[q];
@@ -617,9 +701,9 @@ k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
       }
     }
   }
-  if (tid == 0 && tbase + LBZ_TILE >= U) {                // last tile of this block's list
+  if (tid == 0 && tbase + LBZ_TILE >= U) {                // last tile of this list
     const uint32_t U2 = carry_cnt + tot;
-    meta[b].pad_[1] = U2;                                  // committed by k_round_commit
+    if (sel) meta[b].ul_next = U2; else meta[b].us_next = U2;   // committed by k_round_commit
     meta[b].depth = 2u * h;
     atomicMax(&B.counters[0], U2);
     atomicAdd(&B.counters[1], U2);
@@ -647,7 +731,10 @@ k_bwt_final(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B) {
 
 __global__ void k_bwt_prep(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, uint32_t *__restrict__ counters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nblocks) { meta[i].tie_count = 0; meta[i].unsorted = 0; meta[i].pad_[1] = 0; }
+  if (i < nblocks) {
+    meta[i].tie_count = 0; meta[i].unsorted = 0;
+    meta[i].us = 0; meta[i].ul = 0; meta[i].lbase = 0; meta[i].us_next = 0; meta[i].ul_next = 0;
+  }
   if (i == 0) { counters[0] = 0; counters[1] = 0; counters[3] = 0; }
 }
 // Between rounds: the tied-set size written by the last tile of a block becomes
@@ -656,7 +743,10 @@ __global__ void k_bwt_prep(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, ui
 __global__ void k_round_commit(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, uint32_t *__restrict__ counters,
                                uint32_t *__restrict__ khist) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nblocks) meta[i].unsorted = meta[i].pad_[1];
+  if (i < nblocks) {
+    meta[i].us = meta[i].us_next; meta[i].ul = meta[i].ul_next;
+    meta[i].unsorted = meta[i].us + meta[i].ul;
+  }
   if (i < nblocks * 5 * 256) khist[i] = 0;
   if (i == 0) { counters[0] = 0; counters[1] = 0; }
 }
@@ -754,11 +844,14 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     const uint32_t maxU = h_counters[0];
     if (maxU == 0) break;
     rounds++;
-    nl += 3 + 5 + 2;
+    nl += 5 + 5 + 4;
     const dim3 grid_u((maxU + LBZ_TILE - 1) / LBZ_TILE, nb);
     k_round_commit<<<(nb * 5 * 256 + 255) / 256, 256, 0, st>>>(d_meta, nb, B.counters, B.khist);
-    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h);
+    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h, 0u);
+    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h, 1u);
     k_key_bases<<<nb, 256, 0, st>>>(d_meta, B.khist, B.gbase + (size_t)nb * 256);
+    // list S: one local pass straight into the buffers the five radix passes of list L end in
+    k_small_sort<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, vsrc, kdst, vdst);
     for (uint32_t p = 0; p < 5; p++) {
       if (launch_radix<uint64_t, 1>(cfg, false, maxU, nb, st, g, d_meta, nullptr, vsrc, vdst,
                                     ksrc, kdst, B.tstat, B.gbase + (size_t)nb * 256 + p * 256, 5u * 256u, 8u * p,
@@ -766,9 +859,11 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
       uint64_t *tk = ksrc; ksrc = kdst; kdst = tk;
       uint32_t *tv = vsrc; vsrc = vdst; vdst = tv;
     }
-    // sorted (key,val) now in ksrc/vsrc; compacted survivors go to vdst/pdst/gdst
-    k_round_agg<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h);
-    k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h);
+    // sorted (key,val) of both lists now in ksrc/vsrc; compacted survivors go to vdst/pdst/gdst
+    for (uint32_t sel = 0; sel < 2; sel++) {
+      k_round_agg<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h, sel);
+      k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h, sel);
+    }
     { uint32_t *t = vsrc; vsrc = vdst; vdst = t; }
     { uint32_t *t = psrc; psrc = pdst; pdst = t; }
     { uint32_t *t = gsrc; gsrc = gdst; gdst = t; }

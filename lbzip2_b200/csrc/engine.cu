@@ -38,7 +38,7 @@ int lbz_launch_rle1(const LbzGeom *g, const uint8_t *d_in, const uint32_t *d_chu
 int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B, uint32_t *h_counters,
                 uint32_t *rounds_out, uint64_t *launches, const LbzTimers *tm, cudaStream_t st);
 int lbz_launch_mtf(const LbzGeom *g, LbzBlockMeta *d_meta, const uint8_t *d_bwt, uint8_t *d_mtfrank,
-                   uint16_t *d_mtfv, uint32_t *d_freq, int *d_parttab, cudaStream_t st);
+                   uint16_t *d_mtfv, uint32_t *d_freq, int *d_parttab, uint32_t *d_emitcnt, cudaStream_t st);
 uint32_t lbz_mtf_parts();
 int lbz_launch_huffman(const LbzGeom *g, LbzBlockMeta *d_meta, uint16_t *d_mtfv, const uint32_t *d_freq,
                        void *d_coding, uint32_t cluster_factor, cudaStream_t st);
@@ -75,6 +75,7 @@ struct lbz_engine {
   uint16_t *d_mtfv = nullptr;
   uint32_t *d_freq = nullptr;
   int *d_parttab = nullptr;
+  uint32_t *d_emitcnt = nullptr;
   LbzCoding *d_coding = nullptr;
   LbzBlockMeta *d_meta = nullptr;
   uint8_t *d_out = nullptr, *d_packed = nullptr;
@@ -188,11 +189,12 @@ static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   rc |= dev_alloc(e, &e->d_tstat, NB * (g.S1 / 2048u) * 256);
   rc |= dev_alloc(e, &e->d_gbase, NB * 256 * 6);
   rc |= dev_alloc(e, &e->d_khist, NB * 256 * 5);
-  rc |= dev_alloc(e, &e->d_agg, NB * g.tiles1);
+  rc |= dev_alloc(e, &e->d_agg, 2 * NB * g.tiles1 * 2);   // TileAgg (16 B) for two lists
   rc |= dev_alloc(e, &e->d_counters, 8);
   rc |= dev_alloc(e, &e->d_mtfv, E);
   rc |= dev_alloc(e, &e->d_freq, NB * 260);
   rc |= dev_alloc(e, &e->d_parttab, NB * lbz_mtf_parts() * 256);
+  rc |= dev_alloc(e, &e->d_emitcnt, NB * 16);
   rc |= dev_alloc(e, &e->d_coding, NB);
   rc |= dev_alloc(e, &e->d_meta, NB);
   rc |= dev_alloc(e, &e->d_out, NB * (size_t)g.out_cap);
@@ -307,8 +309,8 @@ static int run_stage(lbz_engine *e, int stage, const uint8_t *d_in, uint8_t *d_p
     case LBZ_ST_BWT:
       return lbz_run_bwt(g, e->d_meta, bwt_buffers(e), e->h_counters, &e->last_rounds, &e->launches, &e->tm, e->st);
     case LBZ_ST_MTF:
-      e->launches += 3;
-      return lbz_launch_mtf(g, e->d_meta, e->d_bwt, e->d_mtfrank, e->d_mtfv, e->d_freq, e->d_parttab, e->st);
+      e->launches += 4;
+      return lbz_launch_mtf(g, e->d_meta, e->d_bwt, e->d_mtfrank, e->d_mtfv, e->d_freq, e->d_parttab, e->d_emitcnt, e->st);
     case LBZ_ST_HUFFMAN:
       e->launches += 1;
       return lbz_launch_huffman(g, e->d_meta, e->d_mtfv, e->d_freq, e->d_coding, CLUSTER_FACTOR, e->st);

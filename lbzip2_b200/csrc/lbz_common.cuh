@@ -55,7 +55,11 @@ struct LbzBlockMeta {
   uint32_t depth;        // prefix length the current order is valid for
   uint32_t tree_cost;    // bits: sum over trees of payload + tree transmission
   uint32_t used[8];      // 256-bit used-byte map, bit v of word v/32
-  uint32_t pad_[2];
+  uint32_t pad_[2];      // [0] = bits written by k_pack (host cross-check)
+  // tied-rotation lists of the refinement rounds: list S holds groups of <= 32
+  // members (sorted locally), list L the larger ones (radix passes); S lives at
+  // list index [0, us), L at [lbase, lbase + ul); *_next are committed between rounds
+  uint32_t us, ul, lbase, us_next, ul_next, pad2_;
 };
 
 // Prefix-code description of one block (global memory, one per block slot).

@@ -285,44 +285,26 @@ k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
 #define EMIT_PER 8
 #define EMIT_TILE (EMIT_THREADS * EMIT_PER)
 
-__global__ void __launch_bounds__(EMIT_THREADS, 1)
-k_mtf_emit(LbzGeom g, LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ bwt,
-           const uint8_t *__restrict__ mtfrank, uint16_t *__restrict__ mtfv,
-           uint32_t *__restrict__ freq_out) {
-  const uint32_t b = blockIdx.x;
-  const uint32_t n = meta[b].n;
-  if (n == 0) return;
-  const uint32_t off = lbz_slot_off(g, b);
-  const uint8_t *src = bwt + off;
-  const uint8_t *rk = mtfrank + off;
-  uint16_t *out = mtfv + off;
+#define EMIT_PARTS 8u
+
+__device__ __forceinline__ void emit_part_range(uint32_t n, uint32_t part, uint32_t &lo, uint32_t &hi) {
+  const uint32_t ntiles = (n + EMIT_TILE - 1) / EMIT_TILE;
+  const uint32_t tpp = (ntiles + EMIT_PARTS - 1) / EMIT_PARTS;
+  lo = min(part * tpp * EMIT_TILE, n);
+  hi = min((part + 1) * tpp * EMIT_TILE, n);
+}
+
+// Walk positions [lo, hi) of a block: zero runs -> RUNA/RUNB digits, other
+// positions -> rank+1.  WRITE = false only counts the emitted symbols (first
+// pass, to learn where each part starts in the output); WRITE = true emits them
+// and accumulates the histogram.  `carry_nz` = last position before lo whose
+// rank is not zero (-1 if none), `m` = output index at lo.
+template <bool WRITE>
+__device__ uint32_t emit_walk(const uint8_t *__restrict__ src, const uint8_t *__restrict__ rk, uint16_t *__restrict__ out,
+                              uint32_t n, uint32_t lo, uint32_t hi, bool first_is_zero, int carry_nz, uint32_t m,
+                              uint32_t *s_freq, uint32_t *ws, int *wsi) {
   const uint32_t tid = threadIdx.x;
-
-  __shared__ uint32_t s_freq[LBZ_MAX_ALPHA + 2];
-  __shared__ uint32_t ws[40];
-  __shared__ int wsi[40];
-  __shared__ uint32_t s_first_dense;
-  for (uint32_t i = tid; i < LBZ_MAX_ALPHA + 2; i += EMIT_THREADS) s_freq[i] = 0;
-  uint32_t ninuse = 0;
-#pragma unroll
-  for (int w = 0; w < 8; w++) ninuse += __popc(meta[b].used[w]);
-  if (tid == 0) {
-    // dense number of the first BWT byte: position 0 is a zero iff it is 0
-    const uint32_t v = src[0];
-    uint32_t cnt = 0;
-    for (uint32_t w = 0; w < 8; w++) {
-      const uint32_t bits = meta[b].used[w];
-      if (w < (v >> 5)) cnt += __popc(bits);
-      else if (w == (v >> 5)) cnt += __popc(bits & ((1u << (v & 31u)) - 1u));
-    }
-    s_first_dense = cnt;
-  }
-  __syncthreads();
-  const bool first_is_zero = (s_first_dense == 0);
-
-  int carry_nz = -1;          // last non-zero-rank position so far
-  uint32_t m = 0;             // symbols written so far
-  for (uint32_t tb = 0; tb < n; tb += EMIT_TILE) {
+  for (uint32_t tb = lo; tb < hi; tb += EMIT_TILE) {
     const uint32_t p0 = tb + tid * EMIT_PER;
     uint32_t c[EMIT_PER + 2];   // bytes p0-1 .. p0+8
 #pragma unroll
@@ -335,7 +317,7 @@ k_mtf_emit(LbzGeom g, LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict
 #pragma unroll
     for (int j = 0; j < EMIT_PER; j++) {
       const uint32_t p = p0 + j;
-      if (p < n) {
+      if (p < hi) {
         const bool z = p ? (c[j + 1] == c[j]) : first_is_zero;
         if (z) zmask |= 1u << j; else last = (int)p;
       }
@@ -349,9 +331,9 @@ k_mtf_emit(LbzGeom g, LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict
     for (int j = 0; j < EMIT_PER; j++) {
       const uint32_t p = p0 + j;
       ec[j] = 0; kk[j] = 0;
-      if (p < n) {
+      if (p < hi) {
         if (zmask & (1u << j)) {
-          const bool runend = (p + 1 >= n) || (c[j + 2] != c[j + 1]);
+          const bool runend = (p + 1 >= n) || (c[j + 2] != c[j + 1]);   // a run is emitted where it ends
           if (runend) {
             const uint32_t k = (uint32_t)((int)p - lnz);
             kk[j] = k;
@@ -366,47 +348,113 @@ k_mtf_emit(LbzGeom g, LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict
     }
     uint32_t tot;
     uint32_t o = m + cta_excl_sum(sum, ws, &tot);
+    if (WRITE) {
 #pragma unroll
-    for (int j = 0; j < EMIT_PER; j++) {
-      const uint32_t p = p0 + j;
-      if (p < n && ec[j]) {
-        if (zmask & (1u << j)) {
-          const uint32_t v = kk[j] + 1u, nd = ec[j];
-          for (uint32_t d = 0; d < nd; d++) out[o + d] = (uint16_t)((v >> d) & 1u);
-          const uint32_t ones = __popc(v & ((1u << nd) - 1u));
-          if (ones) atomicAdd(&s_freq[1], ones);
-          if (nd - ones) atomicAdd(&s_freq[0], nd - ones);
-        } else {
-          const uint32_t sym = (uint32_t)rk[p] + 1u;
-          out[o] = (uint16_t)sym;
-          atomicAdd(&s_freq[sym], 1u);
+      for (int j = 0; j < EMIT_PER; j++) {
+        const uint32_t p = p0 + j;
+        if (p < hi && ec[j]) {
+          if (zmask & (1u << j)) {
+            const uint32_t v = kk[j] + 1u, nd = ec[j];
+            for (uint32_t d = 0; d < nd; d++) out[o + d] = (uint16_t)((v >> d) & 1u);
+            const uint32_t ones = __popc(v & ((1u << nd) - 1u));
+            if (ones) atomicAdd(&s_freq[1], ones);
+            if (nd - ones) atomicAdd(&s_freq[0], nd - ones);
+          } else {
+            const uint32_t sym = (uint32_t)rk[p] + 1u;
+            out[o] = (uint16_t)sym;
+            atomicAdd(&s_freq[sym], 1u);
+          }
+          o += ec[j];
         }
-        o += ec[j];
       }
     }
     m += tot;
     carry_nz = max(carry_nz, tmax);
   }
+  return m;
+}
+
+// Last position before `lo` whose symbol differs from its predecessor (-1 if none):
+// the start of the zero run that may reach into this part.
+__device__ int emit_find_carry(const uint8_t *__restrict__ src, uint32_t lo, bool first_is_zero, int *wsi) {
+  int found = -1;
+  for (int64_t top = (int64_t)lo; top > 0 && found < 0; top -= EMIT_THREADS) {
+    const int64_t p = top - 1 - threadIdx.x;
+    int cand = -1;
+    if (p >= 0) {
+      const bool z = p ? (src[p] == src[p - 1]) : first_is_zero;
+      if (!z) cand = (int)p;
+    }
+    int tmax;
+    (void)cta_excl_max(cand, -1, wsi, &tmax);
+    found = tmax;
+  }
+  return found;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(EMIT_THREADS, 1)
+k_mtf_emit(LbzGeom g, LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ bwt,
+           const uint8_t *__restrict__ mtfrank, uint16_t *__restrict__ mtfv,
+           uint32_t *__restrict__ freq_out, uint32_t *__restrict__ part_count) {
+  const uint32_t b = blockIdx.y, part = blockIdx.x;
+  const uint32_t n = meta[b].n;
+  if (n == 0) return;
+  uint32_t lo, hi;
+  emit_part_range(n, part, lo, hi);
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint8_t *src = bwt + off;
+  uint16_t *out = mtfv + off;
+  const uint32_t tid = threadIdx.x;
+
+  __shared__ uint32_t s_freq[LBZ_MAX_ALPHA + 2];
+  __shared__ uint32_t ws[40];
+  __shared__ int wsi[40];
+  __shared__ uint32_t s_first_dense;
+  for (uint32_t i = tid; i < LBZ_MAX_ALPHA + 2; i += EMIT_THREADS) s_freq[i] = 0;
+  if (!WRITE && part == 0)
+    for (uint32_t i = tid; i < 260; i += EMIT_THREADS) freq_out[b * 260 + i] = 0;
+  if (tid == 0) s_first_dense = dense_of(meta[b].used, src[0]);   // position 0 is a zero iff it is symbol 0
   __syncthreads();
-  const uint32_t eob = ninuse + 1u, as = ninuse + 2u;
-  const uint32_t nm = m + 1u;
-  const uint32_t padded = ((nm + LBZ_GROUP - 1) / LBZ_GROUP) * LBZ_GROUP;
-  if (tid == 0) { out[m] = (uint16_t)eob; s_freq[eob] = 1; }
-  if (tid >= 1 && m + tid < padded) out[m + tid] = (uint16_t)as;      // group padding (encode.c:1034)
+  const bool first_is_zero = (s_first_dense == 0);
+  if (lo >= hi) {
+    if (!WRITE && tid == 0) part_count[b * EMIT_PARTS + part] = 0;
+    return;
+  }
+  const int carry_nz = emit_find_carry(src, lo, first_is_zero, wsi);
+  uint32_t m0 = 0;
+  if (WRITE) for (uint32_t q = 0; q < part; q++) m0 += part_count[b * EMIT_PARTS + q];
+  const uint32_t m = emit_walk<WRITE>(src, mtfrank + off, out, n, lo, hi, first_is_zero, carry_nz, m0, s_freq, ws, wsi);
+  if (!WRITE) {
+    if (tid == 0) part_count[b * EMIT_PARTS + part] = m;
+    return;
+  }
   __syncthreads();
-  for (uint32_t i = tid; i < 260; i += EMIT_THREADS) freq_out[b * 260 + i] = (i < LBZ_MAX_ALPHA + 1) ? s_freq[i] : 0u;
-  if (tid == 0) { meta[b].nmtf = nm; meta[b].alpha_size = as; }
+  for (uint32_t i = tid; i < LBZ_MAX_ALPHA + 1; i += EMIT_THREADS)
+    if (s_freq[i]) atomicAdd(&freq_out[b * 260 + i], s_freq[i]);
+  if (hi == n) {                                          // the part that holds the end of the block
+    uint32_t ninuse = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) ninuse += __popc(meta[b].used[w]);
+    const uint32_t eob = ninuse + 1u, as = ninuse + 2u;
+    const uint32_t nm = m + 1u;
+    const uint32_t padded = ((nm + LBZ_GROUP - 1) / LBZ_GROUP) * LBZ_GROUP;
+    if (tid == 0) { out[m] = (uint16_t)eob; atomicAdd(&freq_out[b * 260 + eob], 1u); }
+    if (tid >= 1 && m + tid < padded) out[m + tid] = (uint16_t)as;      // group padding (encode.c:1034)
+    if (tid == 0) { meta[b].nmtf = nm; meta[b].alpha_size = as; }
+  }
 }
 
 extern "C" uint32_t lbz_mtf_parts() { return MTF_PARTS; }
 
 extern "C" int lbz_launch_mtf(const LbzGeom *g, LbzBlockMeta *d_meta, const uint8_t *d_bwt, uint8_t *d_mtfrank,
-                              uint16_t *d_mtfv, uint32_t *d_freq, int *d_parttab, cudaStream_t st) {
+                              uint16_t *d_mtfv, uint32_t *d_freq, int *d_parttab, uint32_t *d_emitcnt, cudaStream_t st) {
   const uint32_t nb = 2 * g->nchunks;
   if (nb == 0) return 0;
   k_mtf_parttab<<<dim3(MTF_PARTS, nb), MTF_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_parttab);
   k_mtf_ranks<<<dim3(MTF_PARTS, nb), MTF_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_parttab);
-  k_mtf_emit<<<nb, EMIT_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_mtfv, d_freq);
+  k_mtf_emit<false><<<dim3(EMIT_PARTS, nb), EMIT_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_mtfv, d_freq, d_emitcnt);
+  k_mtf_emit<true><<<dim3(EMIT_PARTS, nb), EMIT_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_mtfv, d_freq, d_emitcnt);
   LBZ_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
