@@ -336,7 +336,7 @@ def run_ours(a):
                 "api": "lbz_compress_chunks (pinned host in/out)"},
         "gpu_launches": int(rd["launches"]),
         "clocks": rd["clocks"],
-        "roofline": {"bound": "hbm", "kernel": "k_radix_pass<u32> (one LSD pass of the rotation sort, 8 per batch)",
+        "roofline": {"bound": "hbm", "kernel": "k_text_pass (one LSD pass of the initial rotation sort, 8 per batch)",
                      "achieved": round(k0_gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(k0_gbs / hbm_peak, 4),
                      "traffic": None, "peak_kind": peak_kind,
                      "bytes_per_launch": int(k0_bytes), "avg_launch_ms": round(k0_avg_ms, 4)},

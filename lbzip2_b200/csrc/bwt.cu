@@ -243,6 +243,142 @@ k_radix_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   }
 }
 
+// The eight passes of the initial sort, specialised: (key, index) travel as one
+// 8-byte pair (one 64-bit load/store per element instead of two 32-bit ones).
+//   MODE 0: pair read from `src`
+//   MODE 1: index read from `src`, key = the four leading text bytes of that rotation
+//           (pass 5: bytes 0..3 replace bytes 4..7 as the carried key)
+//   MODE 2: first pass: index = position, key = text bytes 4..7 (no input arrays)
+//   LAST  : last pass: only the index is written (to `sa`), the key is dropped
+struct TextSmem {
+  uint2 spair[512 * 8];
+  uint32_t wcnt[16][256];
+  uint32_t dstart[256];
+  uint32_t delta[256];
+  uint32_t ws[40];
+};
+
+template <int MODE, int LAST>
+__global__ void __launch_bounds__(512, 2)
+k_text_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+            const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
+            uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
+            uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err) {
+  extern __shared__ __align__(16) unsigned char radix_smem_raw[];
+  TextSmem &S = *reinterpret_cast<TextSmem *>(radix_smem_raw);
+  constexpr int THREADS = 512, ITEMS = 8, NW = 16;
+  constexpr uint32_t RTILE = THREADS * ITEMS;
+  const uint32_t rtiles = g.S1 / RTILE;
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
+  const uint32_t cnt = meta[b].n;
+  const uint32_t tbase = tile * RTILE;
+  if (tbase >= cnt) return;
+  const uint32_t n = cnt;
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint32_t tile_cnt = min(RTILE, cnt - tbase);
+  for (uint32_t i = threadIdx.x; i < NW * 256; i += THREADS) (&S.wcnt[0][0])[i] = 0;
+  __syncthreads();
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t lt = lanemask_lt();
+  uint32_t val[ITEMS], key[ITEMS], rd[ITEMS];
+
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
+    const uint32_t idx = tbase + warp * (32 * ITEMS) + it * 32 + lane;
+    const bool valid = idx < cnt;
+    rd[it] = valid ? 0x80000000u : 0u;
+    if (MODE == 2) {
+      val[it] = idx; key[it] = 0;
+    } else {
+      const uint2 pr = valid ? src[off + idx] : make_uint2(0u, 0u);
+      key[it] = pr.x; val[it] = pr.y;
+    }
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) key[it] = rd[it] ? text_key4(T + off, val[it], n) : 0u;
+  }
+  if (MODE == 2) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) key[it] = rd[it] ? text_key4(T + off, wrap_add(val[it], 4u, n), n) : 0u;
+  }
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
+    const bool valid = rd[it] != 0;
+    const uint32_t digit = valid ? ((key[it] >> shift) & 0xFFu) : 0x100u;
+    const uint32_t mask = __match_any_sync(0xffffffffu, digit);
+    uint32_t base = 0;
+    if (valid) base = S.wcnt[warp][digit];
+    __syncwarp();
+    if (valid && (mask & lt) == 0) S.wcnt[warp][digit] = base + __popc(mask);
+    __syncwarp();
+    rd[it] |= (digit << 16) | (base + __popc(mask & lt));
+  }
+  __syncthreads();
+  const uint32_t d = threadIdx.x;
+  uint32_t total = 0;
+  uint32_t *mine = tstat + ((size_t)b * rtiles + tile) * 256 + (d & 255u);
+  const uint32_t ep = (epoch << 20) & TS_EPOCH_MASK;
+  if (d < 256) {
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      const uint32_t c = S.wcnt[w][d];
+      S.wcnt[w][d] = total;
+      total += c;
+    }
+    st_volatile_u32(mine, (tile == 0 ? TS_FLAG_PREFIX : TS_FLAG_AGG) | ep | total);
+  }
+  uint32_t tsum;
+  const uint32_t dst0 = cta_excl_sum(total, S.ws, &tsum);
+  if (d < 256) S.dstart[d] = dst0;
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
+    if (rd[it] & 0x80000000u) {
+      const uint32_t digit = (rd[it] >> 16) & 0xFFu;
+      const uint32_t slot = S.dstart[digit] + S.wcnt[warp][digit] + (rd[it] & 0xFFFFu);
+      S.spair[slot] = make_uint2(key[it], val[it]);
+    }
+  }
+  if (d < 256) {
+    uint32_t excl = 0;
+    if (tile != 0) {
+      const uint32_t *look = mine - 256;
+      uint32_t spins = 0;
+      for (;;) {
+        const uint32_t sw = ld_volatile_u32(look);
+        if ((sw & TS_EPOCH_MASK) != ep || (sw >> 30) == 0u) {
+          if (++spins > TS_SPIN_LIMIT) { *err = 1u; break; }
+          __nanosleep(40);
+          continue;
+        }
+        excl += sw & TS_VALUE_MASK;
+        if (sw & TS_FLAG_PREFIX) break;
+        look -= 256;
+      }
+      st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total) & TS_VALUE_MASK));
+    }
+    S.delta[d] = gbase[(size_t)b * 256 + d] + excl - dst0;
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < tile_cnt; i += THREADS) {
+    const uint2 pr = S.spair[i];
+    const uint32_t o = S.delta[(pr.x >> shift) & 0xFFu] + i;
+    if (LAST) sa_out[off + o] = pr.y; else dst[off + o] = pr;
+  }
+}
+
+template <int MODE, int LAST>
+static int launch_text_pass(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
+                            const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
+                            uint32_t shift, uint32_t epoch, uint32_t *err) {
+  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass<MODE, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem)));
+  k_text_pass<MODE, LAST><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
+                                                                                  shift, epoch, err);
+  return 0;
+}
+
 // Digit bases of the text passes: every pass of the initial sort sees the same
 // multiset of digits (each rotation index occurs once, so the digits at any
 // depth are the bytes of the block), hence one byte histogram per block serves
@@ -318,6 +454,20 @@ __device__ __forceinline__ void list_sel(const LbzBlockMeta &m, uint32_t sel, ui
   if (sel == 0) { base = 0; cnt = m.us; } else { base = m.lbase; cnt = m.ul; }
 }
 
+// Distance from bit x back to the nearest set bit at or before x (0..31), or 32 if
+// none within 32 bits; distance forward to the nearest set bit after x (1..32), or
+// 33 if none.  `bits` is a shared-memory bitmask, x >= 32 and x + 32 in range.
+__device__ __forceinline__ uint32_t win_back(const uint32_t *bits, uint32_t x) {
+  const uint32_t wi = x >> 5, bi = x & 31u;
+  const uint32_t t = (bi == 31u) ? bits[wi] : __funnelshift_r(bits[wi - 1], bits[wi], bi + 1u);
+  return t ? (uint32_t)__clz(t) : 32u;
+}
+__device__ __forceinline__ uint32_t win_fwd(const uint32_t *bits, uint32_t x) {
+  const uint32_t wi = x >> 5, bi = x & 31u;
+  const uint32_t u = (bi == 31u) ? bits[wi + 1] : __funnelshift_r(bits[wi], bits[wi + 1], bi + 1u);
+  return u ? (uint32_t)__ffs(u) : 33u;
+}
+
 // Tile-parallel pass A: head flags of a tile (bit 0) plus the size class of every
 // tied rotation's group (bit 1: the group has <= SMALL_GROUP members), numbers of
 // small/large tied rotations, last head position.  Per-tile aggregates replace a
@@ -335,6 +485,7 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   // flags of positions tbase-HALO .. tbase+LBZ_TILE+HALO ; index = p - tbase + HALO
   __shared__ __align__(16) uint8_t sflag[HALO + LBZ_TILE + HALO + 16];
+  __shared__ uint32_t sbits[(HALO + LBZ_TILE + HALO) / 32 + 2];
   __shared__ uint32_t ws[40];
   __shared__ int wsi[40];
 #pragma unroll 2
@@ -344,12 +495,14 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
     uint64_t k = 0;
     if (valid) k = text_key(Tb, sa[off + p], n);
     uint64_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
+    bool hd = true;                                      // end of block acts as a head
     if (valid) {
       if (lane == 0) kprev = p ? text_key(Tb, sa[off + p - 1], n) : ~k;
-      sflag[HALO + p - tbase] = (p == 0) || (k != kprev);
-    } else {
-      sflag[HALO + p - tbase] = 1;                       // end of block acts as a head
+      hd = (p == 0) || (k != kprev);
     }
+    sflag[HALO + p - tbase] = hd;
+    const uint32_t bw = __ballot_sync(0xffffffffu, hd);
+    if (lane == 0) sbits[1 + ((p - tbase) >> 5)] = bw;   // HALO == 32: the tile starts at word 1
   }
   if (tid < 2 * HALO + 1) {                              // halo flags on both sides (+ the tile's end flag)
     const int64_t p = (tid < HALO) ? (int64_t)tbase - HALO + tid : (int64_t)tbase + LBZ_TILE + (tid - HALO);
@@ -358,6 +511,13 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
     if (p > 0 && p < (int64_t)n)
       f = text_key(Tb, sa[off + (uint32_t)p], n) != text_key(Tb, sa[off + (uint32_t)p - 1], n);
     sflag[x] = f;
+  }
+  __syncthreads();
+  if (tid < 2) {                                         // pack the two halo words from the flag bytes
+    const uint32_t base = tid ? HALO + LBZ_TILE : 0u;
+    uint32_t wv = 0;
+    for (uint32_t q = 0; q < 32; q++) wv |= (uint32_t)(sflag[base + q] & 1u) << q;
+    sbits[tid ? (HALO + LBZ_TILE) / 32 : 0] = wv;
   }
   __syncthreads();
   const bool tracking = BWT_K < n;
@@ -374,11 +534,8 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
       const bool f = fb, f1 = sflag[x + 1] & 1u;
       if (f) last = (int)p;
       if (tracking && !(f && f1)) {
-        uint32_t back = 0, fwd = 1;
-        while (back < SMALL_GROUP && !(sflag[x - back] & 1u)) back++;
-        while (fwd <= SMALL_GROUP && !(sflag[x + fwd] & 1u)) fwd++;
-        const bool is_small = (back < SMALL_GROUP) && (fwd <= SMALL_GROUP) && (back + fwd <= SMALL_GROUP);
-        if (is_small) { small++; fb |= 2u; } else large++;
+        const uint32_t back = win_back(sbits, x), fwd = win_fwd(sbits, x);   // group = [x-back, x+fwd)
+        if (back + fwd <= SMALL_GROUP) { small++; fb |= 2u; } else large++;
       }
     } else {
       fb = 1;
@@ -550,26 +707,39 @@ k_small_sort(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *_
   const uint32_t tbase = blockIdx.x * LBZ_TILE;
   if (tbase >= U) return;
   const uint32_t off = lbz_slot_off(g, b);
-  __shared__ uint64_t sk[SMALL_GROUP + LBZ_TILE + SMALL_GROUP];
+  constexpr uint32_t W = SMALL_GROUP + LBZ_TILE + SMALL_GROUP;        // staged window, SMALL_GROUP == 32
+  __shared__ uint32_t srk[W];                                          // rank part of the key (20 bits)
+  __shared__ uint32_t sbits[W / 32 + 2];                               // group-head bits
   const int64_t lo = (int64_t)tbase - SMALL_GROUP;
-  for (uint32_t x = threadIdx.x; x < SMALL_GROUP + LBZ_TILE + SMALL_GROUP; x += 256) {
-    const int64_t j = lo + x;
-    sk[x] = (j >= 0 && j < (int64_t)U) ? kin[off + j] : ~0ull;       // ~0: belongs to no group
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t x0 = 0; x0 < W; x0 += 256) {                           // W is a multiple of 32: whole warps
+    const uint32_t x = x0 + threadIdx.x;
+    bool hd = true;
+    if (x < W) {
+      const int64_t j = lo + x;
+      if (j >= 0 && j < (int64_t)U) {
+        const uint64_t k = kin[off + j];
+        srk[x] = (uint32_t)k & 0xFFFFFu;
+        hd = (j == 0) || ((kin[off + j - 1] >> 20) != (k >> 20));
+      } else {
+        srk[x] = 0;
+      }
+    }
+    const uint32_t bw = __ballot_sync(0xffffffffu, hd);
+    if (lane == 0 && x < W) sbits[x >> 5] = bw;
   }
+  if (threadIdx.x == 0) sbits[W / 32] = 0xFFFFFFFFu;
   __syncthreads();
   for (uint32_t q = threadIdx.x; q < LBZ_TILE; q += 256) {
     const uint32_t j = tbase + q;
     if (j >= U) break;
     const uint32_t x = SMALL_GROUP + q;
-    const uint64_t k = sk[x];
-    const uint64_t grp = k >> 20;
-    uint32_t hs = x, he = x + 1;
-    while (hs > 0 && (sk[hs - 1] >> 20) == grp) hs--;                   // group extent (<= SMALL_GROUP members)
-    while (he < SMALL_GROUP + LBZ_TILE + SMALL_GROUP && (sk[he] >> 20) == grp) he++;
+    const uint32_t hs = x - win_back(sbits, x), he = x + win_fwd(sbits, x);   // group = [hs, he), <= 32 members
+    const uint32_t k = srk[x];
     uint32_t r = 0;
-    for (uint32_t y = hs; y < he; y++) r += (sk[y] < k) || (sk[y] == k && y < x);
+    for (uint32_t y = hs; y < he; y++) { const uint32_t ky = srk[y]; r += (ky < k) || (ky == k && y < x); }
     const uint32_t dst = (uint32_t)(lo + hs) + r;                       // list index of the sorted place
-    kout[off + dst] = k;
+    kout[off + dst] = kin[off + j];
     vout[off + dst] = vin[off + j];
   }
 }
@@ -801,27 +971,29 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   const dim3 grid_full(g.tiles1, nb);
 
   k_bwt_prep<<<(nb + 255) / 256, 256, 0, st>>>(d_meta, nb, B.counters);
-  uint32_t *k32a = reinterpret_cast<uint32_t *>(B.key), *k32b = reinterpret_cast<uint32_t *>(B.key2);
-  k_sa_init<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, k32a);
-  nl += 3 + BWT_K + 2;
+  uint2 *pa = reinterpret_cast<uint2 *>(B.key), *pb = reinterpret_cast<uint2 *>(B.key2);
+  nl += 2 + BWT_K + 2;
   static int cfg = -1;
   if (cfg < 0) { const char *ev = getenv("LBZ_RADIX_CFG"); cfg = ev ? (atoi(ev) != 0) : 1; }
 
-  uint32_t *src = B.sa, *dst = B.sa2;
   k_text_bases<<<nb, 1024, 0, st>>>(g, d_meta, B.T, B.gbase);
   // LSD over text bytes 7..0 of every rotation: bytes 4..7 travel as a 32-bit key
-  // for the first four passes, bytes 0..3 are fetched once by the fifth pass.
+  // next to the index for the first four passes, bytes 0..3 are fetched once by
+  // the fifth pass; the first pass builds its pairs from the text, the last one
+  // writes the order only.
   for (uint32_t p = 0; p < BWT_K; p++) {
     if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * p], st);
     const uint32_t ep = next_epoch(B, nb, g, st);
-    if (launch_radix<uint32_t, 0>(cfg, p == 4, g.S1, nb, st, g, d_meta, B.T, src, dst, k32a, k32b, B.tstat,
-                                  B.gbase, 256u, (p == 4) ? 0u : 8u * (p & 3u), ep, B.counters + 3)) return -1;
+    const uint32_t shift = 8u * (p & 3u);
+    int rc;
+    if (p == 0) rc = launch_text_pass<2, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, B.counters + 3);
+    else if (p == 4) rc = launch_text_pass<1, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, B.counters + 3);
+    else if (p == BWT_K - 1) rc = launch_text_pass<0, 1>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, B.counters + 3);
+    else rc = launch_text_pass<0, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, B.counters + 3);
+    if (rc) return -1;
     if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * p + 1], st);
-    { uint32_t *t = src; src = dst; dst = t; }
-    { uint32_t *t = k32a; k32a = k32b; k32b = t; }
+    { uint2 *t = pa; pa = pb; pb = t; }
   }
-  // BWT_K is even, so the order is back in B.sa
-  B.sa = src; B.sa2 = dst;
   TileAgg *agg = reinterpret_cast<TileAgg *>(B.agg);
   k_heads_agg<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.head, agg);
   k_ranks_compact<<<grid_full, 256, 0, st>>>(g, d_meta, B, agg);

@@ -281,11 +281,11 @@ k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
 }
 
 // ---------------------------------------------------------------------------
-#define EMIT_THREADS 1024
+#define EMIT_THREADS 256
 #define EMIT_PER 8
 #define EMIT_TILE (EMIT_THREADS * EMIT_PER)
 
-#define EMIT_PARTS 8u
+#define EMIT_PARTS 16u
 
 __device__ __forceinline__ void emit_part_range(uint32_t n, uint32_t part, uint32_t &lo, uint32_t &hi) {
   const uint32_t ntiles = (n + EMIT_TILE - 1) / EMIT_TILE;
@@ -393,7 +393,7 @@ __device__ int emit_find_carry(const uint8_t *__restrict__ src, uint32_t lo, boo
 }
 
 template <bool WRITE>
-__global__ void __launch_bounds__(EMIT_THREADS, 1)
+__global__ void __launch_bounds__(EMIT_THREADS)
 k_mtf_emit(LbzGeom g, LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ bwt,
            const uint8_t *__restrict__ mtfrank, uint16_t *__restrict__ mtfv,
            uint32_t *__restrict__ freq_out, uint32_t *__restrict__ part_count) {
