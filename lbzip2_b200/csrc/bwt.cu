@@ -800,7 +800,7 @@ k_round_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__
 __global__ void __launch_bounds__(256)
 k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
               const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval,
-              const uint32_t *__restrict__ pos, uint32_t *__restrict__ nval,
+              const uint32_t *__restrict__ pos, const uint32_t *__restrict__ ogs, uint32_t *__restrict__ nval,
               uint32_t *__restrict__ npos, uint32_t *__restrict__ ngs,
               const TileAgg *__restrict__ agg, uint32_t h, uint32_t sel) {
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
@@ -862,7 +862,9 @@ k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
     const uint32_t j = j0 + q;
     if (j < U) {
       B.sa[sa_off + myp[q]] = myv[q];
-      B.rank[sa_off + myv[q]] = mygs[q];
+      // the rank only changes for members that left the first subgroup of their old
+      // group (ogs = group start before this round, same for the whole old group)
+      if (mygs[q] != ogs[off + j]) B.rank[sa_off + myv[q]] = mygs[q];
       if (unsmask & (1u << q)) {
         npos[off + o] = myp[q];
         nval[off + o] = myv[q];
@@ -1034,7 +1036,7 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     // sorted (key,val) of both lists now in ksrc/vsrc; compacted survivors go to vdst/pdst/gdst
     for (uint32_t sel = 0; sel < 2; sel++) {
       k_round_agg<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h, sel);
-      k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h, sel);
+      k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, gsrc, vdst, pdst, gdst, agg, h, sel);
     }
     { uint32_t *t = vsrc; vsrc = vdst; vdst = t; }
     { uint32_t *t = psrc; psrc = pdst; pdst = t; }

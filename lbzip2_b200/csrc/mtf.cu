@@ -349,23 +349,33 @@ __device__ uint32_t emit_walk(const uint8_t *__restrict__ src, const uint8_t *__
     uint32_t tot;
     uint32_t o = m + cta_excl_sum(sum, ws, &tot);
     if (WRITE) {
+      uint32_t runa = 0, runb = 0;
 #pragma unroll
       for (int j = 0; j < EMIT_PER; j++) {
         const uint32_t p = p0 + j;
+        uint32_t sym = 0xFFFFu;                           // histogram key of this lane (none)
         if (p < hi && ec[j]) {
           if (zmask & (1u << j)) {
             const uint32_t v = kk[j] + 1u, nd = ec[j];
             for (uint32_t d = 0; d < nd; d++) out[o + d] = (uint16_t)((v >> d) & 1u);
             const uint32_t ones = __popc(v & ((1u << nd) - 1u));
-            if (ones) atomicAdd(&s_freq[1], ones);
-            if (nd - ones) atomicAdd(&s_freq[0], nd - ones);
+            runb += ones; runa += nd - ones;
           } else {
-            const uint32_t sym = (uint32_t)rk[p] + 1u;
+            sym = (uint32_t)rk[p] + 1u;
             out[o] = (uint16_t)sym;
-            atomicAdd(&s_freq[sym], 1u);
           }
           o += ec[j];
         }
+        // warp-aggregated histogram update: MTF ranks are heavily skewed, so many
+        // lanes hit the same bin
+        const uint32_t mm = __match_any_sync(0xffffffffu, sym);
+        if (sym != 0xFFFFu && (mm & lanemask_lt()) == 0) atomicAdd(&s_freq[sym], (uint32_t)__popc(mm));
+      }
+      runa = __reduce_add_sync(0xffffffffu, runa);
+      runb = __reduce_add_sync(0xffffffffu, runb);
+      if ((threadIdx.x & 31u) == 0) {
+        if (runa) atomicAdd(&s_freq[0], runa);
+        if (runb) atomicAdd(&s_freq[1], runb);
       }
     }
     m += tot;
