@@ -800,7 +800,7 @@ k_round_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__
 __global__ void __launch_bounds__(256)
 k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
               const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval,
-              const uint32_t *__restrict__ pos, const uint32_t *__restrict__ ogs, uint32_t *__restrict__ nval,
+              const uint32_t *__restrict__ pos, uint32_t *__restrict__ nval,
               uint32_t *__restrict__ npos, uint32_t *__restrict__ ngs,
               const TileAgg *__restrict__ agg, uint32_t h, uint32_t sel) {
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
@@ -862,9 +862,7 @@ k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
     const uint32_t j = j0 + q;
     if (j < U) {
       B.sa[sa_off + myp[q]] = myv[q];
-      // the rank only changes for members that left the first subgroup of their old
-      // group (ogs = group start before this round, same for the whole old group)
-      if (mygs[q] != ogs[off + j]) B.rank[sa_off + myv[q]] = mygs[q];
+      B.rank[sa_off + myv[q]] = mygs[q];
       if (unsmask & (1u << q)) {
         npos[off + o] = myp[q];
         nval[off + o] = myv[q];
@@ -890,15 +888,31 @@ k_bwt_final(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B) {
   const uint32_t tbase = blockIdx.x * LBZ_TILE;
   if (tbase >= n) return;
   const uint32_t off = lbz_slot_off(g, b);
-  const uint32_t r0 = B.rank[off];
-  uint32_t ties = 0;
   for (uint32_t p = tbase + threadIdx.x; p < min(tbase + LBZ_TILE, n); p += 256) {
     const uint32_t v = B.sa[off + p];
     B.bwt[off + p] = B.T[off + (v ? v - 1 : n - 1)];
-    ties += (B.rank[off + v] == r0);
   }
-  if (ties) atomicAdd(&meta[b].tie_count, ties);
-  if (blockIdx.x == 0 && threadIdx.x == 0) meta[b].bwt_idx = r0;
+}
+
+// Primary index = first position of rotation 0's group; the group is larger than
+// one only for exactly periodic blocks.  Its members are contiguous in the order,
+// so the size is found by walking forward from the group start (one CTA per block).
+__global__ void __launch_bounds__(256)
+k_primary_index(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t n = meta[b].n;
+  if (n == 0) return;
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint32_t r0 = B.rank[off];
+  uint32_t total = 0;
+  for (uint32_t base = r0; base < n; base += 256) {
+    const uint32_t p = base + threadIdx.x;
+    const bool same = (p < n) && (B.rank[off + B.sa[off + p]] == r0);
+    const uint32_t c = (uint32_t)__syncthreads_count(same);
+    total += c;
+    if (c < 256) break;
+  }
+  if (threadIdx.x == 0) { meta[b].bwt_idx = r0; meta[b].tie_count = total; }
 }
 
 __global__ void k_bwt_prep(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, uint32_t *__restrict__ counters) {
@@ -1036,7 +1050,7 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     // sorted (key,val) of both lists now in ksrc/vsrc; compacted survivors go to vdst/pdst/gdst
     for (uint32_t sel = 0; sel < 2; sel++) {
       k_round_agg<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h, sel);
-      k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, gsrc, vdst, pdst, gdst, agg, h, sel);
+      k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h, sel);
     }
     { uint32_t *t = vsrc; vsrc = vdst; vdst = t; }
     { uint32_t *t = psrc; psrc = pdst; pdst = t; }
@@ -1046,8 +1060,9 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   }
   if (tm && tm->enabled) cudaEventRecord(tm->stage[3], st);
   k_bwt_final<<<grid_full, 256, 0, st>>>(g, d_meta, B);
+  k_primary_index<<<nb, 256, 0, st>>>(g, d_meta, B);
   LBZ_CUDA_CHECK(cudaGetLastError());
-  nl += 1;
+  nl += 2;
   if (rounds_out) *rounds_out = rounds;
   if (launches) *launches += nl;
   return 0;
