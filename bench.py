@@ -297,7 +297,13 @@ def run_ours(a):
         else:
             tables, payloads = rd["last"][4]
             stream = sharding.assemble_stream(level, tables, payloads, world)
-            verified["gathered_stream_decodes"] = len(bz2.decompress(stream)) == world * nbytes
+            # expected plain text: chunk i of the job is chunk i // world of rank i % world
+            per_rank = [data] + [make_input(a.workload, nbytes, r) for r in range(1, world)]
+            parts = []
+            for i in range(world * nchunks):
+                r, k = i % world, i // world
+                parts.append(per_rank[r][k * mbs:(k + 1) * mbs])
+            verified["gathered_stream_roundtrip"] = bz2.decompress(stream) == b"".join(parts)
         verified["periodic_blocks"] = sum(1 for r in recs if r.tie_count > 1)
 
     if rank != 0:
