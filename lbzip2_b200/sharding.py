@@ -61,10 +61,16 @@ def assemble_stream(level, tables, payloads, world):
     return b"".join(parts)
 
 
-def gather_blocks(table, payload, dist, device):
+def to_host(tables, payloads):
+    """Device tensors of gather_blocks(..., to_host=False) -> numpy arrays."""
+    return [t.cpu().numpy() for t in tables], [p.cpu().numpy() for p in payloads]
+
+
+def gather_blocks(table, payload, dist, device, to_host=True):
     """Gather (table, payload) of every rank to rank 0 with torch.distributed.
     `payload` is a uint8 torch tensor on `device` (stays on the GPU for NCCL).
-    Returns (tables, payloads) lists of numpy arrays on rank 0, else (None, None)."""
+    Returns (tables, payloads) on rank 0 -- numpy arrays, or tensors that stay on
+    `device` when to_host is False -- else (None, None)."""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     sizes = torch.tensor([table.shape[0], payload.numel()], dtype=torch.int64, device=device)
@@ -83,8 +89,10 @@ def gather_blocks(table, payload, dist, device):
         pl = [torch.zeros_like(ppad) for _ in range(world)]
         dist.gather(tpad, tl, dst=0)
         dist.gather(ppad, pl, dst=0)          # NCCL over NVLink when tensors are on GPUs
-        tables = [tl[r][: all_sizes[r][0]].cpu().numpy() for r in range(world)]
-        payloads = [pl[r][: all_sizes[r][1]].cpu().numpy() for r in range(world)]
+        tables = [tl[r][: all_sizes[r][0]] for r in range(world)]
+        payloads = [pl[r][: all_sizes[r][1]] for r in range(world)]
+        if to_host:
+            return [t.cpu().numpy() for t in tables], [p.cpu().numpy() for p in payloads]
         return tables, payloads
     dist.gather(tpad, None, dst=0)
     dist.gather(ppad, None, dst=0)
