@@ -42,6 +42,9 @@ struct BwtBuffers {
   void *agg;              // per-tile aggregates of the rank/refine passes
   uint32_t *counters;     // [0] = max unsorted over blocks, [1] = total unsorted, [3] = error flag
   uint32_t *epoch;        // host-side pass counter (status-word epoch)
+  int hints;              // use L2 residency hints for the rank scatter/gather
+  void (*on_sorted)(void *);  // host callback after the initial sort has been enqueued (lane staggering)
+  void *on_sorted_arg;
   uint8_t *bwt;           // output last column
 };
 
@@ -620,14 +623,17 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
       v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
     }
 #pragma unroll
+    const uint64_t pol = l2_policy_evict_last();
     for (int j = 0; j < 16; j++) {
       if (p0 + j < n) {
-        B.rank[off + v[j]] = starts[j];
+        if (B.hints) st_u32_hint(&B.rank[off + v[j]], starts[j], pol); else B.rank[off + v[j]] = starts[j];
         if ((smask | lmask) & (1u << j)) {
           const uint32_t o = (smask & (1u << j)) ? os++ : ol++;
-          B.pos[off + o] = p0 + j;
-          B.val[off + o] = v[j];
-          B.gs[off + o] = starts[j];
+          if (B.hints) {
+            __stcs(&B.pos[off + o], p0 + j); __stcs(&B.val[off + o], v[j]); __stcs(&B.gs[off + o], starts[j]);
+          } else {
+            B.pos[off + o] = p0 + j; B.val[off + o] = v[j]; B.gs[off + o] = starts[j];
+          }
         }
       }
     }
@@ -649,7 +655,8 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
 __global__ void __launch_bounds__(256)
 k_round_keys(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint32_t *__restrict__ val,
              const uint32_t *__restrict__ gs, const uint32_t *__restrict__ rank,
-             uint64_t *__restrict__ key, uint32_t *__restrict__ khist, uint32_t h, uint32_t sel) {
+             uint64_t *__restrict__ key, uint32_t *__restrict__ khist, uint32_t h, uint32_t sel, int hints) {
+  const uint64_t pol = l2_policy_evict_last();
   const uint32_t b = blockIdx.y;
   uint32_t lb, U;
   list_sel(meta[b], sel, lb, U);
@@ -672,7 +679,7 @@ k_round_keys(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint32_t *_
   }
 #pragma unroll
   for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
-    if (v[it] != 0xFFFFFFFFu) v[it] = rank[off + wrap_add(v[it], h, n)];
+    if (v[it] != 0xFFFFFFFFu) v[it] = hints ? ld_u32_hint(&rank[off + wrap_add(v[it], h, n)], pol) : rank[off + wrap_add(v[it], h, n)];
   }
 #pragma unroll
   for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
@@ -857,16 +864,16 @@ k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
   }
   uint32_t tot;
   uint32_t o = carry_cnt + cta_excl_sum(__popc(unsmask), ws, &tot);
+  const uint64_t pol = l2_policy_evict_last();
 #pragma unroll
   for (int q = 0; q < 16; q++) {
     const uint32_t j = j0 + q;
     if (j < U) {
       B.sa[sa_off + myp[q]] = myv[q];
-      B.rank[sa_off + myv[q]] = mygs[q];
+      if (B.hints) st_u32_hint(&B.rank[sa_off + myv[q]], mygs[q], pol); else B.rank[sa_off + myv[q]] = mygs[q];
       if (unsmask & (1u << q)) {
-        npos[off + o] = myp[q];
-        nval[off + o] = myv[q];
-        ngs[off + o] = mygs[q];
+        if (B.hints) { __stcs(&npos[off + o], myp[q]); __stcs(&nval[off + o], myv[q]); __stcs(&ngs[off + o], mygs[q]); }
+        else { npos[off + o] = myp[q]; nval[off + o] = myv[q]; ngs[off + o] = mygs[q]; }
         o++;
       }
     }
@@ -1015,6 +1022,7 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   k_ranks_compact<<<grid_full, 256, 0, st>>>(g, d_meta, B, agg);
   LBZ_CUDA_CHECK(cudaGetLastError());
   if (tm && tm->enabled) cudaEventRecord(tm->stage[2], st);
+  if (B.on_sorted) B.on_sorted(B.on_sorted_arg);
 
   uint32_t rounds = 0;
   uint32_t h = BWT_K;
@@ -1035,8 +1043,8 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     nl += 5 + 5 + 4;
     const dim3 grid_u((maxU + LBZ_TILE - 1) / LBZ_TILE, nb);
     k_round_commit<<<(nb * 5 * 256 + 255) / 256, 256, 0, st>>>(d_meta, nb, B.counters, B.khist);
-    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h, 0u);
-    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h, 1u);
+    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h, 0u, B.hints);
+    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h, 1u, B.hints);
     k_key_bases<<<nb, 256, 0, st>>>(d_meta, B.khist, B.gbase + (size_t)nb * 256);
     // list S: one local pass straight into the buffers the five radix passes of list L end in
     k_small_sort<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, vsrc, kdst, vdst);

@@ -29,6 +29,9 @@ struct BwtBuffers {           // must match bwt.cu
   void *agg;
   uint32_t *counters;
   uint32_t *epoch;
+  int hints;
+  void (*on_sorted)(void *);
+  void *on_sorted_arg;
   uint8_t *bwt;
 };
 
@@ -90,6 +93,9 @@ struct lbz_engine {
   // streams, driven by two host threads, so that the latency-bound kernels of one
   // lane (rle1, huffman, round bookkeeping, host round trips) overlap with the
   // bandwidth-bound sort passes of the other, and H2D/D2H overlap with compute.
+  int hints = 0;
+  void (*on_sorted)(void *) = nullptr;  // set per call by the two-lane driver
+  void *on_sorted_arg = nullptr;
   lbz_engine *sib = nullptr;
   uint32_t total_chunks = 0;           // capacity of the whole engine (both lanes)
   cudaEvent_t ev_done = nullptr;
@@ -169,6 +175,7 @@ static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   rc |= cudaEventCreate(&e->ev_call[0]) != cudaSuccess;
   rc |= cudaEventCreate(&e->ev_call[1]) != cudaSuccess;
   e->tm.enabled = 1;
+  { const char *hv = getenv("LBZ_CACHEHINT"); e->hints = hv ? atoi(hv) : 0; }
   rc |= dev_alloc(e, &e->d_in, (size_t)e->max_chunks * g.mbs);
   rc |= dev_alloc(e, &e->d_chunk_len, e->max_chunks);
   rc |= dev_alloc(e, &e->d_T, E);
@@ -282,6 +289,7 @@ static BwtBuffers bwt_buffers(lbz_engine *e) {
   B.pos = e->d_pos; B.pos2 = e->d_pos2; B.gs = e->d_gs; B.gs2 = e->d_gs2;
   B.tstat = e->d_tstat; B.gbase = e->d_gbase; B.khist = e->d_khist; B.agg = e->d_agg;
   B.counters = e->d_counters; B.epoch = &e->epoch; B.bwt = e->d_bwt;
+  B.hints = e->hints; B.on_sorted = e->on_sorted; B.on_sorted_arg = e->on_sorted_arg;
   return B;
 }
 
@@ -403,13 +411,18 @@ static void reset_call_stats(lbz_engine *e) {
 
 // One lane: chunk table, (H2D,) all stages.  Leaves the packed blocks in
 // e->d_packed (or dst_dev if given) and the block records in e->h_meta.
-static int lane_run(lbz_engine *e, const uint8_t *src, bool src_on_device, size_t len, uint8_t *dst_dev, size_t *total) {
+static int lane_run(lbz_engine *e, const uint8_t *src, bool src_on_device, size_t len, uint8_t *dst_dev, size_t *total,
+                    std::future<void> *after_upload = nullptr, cudaEvent_t wait_ev = nullptr) {
   if (cudaSetDevice(e->device) != cudaSuccess) return -1;
   if (set_chunks(e, len)) return -1;
   const uint8_t *d_in = src;
   if (!src_on_device) {
     ENG_CHECK(cudaMemcpyAsync(e->d_in, src, len, cudaMemcpyHostToDevice, e->st));
     d_in = e->d_in;
+  }
+  if (after_upload) {                       // staggered lane: upload first, then wait for the other lane's sort
+    after_upload->wait();
+    cudaStreamWaitEvent(e->st, wait_ev, 0);
   }
   return run_pipeline(e, d_in, dst_dev ? dst_dev : e->d_packed, total);
 }
@@ -438,8 +451,21 @@ static int super_batch(lbz_engine *e, const uint8_t *src, size_t len, uint8_t *d
   std::future<long long> totA_f = totA_p.get_future();
   int rcA = 0, rcB = 0;
   size_t totA = 0, totB = 0;
+  // optional staggering: lane B's kernels wait until lane A has finished its
+  // initial sort, so that B's rle1/sort overlap A's latency-bound tail
+  static int stagger = -1;
+  if (stagger < 0) { const char *sv = getenv("LBZ_STAGGER"); stagger = sv ? atoi(sv) : 0; }
+  std::promise<void> sorted_p;
+  std::future<void> sorted_f = sorted_p.get_future();
+  struct Sig { std::promise<void> *p; bool done; } sig{&sorted_p, false};
+  if (stagger) {
+    A->on_sorted = [](void *a) { Sig *s = static_cast<Sig *>(a); if (!s->done) { s->done = true; s->p->set_value(); } };
+    A->on_sorted_arg = &sig;
+  }
   std::thread tb([&]() {
-    rcB = lane_run(B, src + lenA, on_device, lenB, nullptr, &totB);
+    // staggered: B uploads, then waits until A has enqueued its initial sort and lets
+    // its stream wait for that point on the device
+    rcB = lane_run(B, src + lenA, on_device, lenB, nullptr, &totB, stagger ? &sorted_f : nullptr, A->tm.stage[2]);
     const long long ta = totA_f.get();
     if (rcB == 0 && ta >= 0) {
       if ((size_t)ta + totB > dst_cap) { rcB = -2; return; }
@@ -449,6 +475,10 @@ static int super_batch(lbz_engine *e, const uint8_t *src, size_t len, uint8_t *d
     }
   });
   rcA = lane_run(A, src, on_device, lenA, nullptr, &totA);
+  if (stagger) {
+    A->on_sorted = nullptr;
+    if (!sig.done) { sig.done = true; sorted_p.set_value(); }     // A failed before the sort: release B
+  }
   totA_p.set_value(rcA == 0 ? (long long)totA : -1LL);
   if (rcA == 0) {
     if (totA > dst_cap) rcA = -2;

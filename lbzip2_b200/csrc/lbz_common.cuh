@@ -106,6 +106,23 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
   return r;
 }
 
+// L2 residency hints.  Randomly scattered 4-byte updates (the rank array) should
+// stay in L2 until their sector is complete; data that is streamed through once
+// should not push them out.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_u32_hint(uint32_t *p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_u32_hint(const uint32_t *p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 // Inclusive warp scan (sum).
 __device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v) {
 #pragma unroll

@@ -78,6 +78,95 @@ k_mtf_parttab(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *_
   if (tid < 256) parttab[((size_t)b * MTF_PARTS + part) * 256 + tid] = s_tab[tid];
 }
 
+// One batch of up to 32 events (lane i = i-th event, `valid` lanes only).  All
+// ranks of the batch are computed together from the batch-local occurrence
+// structure:
+//   * symbol seen earlier in the batch (at lane j): rank = number of distinct
+//     symbols in lanes (j, i) = lanes there that are the last occurrence before i
+//     of their symbol ("alive" mask, a prefix-OR of predecessor bits);
+//   * first occurrence in the batch: rank = P[sym] + number of distinct batch
+//     symbols seen earlier whose old place was behind it;
+// then the position table P (P[sym] = place of sym in the recency list) is advanced
+// past the batch in one step: symbols outside the batch slide back by the number of
+// batch symbols that were behind them (256-bit occupancy bitmap SB + suffix counts).
+__device__ __forceinline__ void mtf_batch(uint8_t *P, uint32_t *SB, uint32_t csym, bool valid, uint32_t pos,
+                                          uint8_t *__restrict__ dstr, uint32_t ltm, uint32_t gtm, uint32_t lane) {
+  const uint32_t c = valid ? csym : (0x100u + lane);                   // invalid lanes: unique dummies
+  const uint32_t m = __match_any_sync(0xffffffffu, c);
+  const uint32_t prevm = m & ltm;
+  const bool hasprev = prevm != 0;
+  const uint32_t j = hasprev ? (31u - __clz(prevm)) : 0u;
+  const bool isfirst = valid && !hasprev;
+  const bool islast = valid && ((m & gtm) == 0);
+  const uint32_t Pc = valid ? (uint32_t)P[c] : 0u;
+  uint32_t dead = hasprev ? (1u << j) : 0u;                            // lanes whose symbol occurs again at or before this lane
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, dead, o);
+    if (lane >= (uint32_t)o) dead |= t;
+  }
+  const uint32_t alive = ltm & ~dead;
+  const uint32_t fm = __ballot_sync(0xffffffffu, isfirst);
+  uint32_t cnt = 0;
+  for (uint32_t mm = fm; mm; mm &= mm - 1) {
+    const uint32_t t = __ffs(mm) - 1;
+    const uint32_t pt = __shfl_sync(0xffffffffu, Pc, t);
+    cnt += (t < lane) && (pt > Pc);
+  }
+  const uint32_t rank = hasprev ? __popc((alive >> j) >> 1) : (Pc + cnt);
+  if (valid) dstr[pos] = (uint8_t)rank;
+
+  const uint32_t lastm = __ballot_sync(0xffffffffu, islast);
+  uint32_t Bw[8];
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const uint32_t contrib = (isfirst && (Pc >> 5) == (uint32_t)w) ? (1u << (Pc & 31u)) : 0u;
+    Bw[w] = __reduce_or_sync(0xffffffffu, contrib);
+  }
+  if (lane < 8) {
+    uint32_t mine = 0, suffix = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      if ((uint32_t)w == lane) mine = Bw[w];
+      if ((uint32_t)w > lane) suffix += __popc(Bw[w]);
+    }
+    SB[lane] = mine;
+    SB[8 + lane] = suffix;
+  }
+  __syncwarp();
+  {
+    uint2 pv = *reinterpret_cast<uint2 *>(&P[lane * 8]);
+    uint32_t wv[2] = {pv.x, pv.y};
+#pragma unroll
+    for (int h2 = 0; h2 < 2; h2++) {
+      uint32_t out = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t pk = (wv[h2] >> (8 * k)) & 0xFFu;
+        const uint32_t w = pk >> 5;
+        const uint32_t above = __popc((SB[w] >> (pk & 31u)) >> 1) + SB[8 + w];
+        out |= ((pk + above) & 0xFFu) << (8 * k);
+      }
+      wv[h2] = out;
+    }
+    pv.x = wv[0]; pv.y = wv[1];
+    *reinterpret_cast<uint2 *>(&P[lane * 8]) = pv;
+  }
+  __syncwarp();
+  if (islast) P[c] = (uint8_t)__popc(lastm & gtm);
+  __syncwarp();
+}
+
+struct MtfSmem {
+  int tab[MTF_WARPS][256];
+  int carry[256];
+  uint32_t B[MTF_WARPS][16];
+  uint32_t qpos[MTF_WARPS][64];
+  uint16_t qsym[MTF_WARPS][64];
+  __align__(8) uint8_t P[MTF_WARPS][256];
+  uint8_t dense[256];
+};
+
 __global__ void __launch_bounds__(MTF_THREADS, 2)
 k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ bwt,
             uint8_t *__restrict__ mtfrank, const int *__restrict__ parttab) {
@@ -92,11 +181,15 @@ k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
   uint8_t *dstr = mtfrank + off;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-  __shared__ int s_tab[MTF_WARPS][256];
-  __shared__ int s_carry[256];
-  __shared__ uint8_t s_dense[256];
-  __shared__ __align__(8) uint8_t s_P[MTF_WARPS][256];
-  __shared__ uint32_t s_B[MTF_WARPS][16];
+  extern __shared__ __align__(16) unsigned char mtf_smem_raw[];
+  MtfSmem &SM = *reinterpret_cast<MtfSmem *>(mtf_smem_raw);
+  int (*s_tab)[256] = SM.tab;
+  int *s_carry = SM.carry;
+  uint8_t *s_dense = SM.dense;
+  uint8_t (*s_P)[256] = SM.P;
+  uint32_t (*s_B)[16] = SM.B;
+  uint16_t (*s_qsym)[64] = SM.qsym;
+  uint32_t (*s_qpos)[64] = SM.qpos;
 
   if (tid < 256) {
     // dense renumbering of the used byte values (encode.c:340-355)
@@ -184,99 +277,45 @@ k_mtf_ranks(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
     for (int r = 0; r < 8; r++) P[e[r] & 0xFFu] = (uint8_t)(lane * 8 + r);
     __syncwarp();
 
-    // Walk the segment 32 positions at a time; all 32 ranks of a chunk are
-    // computed together from the chunk-local occurrence structure:
-    //   * symbol seen earlier in the chunk (at lane j): rank = number of distinct
-    //     symbols in lanes (j, i) = lanes there that are the last occurrence
-    //     before i of their symbol ("alive" mask, a prefix-OR of predecessor bits);
-    //   * first occurrence in the chunk: rank = P[sym] + number of distinct chunk
-    //     symbols seen earlier whose old place was behind it;
-    // then the table is advanced past the chunk in one step (symbols outside the
-    // chunk slide back by the number of chunk symbols that were behind them).
+    // Walk the segment.  Positions equal to their predecessor have rank 0 and leave
+    // the list alone, so only the others ("events") are queued (per warp, in shared
+    // memory) and processed 32 at a time by mtf_batch().
     const uint32_t ltm = lanemask_lt();
     const uint32_t gtm = ~ltm & ~(1u << lane);
+    uint16_t *qsym = s_qsym[warp];
+    uint32_t *qpos = s_qpos[warp];
+    uint32_t qn = 0;                                                   // queued events (warp-uniform)
     uint32_t prev_sym = segbase ? s_dense[src[segbase - 1]] : 0u;    // list front before the segment
     for (uint32_t q = 0; q < MTF_SEG / 32; q++) {
       if (segbase + q * 32 >= part_hi) break;
       const uint32_t p = segbase + q * 32 + lane;
       const bool valid = p < part_hi;
-      const uint32_t c = valid ? s_dense[src[p]] : (0x100u + lane);  // invalid lanes: unique dummies
+      const uint32_t c = valid ? s_dense[src[p]] : 0xFFFFu;
       uint32_t pc = __shfl_up_sync(0xffffffffu, c, 1);
       if (lane == 0) pc = prev_sym;
       const bool ev = valid && (c != pc);
       const uint32_t evmask = __ballot_sync(0xffffffffu, ev);
       prev_sym = __shfl_sync(0xffffffffu, c, 31);
-      if (evmask == 0) {                                             // pure run: ranks 0, list unchanged
-        if (valid) dstr[p] = 0;
-        continue;
+      if (valid && !ev) dstr[p] = 0;
+      if (ev) {
+        const uint32_t slot = qn + __popc(evmask & ltm);
+        qsym[slot] = (uint16_t)c;
+        qpos[slot] = p;
       }
-      const uint32_t m = __match_any_sync(0xffffffffu, c);
-      const uint32_t prevm = m & ltm;
-      const bool hasprev = prevm != 0;
-      const uint32_t j = hasprev ? (31u - __clz(prevm)) : 0u;
-      const bool isfirst = valid && !hasprev;
-      const bool islast = valid && ((m & gtm) == 0);
-      const uint32_t Pc = valid ? (uint32_t)P[c] : 0u;
-      // dead = lanes whose symbol occurs again at or before this lane
-      uint32_t dead = hasprev ? (1u << j) : 0u;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, dead, o);
-        if (lane >= (uint32_t)o) dead |= t;
-      }
-      const uint32_t alive = ltm & ~dead;
-      const uint32_t fm = __ballot_sync(0xffffffffu, isfirst);
-      uint32_t cnt = 0;
-      for (uint32_t mm = fm; mm; mm &= mm - 1) {
-        const uint32_t t = __ffs(mm) - 1;
-        const uint32_t pt = __shfl_sync(0xffffffffu, Pc, t);
-        cnt += (t < lane) && (pt > Pc);
-      }
-      const uint32_t rank = hasprev ? __popc((alive >> j) >> 1) : (Pc + cnt);
-      if (valid) dstr[p] = ev ? (uint8_t)rank : (uint8_t)0;
-
-      // ---- advance the table past the chunk ----
-      const uint32_t lastm = __ballot_sync(0xffffffffu, islast);
-      uint32_t Bw[8];
-#pragma unroll
-      for (int w = 0; w < 8; w++) {
-        const uint32_t contrib = (isfirst && (Pc >> 5) == (uint32_t)w) ? (1u << (Pc & 31u)) : 0u;
-        Bw[w] = __reduce_or_sync(0xffffffffu, contrib);
-      }
-      uint32_t *SB = s_B[warp];
-      if (lane < 8) {
-        uint32_t mine = 0, suffix = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) {
-          if ((uint32_t)w == lane) mine = Bw[w];
-          if ((uint32_t)w > lane) suffix += __popc(Bw[w]);
-        }
-        SB[lane] = mine;
-        SB[8 + lane] = suffix;
-      }
+      qn += __popc(evmask);
       __syncwarp();
-      {
-        uint2 pv = *reinterpret_cast<uint2 *>(&P[lane * 8]);
-        uint32_t wv[2] = {pv.x, pv.y};
-#pragma unroll
-        for (int h2 = 0; h2 < 2; h2++) {
-          uint32_t out = 0;
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint32_t pk = (wv[h2] >> (8 * k)) & 0xFFu;
-            const uint32_t w = pk >> 5;
-            const uint32_t above = __popc((SB[w] >> (pk & 31u)) >> 1) + SB[8 + w];
-            out |= ((pk + above) & 0xFFu) << (8 * k);
-          }
-          wv[h2] = out;
-        }
-        pv.x = wv[0]; pv.y = wv[1];
-        *reinterpret_cast<uint2 *>(&P[lane * 8]) = pv;
+      if (qn >= 32) {
+        mtf_batch(P, s_B[warp], qsym[lane], true, qpos[lane], dstr, ltm, gtm, lane);
+        const uint32_t rest = qn - 32;                               // < 32: move the tail to the front
+        const uint16_t ts = (lane < rest) ? qsym[32 + lane] : (uint16_t)0;
+        const uint32_t tp = (lane < rest) ? qpos[32 + lane] : 0u;
+        __syncwarp();
+        if (lane < rest) { qsym[lane] = ts; qpos[lane] = tp; }
+        qn = rest;
+        __syncwarp();
       }
-      __syncwarp();
-      if (islast) P[c] = (uint8_t)__popc(lastm & gtm);
-      __syncwarp();
     }
+    if (qn) mtf_batch(P, s_B[warp], (lane < qn) ? (uint32_t)qsym[lane] : 0u, lane < qn, qpos[lane < qn ? lane : 0], dstr, ltm, gtm, lane);
   }
 }
 
@@ -462,7 +501,8 @@ extern "C" int lbz_launch_mtf(const LbzGeom *g, LbzBlockMeta *d_meta, const uint
   const uint32_t nb = 2 * g->nchunks;
   if (nb == 0) return 0;
   k_mtf_parttab<<<dim3(MTF_PARTS, nb), MTF_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_parttab);
-  k_mtf_ranks<<<dim3(MTF_PARTS, nb), MTF_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_parttab);
+  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_mtf_ranks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MtfSmem)));
+  k_mtf_ranks<<<dim3(MTF_PARTS, nb), MTF_THREADS, sizeof(MtfSmem), st>>>(*g, d_meta, d_bwt, d_mtfrank, d_parttab);
   k_mtf_emit<false><<<dim3(EMIT_PARTS, nb), EMIT_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_mtfv, d_freq, d_emitcnt);
   k_mtf_emit<true><<<dim3(EMIT_PARTS, nb), EMIT_THREADS, 0, st>>>(*g, d_meta, d_bwt, d_mtfrank, d_mtfv, d_freq, d_emitcnt);
   LBZ_CUDA_CHECK(cudaGetLastError());
