@@ -261,8 +261,8 @@ struct TextSmem {
   uint32_t ws[40];
 };
 
-template <int MODE, int LAST>
-__global__ void __launch_bounds__(512, 2)
+template <int MODE, int LAST, int MINB>
+__global__ void __launch_bounds__(512, MINB)
 k_text_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
             const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
             uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
@@ -372,14 +372,23 @@ k_text_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
   }
 }
 
+template <int MODE, int LAST, int MINB>
+static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
+                            const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
+                            uint32_t shift, uint32_t epoch, uint32_t *err) {
+  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem)));
+  k_text_pass<MODE, LAST, MINB><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
+                                                                                        shift, epoch, err);
+  return 0;
+}
 template <int MODE, int LAST>
 static int launch_text_pass(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
                             const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
                             uint32_t shift, uint32_t epoch, uint32_t *err) {
-  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass<MODE, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem)));
-  k_text_pass<MODE, LAST><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
-                                                                                  shift, epoch, err);
-  return 0;
+  static int minb = 0;
+  if (!minb) { const char *ev = getenv("LBZ_TP_MINB"); minb = (ev && atoi(ev) == 3) ? 3 : 2; }
+  if (minb == 3) return launch_text_pass_b<MODE, LAST, 3>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err);
+  return launch_text_pass_b<MODE, LAST, 2>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err);
 }
 
 // Digit bases of the text passes: every pass of the initial sort sees the same
