@@ -386,7 +386,7 @@ static int launch_text_pass(uint32_t nb, cudaStream_t st, const LbzGeom &g, cons
                             const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
                             uint32_t shift, uint32_t epoch, uint32_t *err) {
   static int minb = 0;
-  if (!minb) { const char *ev = getenv("LBZ_TP_MINB"); minb = (ev && atoi(ev) == 3) ? 3 : 2; }
+  if (!minb) { const char *ev = getenv("LBZ_TP_MINB"); minb = (ev && atoi(ev) == 2) ? 2 : 3; }
   if (minb == 3) return launch_text_pass_b<MODE, LAST, 3>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err);
   return launch_text_pass_b<MODE, LAST, 2>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err);
 }
