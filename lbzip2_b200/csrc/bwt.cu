@@ -565,7 +565,7 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
 
 // Tile-parallel pass B: ranks (rank[i] = first position of i's group) and
 // compaction of the members of tied groups into the two round lists.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const TileAgg *__restrict__ agg) {
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
   const uint32_t n = meta[b].n;
@@ -813,7 +813,7 @@ k_round_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
               const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval,
               const uint32_t *__restrict__ pos, uint32_t *__restrict__ nval,

@@ -18,6 +18,8 @@
 #include <vector>
 #include <thread>
 #include <future>
+#include <chrono>
+#include <deque>
 
 struct BwtBuffers {           // must match bwt.cu
   const uint8_t *T;
@@ -685,6 +687,8 @@ void pool_release(int i) {
 }
 }  // namespace
 
+namespace { int batch_limit(); }
+
 #define ENC_MAGIC 0xB2005A42u
 
 extern "C" size_t encoder_alloc_size(unsigned long max_block_size) {
@@ -746,12 +750,116 @@ extern "C" int collect(struct encoder_state *s, const uint8_t *buf, size_t *buf_
     if (m.n >= mbs) { s->rle_state = -1; full = 1; }   // n' == mbs is only reached by a filling write
   }
   *buf_sz = avail - (s->raw_len - old_len);
+  if (batch_limit() > 0) { pool_release(s->pool_slot); s->pool_slot = -1; }   // encode() goes through the batcher
   return full;
 }
 
+// ---- cross-thread batching of encode() ---------------------------------------
+// The scheduler calls encode() from many worker threads, one block each
+// (src/compress.c:113).  One block cannot fill a B200, so the calls are pooled:
+// every encode() queues its staged raw bytes and sleeps; a dispatcher thread
+// collects what arrives within a short window (or until the batch engine is
+// full), pushes the whole batch through the kernels at once and wakes the
+// callers.  `LBZIP2_B200_BATCH` = chunks per batch (default 64, 0 = no batching:
+// every block runs alone on its pooled context).
+namespace {
+struct BReq { encoder_state *s; int rc; bool done; };
+struct Batcher {
+  std::mutex mu;
+  std::condition_variable cv_req, cv_done;
+  std::deque<BReq *> q;
+  bool running = false;
+  int max_batch = -1;
+  lbz_engine *eng[10] = {};
+} g_batch;
+
+int run_batch(int level, std::vector<BReq *> &batch) {
+  lbz_engine *&e = g_batch.eng[level];
+  if (!e) {
+    e = engine_create_one(g_pool.device, level, g_batch.max_batch);
+    if (!e) return -1;
+    e->total_chunks = (uint32_t)g_batch.max_batch;
+  }
+  if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+  const uint32_t k = (uint32_t)batch.size();
+  const size_t mbs = e->g.mbs;
+  e->g.nchunks = k;
+  for (uint32_t c = 0; c < k; c++) {
+    encoder_state *s = batch[c]->s;
+    e->h_chunk_len[c] = s->raw_len;
+    ENG_CHECK(cudaMemcpyAsync(e->d_in + (size_t)c * mbs, s->staged, s->raw_len, cudaMemcpyHostToDevice, e->st));
+  }
+  ENG_CHECK(cudaMemcpyAsync(e->d_chunk_len, e->h_chunk_len, k * sizeof(uint32_t), cudaMemcpyHostToDevice, e->st));
+  size_t total = 0;
+  if (run_pipeline(e, e->d_in, e->d_packed, &total)) return -1;
+  size_t off = 0;
+  for (uint32_t c = 0; c < k; c++) {
+    encoder_state *s = batch[c]->s;
+    const LbzBlockMeta &m0 = e->h_meta[2 * c], &m1 = e->h_meta[2 * c + 1];
+    if (m0.raw_len != s->raw_len || m1.n != 0) { batch[c]->rc = -1; off += m0.out_len + (m1.n ? m1.out_len : 0); continue; }
+    // the raw bytes are no longer needed: the block's bytes take their place in the handle
+    ENG_CHECK(cudaMemcpyAsync(s->staged, e->d_packed + off, m0.out_len, cudaMemcpyDeviceToHost, e->st));
+    s->out_len = m0.out_len;
+    s->crc = m0.crc;
+    off += m0.out_len;
+  }
+  ENG_CHECK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+void batch_worker() {
+  std::unique_lock<std::mutex> lk(g_batch.mu);
+  for (;;) {
+    g_batch.cv_req.wait(lk, [] { return !g_batch.q.empty(); });
+    // gathering window: wait a little for more blocks unless the batch is already full
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(400);
+    while ((int)g_batch.q.size() < g_batch.max_batch &&
+           g_batch.cv_req.wait_until(lk, deadline) != std::cv_status::timeout) {}
+    const int level = (int)(g_batch.q.front()->s->max_block_size / 100000);
+    std::vector<BReq *> batch;
+    for (auto it = g_batch.q.begin(); it != g_batch.q.end() && (int)batch.size() < g_batch.max_batch;) {
+      if ((int)((*it)->s->max_block_size / 100000) == level) { batch.push_back(*it); it = g_batch.q.erase(it); }
+      else ++it;
+    }
+    lk.unlock();
+    const int rc = run_batch(level, batch);
+    lk.lock();
+    for (BReq *r : batch) { if (rc) r->rc = rc; r->done = true; }
+    g_batch.cv_done.notify_all();
+  }
+}
+
+int batch_limit() {
+  std::lock_guard<std::mutex> lk(g_batch.mu);
+  if (g_batch.max_batch < 0) {
+    const char *ev = getenv("LBZIP2_B200_BATCH");
+    g_batch.max_batch = ev ? atoi(ev) : 64;
+    if (g_batch.max_batch < 0) g_batch.max_batch = 0;
+    if (g_batch.max_batch > 1024) g_batch.max_batch = 1024;
+  }
+  return g_batch.max_batch;
+}
+}  // namespace
+
 extern "C" size_t encode(struct encoder_state *s, uint32_t *crc) {
   if (!s || s->magic != ENC_MAGIC) die("encode: state not initialised");
-  if (s->raw_len == 0 || s->pool_slot < 0) die("encode: empty block (src/encode.c:448)");
+  if (s->raw_len == 0) die("encode: empty block (src/encode.c:448)");
+  if (batch_limit() > 0) {
+    if (s->pool_slot >= 0) { pool_release(s->pool_slot); s->pool_slot = -1; }   // collect()'s context is no longer needed
+    BReq r{s, 0, false};
+    {
+      std::unique_lock<std::mutex> lk(g_batch.mu);
+      if (!g_batch.running) { g_batch.running = true; std::thread(batch_worker).detach(); }
+      g_batch.q.push_back(&r);
+      g_batch.cv_req.notify_one();
+      g_batch.cv_done.wait(lk, [&] { return r.done; });
+    }
+    if (r.rc) die("encode: batched kernel pipeline failed");
+    s->done = 2;                             // block bytes live in the handle
+    if (crc) *crc = s->crc;
+    return s->out_len;
+  }
+  if (s->pool_slot < 0) s->pool_slot = pool_acquire((int)(s->max_block_size / 100000));
   lbz_engine *e = g_pool.engines[s->pool_slot];
   // exactly the consumed bytes form this block; run every stage on them
   if (lbz_dbg_load(e, s->staged, s->raw_len)) die("encode: H2D failed");
@@ -772,8 +880,13 @@ extern "C" size_t encode(struct encoder_state *s, uint32_t *crc) {
 extern "C" void *transmit(struct encoder_state *s, void *buf) {
   if (!s || s->magic != ENC_MAGIC || !s->done) die("transmit: encode() has not run");
   if (!buf) die("transmit: NULL buffer is not supported by this build");
-  lbz_engine *e = g_pool.engines[s->pool_slot];
   const size_t bytes = ((size_t)s->out_len + 3) / 4 * 4;
+  if (s->done == 2) {
+    memcpy(buf, s->staged, s->out_len);
+    memset(static_cast<uint8_t *>(buf) + s->out_len, 0, bytes - s->out_len);
+    return buf;
+  }
+  lbz_engine *e = g_pool.engines[s->pool_slot];
   if (lbz_dbg_read(e, LBZ_AR_OUT, 0, buf, bytes)) die("transmit: D2H failed");
   pool_release(s->pool_slot);
   s->pool_slot = -1;
