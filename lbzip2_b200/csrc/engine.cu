@@ -637,7 +637,8 @@ struct Pool {
   int count = 0;
   int max_engines = 0;
   int device = 0;
-} g_pool;
+};
+Pool &g_pool = *new Pool;     // leaked on purpose (see Batcher)
 
 [[noreturn]] void die(const char *msg) {
   fprintf(stderr, "lbzip2_b200: fatal: %s\n", msg);
@@ -771,7 +772,11 @@ struct Batcher {
   bool running = false;
   int max_batch = -1;
   lbz_engine *eng[10] = {};
-} g_batch;
+};
+// Deliberately leaked: the dispatcher thread sleeps on these condition variables
+// for the life of the process, and destroying a condition variable that has a
+// waiter (static destruction at exit) blocks forever in glibc.
+Batcher &g_batch = *new Batcher;
 
 int run_batch(int level, std::vector<BReq *> &batch) {
   lbz_engine *&e = g_batch.eng[level];

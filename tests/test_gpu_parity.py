@@ -364,3 +364,35 @@ def test_reference_cli_drives_the_gpu_engine():
         assert got.returncode == 0 and got.stderr == b"", got.stderr[-500:]
         want = subprocess.run([cpu_cli, "-%d" % lv], input=data, stdout=subprocess.PIPE, check=True).stdout
         assert got.stdout == want
+
+
+def test_reference_shaped_api_from_many_threads():
+    """encode() calls from concurrent host threads are pooled into device batches
+    (engine.cu batch_worker); every block must still be the oracle's."""
+    import threading
+    L = lbzip2_b200.load_library()
+    mbs = 900000
+    inputs = [synth.text(mbs - 3000 - 97 * k, offset=20 + k) for k in range(24)] + [b"q" * 500_000, synth.random_bytes(300_000, seed=21)]
+    results = [None] * len(inputs)
+
+    def one(k):
+        raw = inputs[k]
+        st = C.create_string_buffer(L.encoder_alloc_size(mbs))
+        L.encoder_init(st, mbs, 8)
+        cbuf = C.create_string_buffer(raw, len(raw))
+        left = C.c_size_t(len(raw))
+        L.collect(st, cbuf, C.byref(left))
+        crc = C.c_uint32(0)
+        size = L.encode(st, C.byref(crc))
+        out = C.create_string_buffer((size + 3) // 4 * 4)
+        L.transmit(st, out)
+        results[k] = (len(raw) - left.value, out.raw[:size], crc.value)
+
+    ths = [threading.Thread(target=one, args=(k,)) for k in range(len(inputs))]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for k, raw in enumerate(inputs):
+        st = orclib.orc_block_stages(raw, mbs)
+        assert results[k][0] == st["consumed"], k
+        assert results[k][1] == st["bits"].tobytes(), k
+        assert results[k][2] == st["crc"], k
