@@ -1,20 +1,43 @@
 #!/bin/sh
-# Throughput of the UNMODIFIED reference CLI + scheduler driving the GPU engine through the
-# reference-shaped per-block API (oracle/_ref/lbzip2_gpu), next to the all-CPU reference binary.
+# CLI-level throughput on the GPU box, 1 GB of the benchmark text from /dev/shm to /dev/null:
+#   oracle/_ref/lbzip2        the unmodified reference, all host cores (pthread CPU path)
+#   oracle/_ref/lbzip2_gpu    unmodified reference host code + per-block API of libbz2b200.so
+#   oracle/_ref/lbzip2_b200   reference CLI/scheduler + our batch-aware task graph
+#                             (lbzip2_b200/host/compress_b200.c) + libbz2b200.so
+# and a byte comparison of the three outputs.  Usage: tools/cli_dropin_bench.sh [MB] [GPUS]
 set -e
 cd "$(dirname "$0")/.."
-python - <<'PY'
+MB=${1:-1000}
+GPUS=${2:-1}
+echo "host: $(nproc) online CPUs, cpu.max=$(cat /sys/fs/cgroup/cpu.max 2>/dev/null || echo n/a), $(grep -m1 'model name' /proc/cpuinfo | cut -d: -f2)"
+python - "$MB" <<'PY'
 import sys; sys.path.insert(0, "tests")
 import synth
-open("/dev/shm/lbz_cli_in.raw", "wb").write(synth.text(100_000_000) * 10)
+mb = int(sys.argv[1])
+base = synth.text(100_000_000)
+with open("/dev/shm/lbz_cli_in.raw", "wb") as f:
+    left = mb * 1_000_000
+    while left > 0:
+        f.write(base[:left]); left -= len(base)
 PY
-for n in 32 32 64; do
-  s=$(date +%s.%N)
-  LBZIP2_B200_CONTEXTS=64 oracle/_ref/lbzip2_gpu -9 -n$n -c /dev/shm/lbz_cli_in.raw > /dev/shm/lbz_cli_gpu.bz2
-  e=$(date +%s.%N)
-  echo "lbzip2_gpu -9 -n$n: $(python -c "print(round(1000/($e-$s),1))") MB/s"
+IN=/dev/shm/lbz_cli_in.raw
+t() { # label, command...
+  label=$1; shift
+  s=$(date +%s.%N); "$@"; e=$(date +%s.%N)
+  echo "$label: $(python -c "print(round($MB/($e-$s),1))") MB/s"
+}
+s=$(date +%s.%N); cat $IN > /dev/null; e=$(date +%s.%N)
+echo "cat (page cache read): $(python -c "print(round($MB/($e-$s),1))") MB/s"
+for cfg in "32 2 32" "32 3 64" "64 2 64" "16 4 64" "64 3 128"; do
+  set -- $cfg
+  t "lbzip2_b200 -9 -n$3 batch=$1 engines=$2 gpus=$GPUS" env LBZIP2_B200_BATCH=$1 LBZIP2_B200_ENGINES=$2 LBZIP2_B200_GPUS=$GPUS LBZIP2_B200_STATS=1 \
+     sh -c "oracle/_ref/lbzip2_b200 -9 -n$3 -c $IN > /dev/shm/lbz_cli_b200.bz2"
 done
-s=$(date +%s.%N); oracle/_ref/lbzip2 -9 -c /dev/shm/lbz_cli_in.raw > /dev/shm/lbz_cli_cpu.bz2; e=$(date +%s.%N)
-echo "lbzip2 (CPU, all cores) -9: $(python -c "print(round(1000/($e-$s),1))") MB/s"
-cmp /dev/shm/lbz_cli_gpu.bz2 /dev/shm/lbz_cli_cpu.bz2 && echo "outputs identical"
-rm -f /dev/shm/lbz_cli_in.raw /dev/shm/lbz_cli_gpu.bz2 /dev/shm/lbz_cli_cpu.bz2
+t "lbzip2_gpu  -9 -n64 (per-block API)" env LBZIP2_B200_CONTEXTS=64 sh -c "oracle/_ref/lbzip2_gpu -9 -n64 -c $IN > /dev/shm/lbz_cli_gpu.bz2"
+t "lbzip2 (CPU reference, all cores) -9" sh -c "oracle/_ref/lbzip2 -9 -c $IN > /dev/shm/lbz_cli_cpu.bz2"
+head -c 20000000 $IN > /dev/shm/lbz_cli_20.raw
+s=$(date +%s.%N); oracle/_ref/lbzip2 -9 -n1 -c /dev/shm/lbz_cli_20.raw > /dev/null; e=$(date +%s.%N)
+echo "lbzip2 (CPU reference, -n1, 20 MB): $(python -c "print(round(20/($e-$s),1))") MB/s"
+cmp /dev/shm/lbz_cli_b200.bz2 /dev/shm/lbz_cli_cpu.bz2 && echo "lbzip2_b200 output identical to the reference's"
+cmp /dev/shm/lbz_cli_gpu.bz2 /dev/shm/lbz_cli_cpu.bz2 && echo "lbzip2_gpu output identical to the reference's"
+rm -f /dev/shm/lbz_cli_in.raw /dev/shm/lbz_cli_20.raw /dev/shm/lbz_cli_gpu.bz2 /dev/shm/lbz_cli_cpu.bz2 /dev/shm/lbz_cli_b200.bz2
