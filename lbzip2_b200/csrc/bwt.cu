@@ -46,6 +46,7 @@ struct BwtBuffers {
   void (*on_sorted)(void *);  // host callback after the initial sort has been enqueued (lane staggering)
   void *on_sorted_arg;
   uint8_t *bwt;           // output last column
+  uint32_t K;             // bytes covered by the initial radix sort (5..8)
 };
 
 __device__ __forceinline__ uint32_t wrap_add(uint32_t v, uint32_t d, uint32_t n) {
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(512, MINB)
 k_text_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
             const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
             uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
-            uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err) {
+            uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff) {
   extern __shared__ __align__(16) unsigned char radix_smem_raw[];
   TextSmem &S = *reinterpret_cast<TextSmem *>(radix_smem_raw);
   constexpr int THREADS = 512, ITEMS = 8, NW = 16;
@@ -304,7 +305,7 @@ k_text_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
   }
   if (MODE == 2) {
 #pragma unroll
-    for (int it = 0; it < ITEMS; it++) key[it] = rd[it] ? text_key4(T + off, wrap_add(val[it], 4u, n), n) : 0u;
+    for (int it = 0; it < ITEMS; it++) key[it] = rd[it] ? text_key4(T + off, wrap_add(val[it], koff, n), n) : 0u;
   }
 #pragma unroll
   for (int it = 0; it < ITEMS; it++) {
@@ -375,20 +376,20 @@ k_text_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
 template <int MODE, int LAST, int MINB>
 static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
                             const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
-                            uint32_t shift, uint32_t epoch, uint32_t *err) {
+                            uint32_t shift, uint32_t epoch, uint32_t *err, uint32_t koff) {
   LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem)));
   k_text_pass<MODE, LAST, MINB><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
-                                                                                        shift, epoch, err);
+                                                                                        shift, epoch, err, koff);
   return 0;
 }
 template <int MODE, int LAST>
 static int launch_text_pass(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
                             const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
-                            uint32_t shift, uint32_t epoch, uint32_t *err) {
+                            uint32_t shift, uint32_t epoch, uint32_t *err, uint32_t koff) {
   static int minb = 0;
   if (!minb) { const char *ev = getenv("LBZ_TP_MINB"); minb = (ev && atoi(ev) == 2) ? 2 : 3; }
-  if (minb == 3) return launch_text_pass_b<MODE, LAST, 3>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err);
-  return launch_text_pass_b<MODE, LAST, 2>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err);
+  if (minb == 3) return launch_text_pass_b<MODE, LAST, 3>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff);
+  return launch_text_pass_b<MODE, LAST, 2>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff);
 }
 
 // Digit bases of the text passes: every pass of the initial sort sees the same
@@ -443,18 +444,19 @@ k_key_bases(const LbzBlockMeta *__restrict__ meta, const uint32_t *__restrict__ 
 // Group heads after the initial sort: head[p] = first BWT_K bytes of rotation
 // sa[p] differ from those of sa[p-1].  Keys are only compared for equality, so
 // the 8 bytes are fetched as three aligned words and funnel-shifted.
-__device__ __forceinline__ uint64_t text_key(const uint8_t *__restrict__ Tb, uint32_t v, uint32_t n) {
-  if (v + BWT_K <= n) {
+__device__ __forceinline__ uint64_t text_key(const uint8_t *__restrict__ Tb, uint32_t v, uint32_t n, uint32_t K) {
+  const uint64_t kmask = K >= 8u ? ~0ull : ((1ull << (8u * K)) - 1ull);    // byte d of the rotation sits at bits 8d
+  if (v + 8u <= n) {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(Tb + (v & ~3u));
     const uint32_t sh = 8u * (v & 3u);
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];      // slot capacity >= n + 64: in bounds
     const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
-    return ((uint64_t)x1 << 32) | x0;
+    return (((uint64_t)x1 << 32) | x0) & kmask;
   }
   uint64_t k = 0;
   uint32_t j = v;
 #pragma unroll
-  for (uint32_t d = 0; d < BWT_K; d++) { k |= (uint64_t)Tb[j] << (8 * d); if (++j >= n) j = 0; }
+  for (uint32_t d = 0; d < 8u; d++) { if (d < K) k |= (uint64_t)Tb[j] << (8 * d); if (++j >= n) j = 0; }
   return k;
 }
 
@@ -487,7 +489,7 @@ __device__ __forceinline__ uint32_t win_fwd(const uint32_t *bits, uint32_t x) {
 #define HALO 32u
 __global__ void __launch_bounds__(256)
 k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
-            const uint32_t *__restrict__ sa, uint8_t *__restrict__ head, TileAgg *__restrict__ agg) {
+            const uint32_t *__restrict__ sa, uint8_t *__restrict__ head, TileAgg *__restrict__ agg, uint32_t K) {
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
   const uint32_t n = meta[b].n;
   const uint32_t tbase = tile * LBZ_TILE;
@@ -505,11 +507,11 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
     const uint32_t p = tbase + it * 256 + tid;
     const bool valid = p < n;
     uint64_t k = 0;
-    if (valid) k = text_key(Tb, sa[off + p], n);
+    if (valid) k = text_key(Tb, sa[off + p], n, K);
     uint64_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
     bool hd = true;                                      // end of block acts as a head
     if (valid) {
-      if (lane == 0) kprev = p ? text_key(Tb, sa[off + p - 1], n) : ~k;
+      if (lane == 0) kprev = p ? text_key(Tb, sa[off + p - 1], n, K) : ~k;
       hd = (p == 0) || (k != kprev);
     }
     sflag[HALO + p - tbase] = hd;
@@ -521,7 +523,7 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
     const uint32_t x = (tid < HALO) ? tid : HALO + LBZ_TILE + (tid - HALO);
     uint8_t f = 1;
     if (p > 0 && p < (int64_t)n)
-      f = text_key(Tb, sa[off + (uint32_t)p], n) != text_key(Tb, sa[off + (uint32_t)p - 1], n);
+      f = text_key(Tb, sa[off + (uint32_t)p], n, K) != text_key(Tb, sa[off + (uint32_t)p - 1], n, K);
     sflag[x] = f;
   }
   __syncthreads();
@@ -532,7 +534,7 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
     sbits[tid ? (HALO + LBZ_TILE) / 32 : 0] = wv;
   }
   __syncthreads();
-  const bool tracking = BWT_K < n;
+  const bool tracking = K < n;
   const uint32_t q0 = tid * 16;
   uint32_t small = 0, large = 0;
   int last = -1;
@@ -608,7 +610,7 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
   int tmax;
   int st = cta_excl_max(last, -1, wsi, &tmax);
   st = max(st, carry_last);
-  const bool tracking = BWT_K < n;
+  const bool tracking = B.K < n;
   uint32_t smask = 0, lmask = 0;
   uint32_t starts[16];
 #pragma unroll
@@ -651,7 +653,7 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
     meta[b].us_next = total_s;                            // committed by k_round_commit
     meta[b].ul_next = total_l;
     meta[b].lbase = lbase;
-    meta[b].depth = BWT_K;
+    meta[b].depth = B.K;
     atomicMax(&B.counters[0], max(total_s, total_l));
     atomicAdd(&B.counters[1], total_s + total_l);
   }
@@ -878,8 +880,12 @@ k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
   for (int q = 0; q < 16; q++) {
     const uint32_t j = j0 + q;
     if (j < U) {
-      B.sa[sa_off + myp[q]] = myv[q];
-      if (B.hints) st_u32_hint(&B.rank[sa_off + myv[q]], mygs[q], pol); else B.rank[sa_off + myv[q]] = mygs[q];
+      // the order entry is only final once the rotation leaves the tied lists; the rank
+      // only changes for rotations that are not in the first subgroup of their old group
+      if (!(unsmask & (1u << q))) B.sa[sa_off + myp[q]] = myv[q];
+      if (mygs[q] != (uint32_t)(k[q + 1] >> 20)) {
+        if (B.hints) st_u32_hint(&B.rank[sa_off + myv[q]], mygs[q], pol); else B.rank[sa_off + myv[q]] = mygs[q];
+      }
       if (unsmask & (1u << q)) {
         if (B.hints) { __stcs(&npos[off + o], myp[q]); __stcs(&nval[off + o], myv[q]); __stcs(&ngs[off + o], mygs[q]); }
         else { npos[off + o] = myp[q]; nval[off + o] = myv[q]; ngs[off + o] = mygs[q]; }
@@ -1004,7 +1010,8 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
 
   k_bwt_prep<<<(nb + 255) / 256, 256, 0, st>>>(d_meta, nb, B.counters);
   uint2 *pa = reinterpret_cast<uint2 *>(B.key), *pb = reinterpret_cast<uint2 *>(B.key2);
-  nl += 2 + BWT_K + 2;
+  const uint32_t K = B.K;
+  nl += 2 + K + 2;
   static int cfg = -1;
   if (cfg < 0) { const char *ev = getenv("LBZ_RADIX_CFG"); cfg = ev ? (atoi(ev) != 0) : 1; }
 
@@ -1013,28 +1020,33 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   // next to the index for the first four passes, bytes 0..3 are fetched once by
   // the fifth pass; the first pass builds its pairs from the text, the last one
   // writes the order only.
-  for (uint32_t p = 0; p < BWT_K; p++) {
-    if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * p], st);
+  // K <= 4 would need a single-phase variant; the engine only offers 5..8.
+  const uint32_t koff = K - 4u;
+  for (uint32_t p = 0; p < K; p++) {
+    if (tm && tm->enabled && p < LBZ_NK0) cudaEventRecord(tm->k0[2 * p], st);
     const uint32_t ep = next_epoch(B, nb, g, st);
-    const uint32_t shift = 8u * (p & 3u);
+    const uint32_t shift = p < 4u ? 8u * p : 8u * (p + 4u - K);
+    const bool last = (p == K - 1u);
     int rc;
-    if (p == 0) rc = launch_text_pass<2, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, B.counters + 3);
-    else if (p == 4) rc = launch_text_pass<1, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, B.counters + 3);
-    else if (p == BWT_K - 1) rc = launch_text_pass<0, 1>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, B.counters + 3);
-    else rc = launch_text_pass<0, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, B.counters + 3);
+    uint32_t *const er = B.counters + 3;
+    if (p == 0) rc = launch_text_pass<2, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
+    else if (p == 4 && last) rc = launch_text_pass<1, 1>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
+    else if (p == 4) rc = launch_text_pass<1, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
+    else if (last) rc = launch_text_pass<0, 1>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
+    else rc = launch_text_pass<0, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
     if (rc) return -1;
-    if (tm && tm->enabled) cudaEventRecord(tm->k0[2 * p + 1], st);
+    if (tm && tm->enabled && p < LBZ_NK0) cudaEventRecord(tm->k0[2 * p + 1], st);
     { uint2 *t = pa; pa = pb; pb = t; }
   }
   TileAgg *agg = reinterpret_cast<TileAgg *>(B.agg);
-  k_heads_agg<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.head, agg);
+  k_heads_agg<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.head, agg, K);
   k_ranks_compact<<<grid_full, 256, 0, st>>>(g, d_meta, B, agg);
   LBZ_CUDA_CHECK(cudaGetLastError());
   if (tm && tm->enabled) cudaEventRecord(tm->stage[2], st);
   if (B.on_sorted) B.on_sorted(B.on_sorted_arg);
 
   uint32_t rounds = 0;
-  uint32_t h = BWT_K;
+  uint32_t h = K;
   uint64_t *ksrc = B.key, *kdst = B.key2;
   uint32_t *vsrc = B.val, *vdst = B.val2;
   uint32_t *psrc = B.pos, *pdst = B.pos2;
@@ -1047,6 +1059,9 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
       return -1;
     }
     const uint32_t maxU = h_counters[0];
+    static int round_stats = -1;
+    if (round_stats < 0) round_stats = getenv("LBZ_ROUND_STATS") != nullptr;
+    if (round_stats) fprintf(stderr, "lbzip2_b200: sort depth %u: %u rotations still tied (largest list %u)\n", h, h_counters[1], maxU);
     if (maxU == 0) break;
     rounds++;
     nl += 5 + 5 + 4;

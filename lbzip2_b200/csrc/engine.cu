@@ -35,6 +35,7 @@ struct BwtBuffers {           // must match bwt.cu
   void (*on_sorted)(void *);
   void *on_sorted_arg;
   uint8_t *bwt;
+  uint32_t K;
 };
 
 extern "C" {
@@ -96,6 +97,7 @@ struct lbz_engine {
   // lane (rle1, huffman, round bookkeeping, host round trips) overlap with the
   // bandwidth-bound sort passes of the other, and H2D/D2H overlap with compute.
   int hints = 0;
+  uint32_t bwt_k = 8;                  // bytes covered by the initial radix sort (LBZ_BWT_K, 5..8)
   void (*on_sorted)(void *) = nullptr;  // set per call by the two-lane driver
   void *on_sorted_arg = nullptr;
   lbz_engine *sib = nullptr;
@@ -178,6 +180,7 @@ static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   rc |= cudaEventCreate(&e->ev_call[1]) != cudaSuccess;
   e->tm.enabled = 1;
   { const char *hv = getenv("LBZ_CACHEHINT"); e->hints = hv ? atoi(hv) : 0; }
+  { const char *kv = getenv("LBZ_BWT_K"); const int k = kv ? atoi(kv) : 8; e->bwt_k = (uint32_t)(k < 5 ? 5 : (k > 8 ? 8 : k)); }
   rc |= dev_alloc(e, &e->d_in, (size_t)e->max_chunks * g.mbs);
   rc |= dev_alloc(e, &e->d_chunk_len, e->max_chunks);
   rc |= dev_alloc(e, &e->d_T, E);
@@ -291,7 +294,7 @@ static BwtBuffers bwt_buffers(lbz_engine *e) {
   B.pos = e->d_pos; B.pos2 = e->d_pos2; B.gs = e->d_gs; B.gs2 = e->d_gs2;
   B.tstat = e->d_tstat; B.gbase = e->d_gbase; B.khist = e->d_khist; B.agg = e->d_agg;
   B.counters = e->d_counters; B.epoch = &e->epoch; B.bwt = e->d_bwt;
-  B.hints = e->hints; B.on_sorted = e->on_sorted; B.on_sorted_arg = e->on_sorted_arg;
+  B.K = e->bwt_k; B.hints = e->hints; B.on_sorted = e->on_sorted; B.on_sorted_arg = e->on_sorted_arg;
   return B;
 }
 
@@ -354,7 +357,7 @@ static int run_pipeline(lbz_engine *e, const uint8_t *d_in, uint8_t *d_packed, s
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->tm.stage[i], e->tm.stage[i + 1]) == cudaSuccess) e->stage_ms[i] += ms;
   }
-  for (int i = 0; i < LBZ_NK0; i++) {
+  for (int i = 0; i < (int)e->bwt_k && i < LBZ_NK0; i++) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->tm.k0[2 * i], e->tm.k0[2 * i + 1]) == cudaSuccess) { e->k0_ms += ms; e->k0_launches++; }
   }

@@ -46,6 +46,7 @@
 
 #include <string.h>             /* memcpy() */
 #include <stdio.h>              /* fprintf() */
+#include <time.h>               /* clock_gettime() */
 
 #include "main.h"               /* bs100k, ultra, xmalloc(), failx() */
 #include "process.h"            /* struct process, queues */
@@ -106,6 +107,18 @@ static uint64_t order;          /* next sequence number the writer expects */
 static uint32_t combined_crc;
 static bool stats;
 static unsigned long stat_batches, stat_chunks, stat_blocks;
+static double stat_t0, stat_init, stat_gpu, stat_stage, stat_copy;
+static unsigned engines_level;  /* level the engines were created for (0 = none yet) */
+
+
+static double
+now(void)
+{
+  struct timespec ts;
+
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 
 static unsigned
@@ -175,6 +188,7 @@ do_stage(void)
   struct in_blk *iblk;
   struct slot *s;
   size_t off;
+  double t0;
 
   iblk = dequeue(stage_q);
   next_stage++;
@@ -201,11 +215,14 @@ do_stage(void)
   }
   sched_unlock();
 
+  t0 = stats ? now() : 0.0;
   memcpy(s->h_in + off, iblk->buffer, iblk->size);
   source_release_buffer(iblk->buffer);
   free(iblk);
+  t0 = stats ? now() - t0 : 0.0;
 
   sched_lock();
+  stat_stage += t0;
   s->staged++;
 }
 
@@ -224,6 +241,7 @@ do_launch(void)
   struct out_blk *oblk;
   size_t out_len, nrec, k;
   int i, rc;
+  double t0, t1, t2;
 
   i = launchable();
   s = &slots[i];
@@ -235,10 +253,12 @@ do_launch(void)
 
   out_len = 0;
   nrec = 0;
+  t0 = stats ? now() : 0.0;
   rc = lbz_compress_chunks(s->eng, s->h_in, s->in_len, s->h_out, s->out_cap,
                            &out_len, s->recs, 2u * batch_cap, &nrec);
   if (rc != 0)
     failx(0, "GPU compression failed (lbz_compress_chunks returned %d)", rc);
+  t1 = stats ? now() : 0.0;
 
   oblk = XMALLOC(struct out_blk);
   oblk->pos.major = s->first_seq;
@@ -253,8 +273,12 @@ do_launch(void)
   for (k = 0; k < nrec; k++)
     oblk->crc[k] = s->recs[k].crc;
 
+  t2 = stats ? now() : 0.0;
+
   sched_lock();
   if (stats) {
+    stat_gpu += t1 - t0;
+    stat_copy += t2 - t1;
     stat_batches++;
     stat_chunks += s->assigned;
     stat_blocks += nrec;
@@ -333,6 +357,9 @@ init(void)
   uint8_t header[HEADER_SIZE];
   unsigned per_dev, ngpu, dev0, i;
 
+  stat_t0 = now();
+  stat_batches = stat_chunks = stat_blocks = 0;
+  stat_gpu = stat_stage = stat_copy = 0.0;
   if (ultra)
     failx(0, "-u is not supported by the GPU task graph");
   assert(1 <= bs100k && bs100k <= 9);
@@ -347,19 +374,34 @@ init(void)
     num_slots = MAX_SLOTS;
   chunk_size = bs100k * 100000u;
 
-  for (i = 0; i < num_slots; i++) {
-    struct slot *s = &slots[i];
+  /* The engines outlive one call of work(): main() runs work() once per operand
+     (src/main.c:935), and setting up device memory costs more than compressing a
+     small file.  They are never torn down; the process exit releases the device. */
+  if (engines_level != bs100k) {
+    if (engines_level != 0)
+      for (i = 0; i < num_slots; i++) {
+        lbz_engine_destroy(slots[i].eng);
+        lbz_host_free(slots[i].h_in);
+        lbz_host_free(slots[i].h_out);
+        free(slots[i].recs);
+      }
+    for (i = 0; i < num_slots; i++) {
+      struct slot *s = &slots[i];
 
-    s->eng = lbz_engine_create((int)(dev0 + i % ngpu), (int)bs100k,
-                               (int)batch_cap);
-    s->out_cap = lbz_bound((size_t)batch_cap * chunk_size);
-    s->h_in = lbz_host_alloc((size_t)batch_cap * chunk_size);
-    s->h_out = lbz_host_alloc(s->out_cap);
-    if (s->eng == NULL || s->h_in == NULL || s->h_out == NULL)
-      failx(0, "cannot set up the GPU engine (device %u)", dev0 + i % ngpu);
-    s->recs = XNMALLOC(2u * batch_cap, lbz_block_rec);
-    s->state = B_FREE;
+      s->eng = lbz_engine_create((int)(dev0 + i % ngpu), (int)bs100k,
+                                 (int)batch_cap);
+      s->out_cap = lbz_bound((size_t)batch_cap * chunk_size);
+      s->h_in = lbz_host_alloc((size_t)batch_cap * chunk_size);
+      s->h_out = lbz_host_alloc(s->out_cap);
+      if (s->eng == NULL || s->h_in == NULL || s->h_out == NULL)
+        failx(0, "cannot set up the GPU engine (device %u)", dev0 + i % ngpu);
+      s->recs = XNMALLOC(2u * batch_cap, lbz_block_rec);
+    }
+    engines_level = bs100k;
   }
+  for (i = 0; i < num_slots; i++)
+    slots[i].state = B_FREE;
+  stat_init = now() - stat_t0;
 
   pqueue_init(stage_q, total_in_slots);
   pqueue_init(reord_q, MAX_UNSUNK);
@@ -383,7 +425,6 @@ static void
 uninit(void)
 {
   uint8_t trailer[TRAILER_SIZE];
-  unsigned i;
 
   trailer[0] = 0x17;            /* end-of-stream magic + stream CRC, */
   trailer[1] = 0x72;            /* src/compress.c:304-321            */
@@ -399,18 +440,15 @@ uninit(void)
 
   if (stats) {
     fprintf(stderr, "lbzip2_b200: %lu batches, %lu chunks (%.1f per batch), "
-            "%lu blocks, %u engines x %u chunks\n", stat_batches, stat_chunks,
-            stat_batches ? (double)stat_chunks / stat_batches : 0.0,
-            stat_blocks, num_slots, batch_cap);
+            "%lu blocks, %u engines x %u chunks; wall %.3f s = setup %.3f + "
+            "stream %.3f; in lbz_compress_chunks %.3f s, staging copies %.3f s, "
+            "output copies %.3f s (summed over threads)\n", stat_batches,
+            stat_chunks, stat_batches ? (double)stat_chunks / stat_batches : 0.0,
+            stat_blocks, num_slots, batch_cap, now() - stat_t0, stat_init,
+            now() - stat_t0 - stat_init, stat_gpu, stat_stage, stat_copy);
     fflush(stderr);             /* main.c:912-916 makes stderr fully buffered */
   }
 
-  for (i = 0; i < num_slots; i++) {
-    lbz_engine_destroy(slots[i].eng);
-    lbz_host_free(slots[i].h_in);
-    lbz_host_free(slots[i].h_out);
-    free(slots[i].recs);
-  }
   pqueue_uninit(stage_q);
   pqueue_uninit(reord_q);
 }
