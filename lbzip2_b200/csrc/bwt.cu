@@ -47,6 +47,7 @@ struct BwtBuffers {
   void *on_sorted_arg;
   uint8_t *bwt;           // output last column
   uint32_t K;             // bytes covered by the initial radix sort (5..8)
+  uint32_t *hbits, *cbits; // group-head / size-class bitmaps (1 bit per order position), alias of `head`
 };
 
 __device__ __forceinline__ uint32_t wrap_add(uint32_t v, uint32_t d, uint32_t n) {
@@ -373,13 +374,182 @@ k_text_pass(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
   }
 }
 
+
+// Second implementation of the same pass, written for instruction count: loads are
+// issued before the counters are cleared, tile-bound checks are one compare against a
+// per-thread limit, in-warp ranks are packed four to a register, the per-digit
+// totals are summed by all 512 threads (two halves of eight warps each) and scanned
+// with two barriers.  Same shared-memory protocol and status words as k_text_pass.
+struct TextSmem2 {
+  uint2 spair[512 * 8];
+  uint32_t wcnt[16][256];
+  uint32_t hsum[2][256];
+  uint32_t dstart[2][256];
+  uint32_t delta[256];
+  uint32_t ws[8];
+};
+
+template <int MODE, int LAST, int MINB>
+__global__ void __launch_bounds__(512, MINB)
+k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+             const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
+             uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
+             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff) {
+  extern __shared__ __align__(16) unsigned char radix_smem_raw[];
+  TextSmem2 &S = *reinterpret_cast<TextSmem2 *>(radix_smem_raw);
+  constexpr int THREADS = 512, ITEMS = 8;
+  constexpr uint32_t RTILE = THREADS * ITEMS;
+  const uint32_t rtiles = g.S1 / RTILE;
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
+  const uint32_t n = meta[b].n;
+  const uint32_t tbase = tile * RTILE;
+  if (tbase >= n) return;
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint32_t tile_cnt = min(RTILE, n - tbase);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint32_t wbase = warp * (32 * ITEMS) + lane;              // tile index of this thread's item 0
+  const uint32_t lim = tile_cnt > wbase ? tile_cnt - wbase : 0u;  // item `it` exists iff it * 32 < lim
+
+  uint32_t val[ITEMS], key[ITEMS];
+  if (MODE == 2) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) val[it] = tbase + wbase + it * 32;
+  } else {
+    const uint2 *sp = src + off + tbase + wbase;
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const uint2 pr = (it * 32u < lim) ? sp[it * 32] : make_uint2(0u, 0u);
+      key[it] = pr.x; val[it] = pr.y;
+    }
+  }
+  {
+    uint4 *z = reinterpret_cast<uint4 *>(&S.wcnt[0][0]);
+    z[tid] = make_uint4(0u, 0u, 0u, 0u);
+    z[tid + THREADS] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) key[it] = (it * 32u < lim) ? text_key4(T + off, val[it], n) : 0u;
+  }
+  if (MODE == 2) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) key[it] = (it * 32u < lim) ? text_key4(T + off, wrap_add(val[it], koff, n), n) : 0u;
+  }
+  __syncthreads();
+
+  const uint32_t lt = lanemask_lt();
+  uint32_t *wrow = &S.wcnt[warp][0];
+  uint32_t rkp[ITEMS / 4];                                         // in-warp ranks (< 256), four per register
+#pragma unroll
+  for (int q = 0; q < ITEMS / 4; q++) rkp[q] = 0;
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
+    const bool valid = it * 32u < lim;
+    const uint32_t digit = valid ? ((key[it] >> shift) & 0xFFu) : 0x100u;   // missing items: a group of their own
+    const uint32_t mask = __match_any_sync(0xffffffffu, digit);
+    uint32_t base = 0;
+    if (valid) base = wrow[digit];
+    __syncwarp();
+    if (valid && (mask & lt) == 0) wrow[digit] = base + __popc(mask);       // group leader
+    __syncwarp();
+    rkp[it >> 2] |= (base + __popc(mask & lt)) << (8 * (it & 3));
+  }
+  __syncthreads();
+
+  // per-digit totals: thread (d, half) sums eight warps, the halves meet in hsum
+  const uint32_t d = tid & 255u, half = tid >> 8;
+  {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t c = S.wcnt[half * 8 + w][d]; S.wcnt[half * 8 + w][d] = run; run += c; }
+    S.hsum[half][d] = run;
+  }
+  __syncthreads();
+  uint32_t *mine = tstat + ((size_t)b * rtiles + tile) * 256 + d;
+  const uint32_t ep = (epoch << 20) & TS_EPOCH_MASK;
+  uint32_t inc = 0, total = 0, h0 = 0;
+  if (half == 0) {
+    h0 = S.hsum[0][d];
+    total = h0 + S.hsum[1][d];
+    st_volatile_u32(mine, (tile == 0 ? TS_FLAG_PREFIX : TS_FLAG_AGG) | ep | total);
+    inc = warp_incl_sum(total);
+    if (lane == 31) S.ws[warp] = inc;
+  }
+  __syncthreads();
+  uint32_t dst0 = 0;
+  if (half == 0) {
+    uint32_t wb = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; w++) wb += (w < warp) ? S.ws[w] : 0u;
+    dst0 = wb + inc - total;                                       // start of digit d inside the tile
+    S.dstart[0][d] = dst0;                                         // warps 0..7
+    S.dstart[1][d] = dst0 + h0;                                    // warps 8..15 come after the first half's items
+  }
+  __syncthreads();
+  {
+    const uint32_t *drow = &S.dstart[half][0];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      if (it * 32u < lim) {
+        const uint32_t digit = (key[it] >> shift) & 0xFFu;
+        const uint32_t slot = drow[digit] + wrow[digit] + ((rkp[it >> 2] >> (8 * (it & 3))) & 0xFFu);
+        S.spair[slot] = make_uint2(key[it], val[it]);
+      }
+    }
+  }
+  if (half == 0) {
+    uint32_t excl = 0;
+    if (tile != 0) {
+      const uint32_t *look = mine - 256;
+      uint32_t spins = 0;
+      for (;;) {
+        const uint32_t sw = ld_volatile_u32(look);
+        if ((sw & TS_EPOCH_MASK) != ep || (sw >> 30) == 0u) {
+          if (++spins > TS_SPIN_LIMIT) { *err = 1u; break; }
+          __nanosleep(40);
+          continue;
+        }
+        excl += sw & TS_VALUE_MASK;
+        if (sw & TS_FLAG_PREFIX) break;
+        look -= 256;
+      }
+      st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total) & TS_VALUE_MASK));
+    }
+    S.delta[d] = gbase[(size_t)b * 256 + d] + excl - dst0;
+  }
+  __syncthreads();
+  if (LAST) {
+    uint32_t *o = sa_out + off;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+      const uint32_t i = tid + k * THREADS;
+      if (i < tile_cnt) { const uint2 pr = S.spair[i]; o[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr.y; }
+    }
+  } else {
+    uint2 *o = dst + off;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+      const uint32_t i = tid + k * THREADS;
+      if (i < tile_cnt) { const uint2 pr = S.spair[i]; o[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr; }
+    }
+  }
+}
+
 template <int MODE, int LAST, int MINB>
 static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
                             const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
                             uint32_t shift, uint32_t epoch, uint32_t *err, uint32_t koff) {
-  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem)));
-  k_text_pass<MODE, LAST, MINB><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
-                                                                                        shift, epoch, err, koff);
+  static int v1 = -1;
+  if (v1 < 0) { const char *ev = getenv("LBZ_TP_V1"); v1 = (ev && atoi(ev) != 0) ? 1 : 0; }
+  if (v1) {
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem)));
+    k_text_pass<MODE, LAST, MINB><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
+                                                                                          shift, epoch, err, koff);
+    return 0;
+  }
+  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
+  k_text_pass2<MODE, LAST, MINB><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
+                                                                                          shift, epoch, err, koff);
   return 0;
 }
 template <int MODE, int LAST>
@@ -899,6 +1069,322 @@ k_round_apply(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
     meta[b].depth = 2u * h;
     atomicMax(&B.counters[0], U2);
     atomicAdd(&B.counters[1], U2);
+    if (!sel) atomicAdd(&B.counters[4], U2);              // diagnostics only (LBZ_ROUND_STATS)
+  }
+}
+
+
+// ===========================================================================
+// Bitmask formulation of the rank/refine passes.  Group structure is kept as one
+// bit per position (head bit) so that group starts, "still tied" flags and
+// compaction offsets come from popcounts and find-highest-bit on shared-memory
+// words, and every global access is striped: consecutive lanes touch consecutive
+// elements (the earlier kernels gave each thread 16 consecutive elements, which
+// made every load and store instruction touch 32 different cache lines).
+__device__ __forceinline__ uint32_t lanemask_le() { return lanemask_lt() | (1u << (threadIdx.x & 31u)); }
+__device__ __forceinline__ uint32_t valid_bits(uint32_t base, uint32_t n) {     // bits of word [base, base+32) below n
+  if (base >= n) return 0u;
+  const uint32_t c = n - base;
+  return c >= 32u ? 0xFFFFFFFFu : ((1u << c) - 1u);
+}
+
+// Tile-parallel pass A (replaces k_heads_agg): head bits + size-class bits of a tile
+// as bitmaps, numbers of small/large tied rotations, last head position.
+__global__ void __launch_bounds__(256)
+k_heads_bits(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+             const uint32_t *__restrict__ sa, uint32_t *__restrict__ hbits, uint32_t *__restrict__ cbits,
+             TileAgg *__restrict__ agg, uint32_t K) {
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
+  const uint32_t n = meta[b].n;
+  const uint32_t tbase = tile * LBZ_TILE;
+  if (tbase >= n) return;
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint8_t *Tb = T + off;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  // sbits[0] = positions tbase-32..tbase-1, sbits[1..128] = the tile, sbits[129] = the 32 positions after it
+  __shared__ uint32_t sbits[132];
+  __shared__ uint32_t ws[40];
+  __shared__ int wsi[40];
+#pragma unroll 2
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
+    const uint32_t p = tbase + it * 256 + tid;
+    const bool valid = p < n;
+    uint64_t k = 0;
+    if (valid) k = text_key(Tb, sa[off + p], n, K);
+    uint64_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
+    bool hd = true;                                      // past the end of the block: head
+    if (valid) {
+      if (lane == 0) kprev = p ? text_key(Tb, sa[off + p - 1], n, K) : ~k;
+      hd = (p == 0) || (k != kprev);
+    }
+    const uint32_t bw = __ballot_sync(0xffffffffu, hd);
+    if (lane == 0) sbits[1 + it * 8 + warp] = bw;
+  }
+  if (tid < 64) {                                        // two whole warps: the halo words
+    const int64_t p = (warp == 0) ? (int64_t)tbase - 32 + lane : (int64_t)tbase + LBZ_TILE + lane;
+    bool f = true;
+    if (p > 0 && p < (int64_t)n)
+      f = text_key(Tb, sa[off + (uint32_t)p], n, K) != text_key(Tb, sa[off + (uint32_t)p - 1], n, K);
+    const uint32_t bw = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) sbits[warp == 0 ? 0 : 129] = bw;
+  }
+  if (tid == 64) { sbits[130] = 0xFFFFFFFFu; sbits[131] = 0xFFFFFFFFu; }
+  __syncthreads();
+  const bool tracking = K < n;
+  const uint32_t wordbase = (off + tbase) >> 5;
+  uint32_t small = 0, large = 0;
+  int last = -1;
+#pragma unroll 2
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
+    const uint32_t w = it * 8 + warp;
+    const uint32_t p = tbase + w * 32 + lane;
+    const uint32_t x = HALO + w * 32 + lane;
+    const uint32_t H = sbits[1 + w];
+    const uint32_t Hn = (H >> 1) | (sbits[2 + w] << 31);
+    const bool tied = (p < n) && tracking && !(((H >> lane) & 1u) && ((Hn >> lane) & 1u));
+    bool sm = false;
+    if (tied) sm = (win_back(sbits, x) + win_fwd(sbits, x)) <= SMALL_GROUP;   // group = [x-back, x+fwd)
+    const uint32_t bt = __ballot_sync(0xffffffffu, tied);
+    const uint32_t bs = __ballot_sync(0xffffffffu, sm);
+    if (lane == 0) {
+      hbits[wordbase + w] = H;
+      cbits[wordbase + w] = bs;
+      small += __popc(bs);
+      large += __popc(bt & ~bs);
+      const uint32_t hv = H & valid_bits(tbase + w * 32, n);
+      if (hv) last = max(last, (int)(tbase + w * 32 + 31u - (uint32_t)__clz(hv)));
+    }
+  }
+  uint32_t tots, totl;
+  int tmax;
+  (void)cta_excl_sum(small, ws, &tots);
+  (void)cta_excl_sum(large, ws, &totl);
+  (void)cta_excl_max(last, -1, wsi, &tmax);
+  if (tid == 0) { TileAgg a; a.small = tots; a.large = totl; a.last = tmax; a.pad = 0; agg[(size_t)b * g.tiles1 + tile] = a; }
+}
+
+// Tile-parallel pass B (replaces k_ranks_compact): ranks and compaction of the tied
+// rotations into the two round lists, from the bitmaps.
+__global__ void __launch_bounds__(256, 4)
+k_ranks_compact2(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const TileAgg *__restrict__ agg) {
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
+  const uint32_t n = meta[b].n;
+  const uint32_t tbase = tile * LBZ_TILE;
+  if (tbase >= n) return;
+  const uint32_t off = lbz_slot_off(g, b);
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  __shared__ uint32_t hb[130], sb[128], lbm[128], spre[128], lpre[128];
+  __shared__ int lastpre[128];
+  __shared__ uint32_t ws[40];
+  __shared__ int wsi[40];
+  const uint32_t ntiles = (n + LBZ_TILE - 1) / LBZ_TILE;
+  uint32_t cs = 0, cl = 0, alls = 0, alll = 0;
+  int l = -1;
+  for (uint32_t t = tid; t < ntiles; t += 256) {
+    const TileAgg a = agg[(size_t)b * g.tiles1 + t];
+    alls += a.small; alll += a.large;
+    if (t < tile) { cs += a.small; cl += a.large; l = max(l, a.last); }
+  }
+  uint32_t carry_s, carry_l, total_s, total_l;
+  int carry_last;
+  (void)cta_excl_sum(cs, ws, &carry_s);
+  (void)cta_excl_sum(cl, ws, &carry_l);
+  (void)cta_excl_sum(alls, ws, &total_s);
+  (void)cta_excl_sum(alll, ws, &total_l);
+  (void)cta_excl_max(l, -1, wsi, &carry_last);
+  const uint32_t lbase = total_s;
+  const uint32_t wordbase = (off + tbase) >> 5;
+  if (tid < 128) hb[tid] = B.hbits[wordbase + tid];
+  if (tid == 128) { hb[128] = (tbase + LBZ_TILE >= n) ? 1u : B.hbits[wordbase + 128]; hb[129] = 0u; }
+  __syncthreads();
+  const bool tracking = B.K < n;
+  uint32_t sw = 0, lw = 0;
+  int lastw = -1;
+  if (tid < 128) {
+    const uint32_t H = hb[tid], Hn = (H >> 1) | (hb[tid + 1] << 31);
+    const uint32_t V = valid_bits(tbase + tid * 32, n);
+    const uint32_t tied = tracking ? (~(H & Hn) & V) : 0u;
+    const uint32_t cw = B.cbits[wordbase + tid];
+    sw = tied & cw; lw = tied & ~cw;
+    sb[tid] = sw; lbm[tid] = lw;
+    if (H & V) lastw = (int)(tbase + tid * 32 + 31u - (uint32_t)__clz(H & V));
+  }
+  uint32_t tots, totl;
+  int tmax;
+  const uint32_t exs = cta_excl_sum(__popc(sw), ws, &tots);
+  const uint32_t exl = cta_excl_sum(__popc(lw), ws, &totl);
+  const int exm = cta_excl_max(lastw, -1, wsi, &tmax);
+  if (tid < 128) { spre[tid] = exs; lpre[tid] = exl; lastpre[tid] = max(exm, carry_last); }
+  __syncthreads();
+  const uint32_t lt = lanemask_lt(), le = lanemask_le();
+  const uint64_t pol = l2_policy_evict_last();
+#pragma unroll 4
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
+    const uint32_t w = it * 8 + warp;
+    const uint32_t p = tbase + w * 32 + lane;
+    if (p < n) {
+      const uint32_t v = B.sa[off + p];
+      const uint32_t m = hb[w] & le;
+      const uint32_t st = m ? (tbase + w * 32 + 31u - (uint32_t)__clz(m)) : (uint32_t)lastpre[w];
+      if (B.hints) st_u32_hint(&B.rank[off + v], st, pol); else B.rank[off + v] = st;
+      const uint32_t sm = sb[w], lm = lbm[w];
+      if ((sm >> lane) & 1u) {
+        const uint32_t o = carry_s + spre[w] + __popc(sm & lt);
+        B.pos[off + o] = p; B.val[off + o] = v; B.gs[off + o] = st;
+      } else if ((lm >> lane) & 1u) {
+        const uint32_t o = lbase + carry_l + lpre[w] + __popc(lm & lt);
+        B.pos[off + o] = p; B.val[off + o] = v; B.gs[off + o] = st;
+      }
+    }
+  }
+  if (tid == 0 && tbase + LBZ_TILE >= n) {               // last tile of the block
+    meta[b].us_next = total_s;                            // committed by k_round_commit
+    meta[b].ul_next = total_l;
+    meta[b].lbase = lbase;
+    meta[b].depth = B.K;
+    atomicMax(&B.counters[0], max(total_s, total_l));
+    atomicAdd(&B.counters[1], total_s + total_l);
+    atomicAdd(&B.counters[4], total_s);                   // diagnostics only (LBZ_ROUND_STATS)
+  }
+}
+
+// Head bits of one tile of a sorted round list: hb[w] bit l = key of list index
+// tbase + 32w + l differs from its predecessor (or starts / lies beyond the list);
+// hb[128] bit 0 = the same for the element right after the tile.
+__device__ __forceinline__ void round_head_bits(const uint64_t *__restrict__ skey, uint32_t off, uint32_t tbase,
+                                                uint32_t U, uint32_t *hb) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+#pragma unroll 4
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
+    const uint32_t j = tbase + it * 256 + tid;
+    const uint64_t k = (j < U) ? skey[off + j] : ~0ull;              // real keys have 40 bits
+    uint64_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
+    if (lane == 0) kprev = (j > 0 && j < U) ? skey[off + j - 1] : ~0ull;
+    const bool hd = (j >= U) || (j == 0) || (k != kprev);
+    const uint32_t bw = __ballot_sync(0xffffffffu, hd);
+    if (lane == 0) hb[it * 8 + warp] = bw;
+  }
+  if (tid == 0) {
+    const uint32_t jn = tbase + LBZ_TILE;
+    hb[128] = (jn >= U) ? 1u : (uint32_t)(skey[off + jn] != skey[off + jn - 1]);
+    hb[129] = 0u;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_round_agg2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__restrict__ skey,
+             TileAgg *__restrict__ agg, uint32_t h, uint32_t sel) {
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
+  uint32_t lb, U;
+  list_sel(meta[b], sel, lb, U);
+  const uint32_t tbase = tile * LBZ_TILE;
+  if (tbase >= U) return;
+  const uint32_t n = meta[b].n;
+  const uint32_t off = lbz_slot_off(g, b) + lb;
+  const uint32_t tid = threadIdx.x;
+  const bool more = (2u * h < n);
+  __shared__ uint32_t hb[130];
+  __shared__ uint32_t ws[40];
+  __shared__ int wsi[40];
+  round_head_bits(skey, off, tbase, U, hb);
+  uint32_t uns = 0;
+  int last = -1;
+  if (tid < 128) {
+    const uint32_t H = hb[tid], Hn = (H >> 1) | (hb[tid + 1] << 31);
+    const uint32_t V = valid_bits(tbase + tid * 32, U);
+    if (more) uns = __popc(~(H & Hn) & V);
+    if (H & V) last = (int)(tbase + tid * 32 + 31u - (uint32_t)__clz(H & V));
+  }
+  uint32_t tot;
+  int tmax;
+  (void)cta_excl_sum(uns, ws, &tot);
+  (void)cta_excl_max(last, -1, wsi, &tmax);
+  if (tid == 0) {
+    TileAgg a; a.small = tot; a.large = 0; a.last = tmax; a.pad = 0;
+    agg[((size_t)sel * gridDim.y + b) * g.tiles1 + tile] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_round_apply2(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
+               const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval,
+               const uint32_t *__restrict__ pos, uint32_t *__restrict__ nval,
+               uint32_t *__restrict__ npos, uint32_t *__restrict__ ngs,
+               const TileAgg *__restrict__ agg, uint32_t h, uint32_t sel) {
+  const uint32_t b = blockIdx.y, tile = blockIdx.x;
+  uint32_t lb, U;
+  list_sel(meta[b], sel, lb, U);
+  const uint32_t tbase = tile * LBZ_TILE;
+  if (tbase >= U) return;
+  const uint32_t n = meta[b].n;
+  const uint32_t sa_off = lbz_slot_off(g, b);       // order / rank arrays
+  const uint32_t off = sa_off + lb;                  // list arrays
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const bool more = (2u * h < n);
+  __shared__ uint32_t hb[130], ub[128], upre[128];
+  __shared__ int lastpre[128];
+  __shared__ uint32_t ws[40];
+  __shared__ int wsi[40];
+  uint32_t c = 0;
+  int l = -1;
+  for (uint32_t t = tid; t < tile; t += 256) {
+    const TileAgg a = agg[((size_t)sel * gridDim.y + b) * g.tiles1 + t];
+    c += a.small; l = max(l, a.last);
+  }
+  uint32_t carry_cnt;
+  int carry_last;
+  (void)cta_excl_sum(c, ws, &carry_cnt);
+  (void)cta_excl_max(l, -1, wsi, &carry_last);
+  round_head_bits(skey, off, tbase, U, hb);
+  uint32_t uw = 0;
+  int lastw = -1;
+  if (tid < 128) {
+    const uint32_t H = hb[tid], Hn = (H >> 1) | (hb[tid + 1] << 31);
+    const uint32_t V = valid_bits(tbase + tid * 32, U);
+    if (more) uw = ~(H & Hn) & V;
+    ub[tid] = uw;
+    if (H & V) lastw = (int)(tbase + tid * 32 + 31u - (uint32_t)__clz(H & V));
+  }
+  uint32_t tot;
+  int tmax;
+  const uint32_t exu = cta_excl_sum(__popc(uw), ws, &tot);
+  const int exm = cta_excl_max(lastw, -1, wsi, &tmax);
+  if (tid < 128) { upre[tid] = exu; lastpre[tid] = max(exm, carry_last); }
+  __syncthreads();
+  const uint32_t lt = lanemask_lt(), le = lanemask_le();
+  const uint64_t pol = l2_policy_evict_last();
+#pragma unroll 4
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
+    const uint32_t w = it * 8 + warp;
+    const uint32_t j = tbase + w * 32 + lane;
+    if (j < U) {
+      const uint64_t key = skey[off + j];
+      const uint32_t myp = pos[off + j], myv = sval[off + j];
+      const uint32_t m = hb[w] & le;
+      const uint32_t st = m ? (tbase + w * 32 + 31u - (uint32_t)__clz(m)) : (uint32_t)lastpre[w];
+      const uint32_t mygs = pos[off + st];                 // SA position of the group's head element
+      const uint32_t um = ub[w];
+      const bool uns = (um >> lane) & 1u;
+      // the order entry is only final once the rotation leaves the tied lists; the rank
+      // only changes for rotations that are not in the first subgroup of their old group
+      if (!uns) B.sa[sa_off + myp] = myv;
+      if (mygs != (uint32_t)(key >> 20)) {
+        if (B.hints) st_u32_hint(&B.rank[sa_off + myv], mygs, pol); else B.rank[sa_off + myv] = mygs;
+      }
+      if (uns) {
+        const uint32_t o = carry_cnt + upre[w] + __popc(um & lt);
+        npos[off + o] = myp; nval[off + o] = myv; ngs[off + o] = mygs;
+      }
+    }
+  }
+  if (tid == 0 && tbase + LBZ_TILE >= U) {                // last tile of this list
+    const uint32_t U2 = carry_cnt + tot;
+    if (sel) meta[b].ul_next = U2; else meta[b].us_next = U2;   // committed by k_round_commit
+    meta[b].depth = 2u * h;
+    atomicMax(&B.counters[0], U2);
+    atomicAdd(&B.counters[1], U2);
+    if (!sel) atomicAdd(&B.counters[4], U2);              // diagnostics only (LBZ_ROUND_STATS)
   }
 }
 
@@ -943,7 +1429,7 @@ __global__ void k_bwt_prep(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, ui
     meta[i].tie_count = 0; meta[i].unsorted = 0;
     meta[i].us = 0; meta[i].ul = 0; meta[i].lbase = 0; meta[i].us_next = 0; meta[i].ul_next = 0;
   }
-  if (i == 0) { counters[0] = 0; counters[1] = 0; counters[3] = 0; }
+  if (i == 0) { counters[0] = 0; counters[1] = 0; counters[3] = 0; counters[4] = 0; }
 }
 // Between rounds: the tied-set size written by the last tile of a block becomes
 // the segment size of the next round (kept apart so that no kernel reads and
@@ -956,7 +1442,7 @@ __global__ void k_round_commit(LbzBlockMeta *__restrict__ meta, uint32_t nblocks
     meta[i].unsorted = meta[i].us + meta[i].ul;
   }
   if (i < nblocks * 5 * 256) khist[i] = 0;
-  if (i == 0) { counters[0] = 0; counters[1] = 0; }
+  if (i == 0) { counters[0] = 0; counters[1] = 0; counters[4] = 0; }
 }
 
 template <typename K, int COUNT_U, int GATHER, int THREADS, int ITEMS>
@@ -1039,8 +1525,15 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     { uint2 *t = pa; pa = pb; pb = t; }
   }
   TileAgg *agg = reinterpret_cast<TileAgg *>(B.agg);
-  k_heads_agg<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.head, agg, K);
-  k_ranks_compact<<<grid_full, 256, 0, st>>>(g, d_meta, B, agg);
+  static int rv1 = -1;
+  if (rv1 < 0) { const char *ev = getenv("LBZ_ROUND_V1"); rv1 = (ev && atoi(ev) != 0) ? 1 : 0; }
+  if (rv1) {
+    k_heads_agg<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.head, agg, K);
+    k_ranks_compact<<<grid_full, 256, 0, st>>>(g, d_meta, B, agg);
+  } else {
+    k_heads_bits<<<grid_full, 256, 0, st>>>(g, d_meta, B.T, B.sa, B.hbits, B.cbits, agg, K);
+    k_ranks_compact2<<<grid_full, 256, 0, st>>>(g, d_meta, B, agg);
+  }
   LBZ_CUDA_CHECK(cudaGetLastError());
   if (tm && tm->enabled) cudaEventRecord(tm->stage[2], st);
   if (B.on_sorted) B.on_sorted(B.on_sorted_arg);
@@ -1052,7 +1545,7 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   uint32_t *psrc = B.pos, *pdst = B.pos2;
   uint32_t *gsrc = B.gs, *gdst = B.gs2;
   for (;;) {
-    LBZ_CUDA_CHECK(cudaMemcpyAsync(h_counters, B.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    LBZ_CUDA_CHECK(cudaMemcpyAsync(h_counters, B.counters, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     LBZ_CUDA_CHECK(cudaStreamSynchronize(st));
     if (h_counters[3]) {
       fprintf(stderr, "lbzip2_b200: chained scan timed out (tile scheduling assumption violated)\n");
@@ -1061,7 +1554,7 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     const uint32_t maxU = h_counters[0];
     static int round_stats = -1;
     if (round_stats < 0) round_stats = getenv("LBZ_ROUND_STATS") != nullptr;
-    if (round_stats) fprintf(stderr, "lbzip2_b200: sort depth %u: %u rotations still tied (largest list %u)\n", h, h_counters[1], maxU);
+    if (round_stats) fprintf(stderr, "lbzip2_b200: sort depth %u: %u rotations still tied, %u of them in groups <= %u (largest list %u)\n", h, h_counters[1], h_counters[4], SMALL_GROUP, maxU);
     if (maxU == 0) break;
     rounds++;
     nl += 5 + 5 + 4;
@@ -1081,8 +1574,13 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     }
     // sorted (key,val) of both lists now in ksrc/vsrc; compacted survivors go to vdst/pdst/gdst
     for (uint32_t sel = 0; sel < 2; sel++) {
-      k_round_agg<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h, sel);
-      k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h, sel);
+      if (rv1) {
+        k_round_agg<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h, sel);
+        k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h, sel);
+      } else {
+        k_round_agg2<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h, sel);
+        k_round_apply2<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h, sel);
+      }
     }
     { uint32_t *t = vsrc; vsrc = vdst; vdst = t; }
     { uint32_t *t = psrc; psrc = pdst; pdst = t; }

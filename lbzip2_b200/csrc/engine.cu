@@ -36,6 +36,7 @@ struct BwtBuffers {           // must match bwt.cu
   void *on_sorted_arg;
   uint8_t *bwt;
   uint32_t K;
+  uint32_t *hbits, *cbits;
 };
 
 extern "C" {
@@ -294,6 +295,8 @@ static BwtBuffers bwt_buffers(lbz_engine *e) {
   B.pos = e->d_pos; B.pos2 = e->d_pos2; B.gs = e->d_gs; B.gs2 = e->d_gs2;
   B.tstat = e->d_tstat; B.gbase = e->d_gbase; B.khist = e->d_khist; B.agg = e->d_agg;
   B.counters = e->d_counters; B.epoch = &e->epoch; B.bwt = e->d_bwt;
+  B.hbits = reinterpret_cast<uint32_t *>(e->d_head);
+  B.cbits = B.hbits + ((size_t)e->max_chunks * e->g.stride) / 32 + 64;   // the byte array holds both bitmaps with room to spare
   B.K = e->bwt_k; B.hints = e->hints; B.on_sorted = e->on_sorted; B.on_sorted_arg = e->on_sorted_arg;
   return B;
 }

@@ -73,11 +73,15 @@ struct out_blk {
   size_t ncrc;
 };
 
-enum batch_state { B_FREE, B_OPEN, B_SEALED, B_RUNNING };
+enum batch_state { B_NONE, B_CREATING, B_FREE, B_OPEN, B_SEALED, B_RUNNING };
 
-/* One engine = one batch in flight. */
+/* One engine = one batch in flight.  Engines are created on demand (task
+   `create'): setting up device memory takes longer than compressing a small
+   file, so a slot stays B_NONE until input is actually waiting for it, and the
+   set-up of engine k+1 overlaps the first batches of engine k. */
 struct slot {
   lbz_engine *eng;
+  int device;
   uint8_t *h_in;                /* pinned staging: cap chunks */
   uint8_t *h_out;               /* pinned output */
   size_t out_cap;
@@ -100,6 +104,7 @@ static unsigned batch_cap;      /* chunks per batch */
 static size_t chunk_size;       /* bs100k * 100000 */
 static int open_slot;           /* slot of the batch being filled, or -1 */
 static unsigned running;        /* batches on the GPU */
+static unsigned creating;       /* engines being set up */
 static unsigned unsunk;
 static uint64_t next_id;        /* next input sequence number */
 static uint64_t next_stage;     /* next sequence number to be staged */
@@ -108,6 +113,7 @@ static uint32_t combined_crc;
 static bool stats;
 static unsigned long stat_batches, stat_chunks, stat_blocks;
 static double stat_t0, stat_init, stat_gpu, stat_stage, stat_copy;
+static unsigned stat_engines;
 static unsigned engines_level;  /* level the engines were created for (0 = none yet) */
 
 
@@ -168,6 +174,44 @@ launchable(void)
       return (int)i;
   }
   return -1;
+}
+
+
+static bool
+can_create(void)
+{
+  /* input is waiting, no batch is open and no engine is free: set up another one */
+  return creating == 0 && !empty(stage_q) && open_slot < 0 &&
+    find_slot(B_FREE) < 0 && find_slot(B_NONE) >= 0;
+}
+
+
+static void
+do_create(void)
+{
+  struct slot *s;
+  double t0;
+
+  s = &slots[find_slot(B_NONE)];
+  s->state = B_CREATING;
+  creating++;
+  sched_unlock();
+
+  t0 = now();
+  s->eng = lbz_engine_create(s->device, (int)bs100k, (int)batch_cap);
+  s->out_cap = lbz_bound((size_t)batch_cap * chunk_size);
+  s->h_in = lbz_host_alloc((size_t)batch_cap * chunk_size);
+  s->h_out = lbz_host_alloc(s->out_cap);
+  if (s->eng == NULL || s->h_in == NULL || s->h_out == NULL)
+    failx(0, "cannot set up the GPU engine (device %d)", s->device);
+  s->recs = XNMALLOC(2u * batch_cap, lbz_block_rec);
+  t0 = now() - t0;
+
+  sched_lock();
+  stat_init += t0;
+  stat_engines++;
+  creating--;
+  s->state = B_FREE;
 }
 
 
@@ -320,7 +364,7 @@ static bool
 can_terminate(void)
 {
   return eof && empty(stage_q) && empty(reord_q) && unsunk == 0 &&
-    out_slots == total_out_slots;
+    creating == 0 && out_slots == total_out_slots;
 }
 
 
@@ -375,33 +419,28 @@ init(void)
   chunk_size = bs100k * 100000u;
 
   /* The engines outlive one call of work(): main() runs work() once per operand
-     (src/main.c:935), and setting up device memory costs more than compressing a
-     small file.  They are never torn down; the process exit releases the device. */
+     (src/main.c:935).  They are never torn down; process exit releases the device. */
   if (engines_level != bs100k) {
-    if (engines_level != 0)
-      for (i = 0; i < num_slots; i++) {
-        lbz_engine_destroy(slots[i].eng);
-        lbz_host_free(slots[i].h_in);
-        lbz_host_free(slots[i].h_out);
-        free(slots[i].recs);
-      }
-    for (i = 0; i < num_slots; i++) {
+    for (i = 0; i < MAX_SLOTS; i++) {
       struct slot *s = &slots[i];
 
-      s->eng = lbz_engine_create((int)(dev0 + i % ngpu), (int)bs100k,
-                                 (int)batch_cap);
-      s->out_cap = lbz_bound((size_t)batch_cap * chunk_size);
-      s->h_in = lbz_host_alloc((size_t)batch_cap * chunk_size);
-      s->h_out = lbz_host_alloc(s->out_cap);
-      if (s->eng == NULL || s->h_in == NULL || s->h_out == NULL)
-        failx(0, "cannot set up the GPU engine (device %u)", dev0 + i % ngpu);
-      s->recs = XNMALLOC(2u * batch_cap, lbz_block_rec);
+      if (s->eng != NULL) {
+        lbz_engine_destroy(s->eng);
+        lbz_host_free(s->h_in);
+        lbz_host_free(s->h_out);
+        free(s->recs);
+        s->eng = NULL;
+      }
     }
     engines_level = bs100k;
   }
-  for (i = 0; i < num_slots; i++)
-    slots[i].state = B_FREE;
-  stat_init = now() - stat_t0;
+  for (i = 0; i < num_slots; i++) {
+    slots[i].device = (int)(dev0 + i % ngpu);
+    slots[i].state = slots[i].eng != NULL ? B_FREE : B_NONE;
+  }
+  creating = 0;
+  stat_init = 0.0;
+  stat_engines = 0;
 
   pqueue_init(stage_q, total_in_slots);
   pqueue_init(reord_q, MAX_UNSUNK);
@@ -440,12 +479,12 @@ uninit(void)
 
   if (stats) {
     fprintf(stderr, "lbzip2_b200: %lu batches, %lu chunks (%.1f per batch), "
-            "%lu blocks, %u engines x %u chunks; wall %.3f s = setup %.3f + "
-            "stream %.3f; in lbz_compress_chunks %.3f s, staging copies %.3f s, "
+            "%lu blocks, %u engines x %u chunks (%u set up in %.3f s); wall "
+            "%.3f s; in lbz_compress_chunks %.3f s, staging copies %.3f s, "
             "output copies %.3f s (summed over threads)\n", stat_batches,
             stat_chunks, stat_batches ? (double)stat_chunks / stat_batches : 0.0,
-            stat_blocks, num_slots, batch_cap, now() - stat_t0, stat_init,
-            now() - stat_t0 - stat_init, stat_gpu, stat_stage, stat_copy);
+            stat_blocks, num_slots, batch_cap, stat_engines, stat_init,
+            now() - stat_t0, stat_gpu, stat_stage, stat_copy);
     fflush(stderr);             /* main.c:912-916 makes stderr fully buffered */
   }
 
@@ -458,6 +497,7 @@ static const struct task task_list[] = {
   { "reorder", can_reorder, do_reorder },
   { "launch",  can_launch,  do_launch  },
   { "stage",   can_stage,   do_stage   },
+  { "create",  can_create,  do_create  },
   { NULL,      NULL,        NULL       },
 };
 

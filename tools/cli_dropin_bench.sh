@@ -31,7 +31,8 @@ s=$(date +%s.%N); cat $IN > /dev/null; e=$(date +%s.%N)
 echo "cat (page cache read): $(python -c "print(round($MB/($e-$s),1))") MB/s"
 # first call pays the one-off driver/library page-in of a fresh box: warm up once, untimed
 LBZIP2_B200_BATCH=8 LBZIP2_B200_ENGINES=1 oracle/_ref/lbzip2_b200 -9 -n8 -c /dev/shm/lbz_cli_20.raw > /dev/null
-for cfg in ${CLI_CONFIGS:-"32 2 64" "16 4 64" "64 2 64" "32 3 64"}; do
+eval "set -- ${CLI_CONFIGS:-\"32 2 64\" \"16 4 64\" \"64 2 64\" \"32 3 64\"}"
+for cfg in "$@"; do
   set -- $cfg
   for rep in 1 2; do
     t "lbzip2_b200 -9 -n$3 batch=$1 engines=$2 gpus=$GPUS" env LBZIP2_B200_BATCH=$1 LBZIP2_B200_ENGINES=$2 LBZIP2_B200_GPUS=$GPUS LBZIP2_B200_STATS=1 \
