@@ -220,13 +220,17 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather(recs, payload_dev, to_host):
-        """NCCL gather of the block bitstreams to rank 0 (they stay in rank 0's HBM for
-        the device leg and are copied to its host memory for the end-to-end leg)."""
+    gth = sharding.BlockGatherer(dist, dev, max_blocks=2 * nchunks + 2, max_payload=cap) if world > 1 else None
+
+    def gather(recs, payload_dev, tables_only):
+        """Device leg: NCCL gather of the block bitstreams into rank 0's HBM in one
+        point-to-point transfer per rank (stream order is then a table lookup).
+        Host leg: every rank's blocks are already in its own pinned host memory (the
+        D2H is inside lbz_compress_chunks); only the block table travels to rank 0 --
+        what a multi-process writer needs to pwrite every block at its stream offset."""
         if world == 1:
             return None
-        table = sharding.block_table(recs, mbs)
-        return sharding.gather_blocks(table, payload_dev, dist, dev, to_host=to_host)
+        return gth.gather(sharding.block_table(recs, mbs), payload_dev, tables_only=tables_only)
 
     def step_device():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -241,10 +245,7 @@ def run_ours(a):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         n_out, recs = eng.compress_chunks_ptr(h_in, nbytes, h_out, cap, device=False)
-        g = None
-        if world > 1:
-            pay = torch.frombuffer((C.c_uint8 * n_out).from_address(h_out), dtype=torch.uint8).to(dev, non_blocking=True)
-            g = gather(recs, pay, True)
+        g = gather(recs, d_out[:0], True)
         ev1.record()
         ev1.synchronize()
         return ev0.elapsed_time(ev1), eng.last_ms, n_out, recs, g
@@ -365,7 +366,8 @@ def run_ours(a):
                    else "%d MB %s per GPU at -%d" % (a.size_mb, a.workload, level),
                    "chunks_per_gpu": nchunks, "blocks": len(recs), "l2": "inputs (100 MB) and working set (>7 GB) larger than L2",
                    "generator": "tests/synth.py seed 0x5EED, stream offset = rank",
-                   "gather": "NCCL gather of block bitstreams to rank 0" if world > 1 else "none (single GPU)"},
+                   "gather": ("device leg: NCCL gather of block bitstreams + block table to rank 0; host leg: block table only, "
+                              "payload stays in each rank's pinned host memory") if world > 1 else "none (single GPU)"},
         "e2e": {"value": round(e2e, 2), "unit": "MB/s", "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": world * nbytes, "d2h_bytes_per_step": int(world * rh["last"][2]),
                 "api": "lbz_compress_chunks (pinned host in/out)"},

@@ -105,6 +105,7 @@ static size_t chunk_size;       /* bs100k * 100000 */
 static int open_slot;           /* slot of the batch being filled, or -1 */
 static unsigned running;        /* batches on the GPU */
 static unsigned creating;       /* engines being set up */
+static bool dev_creating[64];   /* ... one at a time per device */
 static unsigned unsunk;
 static uint64_t next_id;        /* next input sequence number */
 static uint64_t next_stage;     /* next sequence number to be staged */
@@ -177,12 +178,25 @@ launchable(void)
 }
 
 
+/* A slot without an engine whose device is not busy setting one up. */
+static int
+creatable(void)
+{
+  unsigned i;
+
+  for (i = 0; i < num_slots; i++)
+    if (slots[i].state == B_NONE && !dev_creating[slots[i].device])
+      return (int)i;
+  return -1;
+}
+
+
 static bool
 can_create(void)
 {
   /* input is waiting, no batch is open and no engine is free: set up another one */
-  return creating == 0 && !empty(stage_q) && open_slot < 0 &&
-    find_slot(B_FREE) < 0 && find_slot(B_NONE) >= 0;
+  return !empty(stage_q) && open_slot < 0 && find_slot(B_FREE) < 0 &&
+    creatable() >= 0;
 }
 
 
@@ -192,8 +206,9 @@ do_create(void)
   struct slot *s;
   double t0;
 
-  s = &slots[find_slot(B_NONE)];
+  s = &slots[creatable()];
   s->state = B_CREATING;
+  dev_creating[s->device] = true;
   creating++;
   sched_unlock();
 
@@ -211,6 +226,7 @@ do_create(void)
   stat_init += t0;
   stat_engines++;
   creating--;
+  dev_creating[s->device] = false;
   s->state = B_FREE;
 }
 
@@ -439,6 +455,7 @@ init(void)
     slots[i].state = slots[i].eng != NULL ? B_FREE : B_NONE;
   }
   creating = 0;
+  memset(dev_creating, 0, sizeof(dev_creating));
   stat_init = 0.0;
   stat_engines = 0;
 

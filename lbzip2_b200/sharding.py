@@ -97,3 +97,72 @@ def gather_blocks(table, payload, dist, device, to_host=True):
     dist.gather(tpad, None, dst=0)
     dist.gather(ppad, None, dst=0)
     return None, None
+
+
+class BlockGatherer:
+    """Reusable gather of (block table, payload) to rank 0 with preallocated buffers.
+
+    Step 1: one fixed-shape gather of a small header+table tensor (int64
+    [1 + max_blocks, 3]; row 0 = (nblocks, payload bytes, 0)) -- the only
+    host-visible synchronisation (rank 0 reads it to learn the sizes).
+    Step 2: every rank sends exactly its payload bytes to rank 0 with one
+    point-to-point transfer (NCCL send/recv over NVLink; batched so that all
+    transfers are in flight together); rank 0 receives each into a fixed region
+    of one preallocated buffer.  Nothing is padded and nothing is allocated per
+    call.  With `tables_only` the payload step is skipped (host-sink mode: every
+    rank keeps its blocks in its own host memory and writes them at the offsets
+    the table gives, the way a multi-process writer would pwrite them).
+    """
+
+    def __init__(self, dist, device, max_blocks, max_payload):
+        import torch
+        self.dist, self.device = dist, device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.max_blocks, self.max_payload = int(max_blocks), int(max_payload)
+        self.tbuf = torch.zeros((1 + self.max_blocks, 3), dtype=torch.int64, device=device)
+        self.tstage = torch.zeros((1 + self.max_blocks, 3), dtype=torch.int64).pin_memory() if str(device) != "cpu" \
+            else torch.zeros((1 + self.max_blocks, 3), dtype=torch.int64)
+        if self.rank == 0:
+            self.tall = [torch.zeros_like(self.tbuf) for _ in range(self.world)]
+            self.pall = torch.empty((self.world, self.max_payload), dtype=torch.uint8, device=device)
+        else:
+            self.tall, self.pall = None, None
+
+    def gather(self, table, payload, tables_only=False):
+        """table: int64 numpy [nblocks, 3]; payload: uint8 tensor on `device`.
+        Rank 0 returns (tables, payloads) as tensors on `device` (payloads are views of
+        the preallocated buffer; None entries with tables_only); other ranks (None, None)."""
+        import torch
+        dist = self.dist
+        nb, nbytes = int(table.shape[0]), int(payload.numel())
+        if nb > self.max_blocks or nbytes > self.max_payload:
+            raise ValueError("BlockGatherer capacity exceeded")
+        self.tstage[0, 0], self.tstage[0, 1], self.tstage[0, 2] = nb, nbytes, 0
+        if nb:
+            self.tstage[1:1 + nb] = torch.from_numpy(table)
+        self.tbuf.copy_(self.tstage, non_blocking=True)
+        dist.gather(self.tbuf, self.tall, dst=0)
+        if self.rank != 0:
+            if not tables_only and nbytes:
+                # batched on both sides: rank 0 posts batched receives, and batched and
+                # unbatched point-to-point calls do not share a communicator in torch's NCCL group
+                for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, payload, 0)]):
+                    w.wait()
+            return None, None
+        heads = torch.stack([t[0] for t in self.tall]).cpu().tolist()      # the one host sync
+        tables = [self.tall[r][1:1 + heads[r][0]] for r in range(self.world)]
+        if tables_only:
+            return tables, [None] * self.world
+        payloads = [None] * self.world
+        ops = []
+        for r in range(self.world):
+            n = heads[r][1]
+            payloads[r] = self.pall[r, :n]
+            if r == 0:
+                payloads[0].copy_(payload, non_blocking=True)
+            elif n:
+                ops.append(dist.P2POp(dist.irecv, payloads[r], r))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return tables, payloads

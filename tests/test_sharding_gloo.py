@@ -37,8 +37,16 @@ def _worker(rank, world, path, level, data, q):
         off += i.consumed
     table = sharding.block_table(recs, mbs)
     tables, payloads = sharding.gather_blocks(table, torch.from_numpy(payload.copy()), dist, "cpu")
+    # the preallocated gatherer bench.py uses on GPUs (NCCL) must agree; run it twice (buffer reuse)
+    gth = sharding.BlockGatherer(dist, "cpu", max_blocks=64, max_payload=2_000_000)
+    for _ in range(2):
+        t2, p2 = gth.gather(table, torch.from_numpy(payload.copy()))
+    t3, p3 = gth.gather(table, torch.from_numpy(payload.copy()), tables_only=True)
     if rank == 0:
-        q.put(sharding.assemble_stream(level, tables, payloads, world))
+        stream = sharding.assemble_stream(level, tables, payloads, world)
+        assert sharding.assemble_stream(level, *sharding.to_host(t2, p2), world) == stream
+        assert all(np.array_equal(a.numpy(), b.numpy()) for a, b in zip(t2, t3)) and p3 == [None] * world
+        q.put(stream)
     dist.barrier()
     dist.destroy_process_group()
 
