@@ -28,7 +28,7 @@ class BlockMeta(C.Structure):
         "n", "raw_len", "crc", "bwt_idx", "tie_count", "nmtf", "alpha_size", "num_trees",
         "num_selectors", "tree_pad", "out_len", "unsorted", "depth", "tree_cost")] + [
         ("used", C.c_uint32 * 8), ("pad_", C.c_uint32 * 2)] + [
-        (n, C.c_uint32) for n in ("us", "ul", "lbase", "us_next", "ul_next", "pad2_")]
+        (n, C.c_uint32) for n in ("us", "ul", "lbase", "us_next", "ul_next", "lbase_next")]
 
 
 class Coding(C.Structure):

@@ -389,12 +389,14 @@ struct TextSmem2 {
   uint32_t ws[8];
 };
 
-template <int MODE, int LAST, int MINB>
+// LIST = 1: the same pass over the (32-bit key, index) pairs of a block's round list L
+// (segment = meta.ul elements at list offset meta.lbase; digit bases per block and pass).
+template <int MODE, int LAST, int MINB, int LIST = 0>
 __global__ void __launch_bounds__(512, MINB)
 k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
              const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
              uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
-             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff) {
+             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride) {
   extern __shared__ __align__(16) unsigned char radix_smem_raw[];
   TextSmem2 &S = *reinterpret_cast<TextSmem2 *>(radix_smem_raw);
   constexpr int THREADS = 512, ITEMS = 8;
@@ -402,10 +404,11 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   const uint32_t rtiles = g.S1 / RTILE;
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
   const uint32_t n = meta[b].n;
+  const uint32_t cnt = LIST ? meta[b].ul : n;
   const uint32_t tbase = tile * RTILE;
-  if (tbase >= n) return;
-  const uint32_t off = lbz_slot_off(g, b);
-  const uint32_t tile_cnt = min(RTILE, n - tbase);
+  if (tbase >= cnt) return;
+  const uint32_t off = lbz_slot_off(g, b) + (LIST ? meta[b].lbase : 0u);
+  const uint32_t tile_cnt = min(RTILE, cnt - tbase);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   const uint32_t wbase = warp * (32 * ITEMS) + lane;              // tile index of this thread's item 0
   const uint32_t lim = tile_cnt > wbase ? tile_cnt - wbase : 0u;  // item `it` exists iff it * 32 < lim
@@ -515,7 +518,7 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
       }
       st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total) & TS_VALUE_MASK));
     }
-    S.delta[d] = gbase[(size_t)b * 256 + d] + excl - dst0;
+    S.delta[d] = gbase[(size_t)b * gstride + d] + excl - dst0;
   }
   __syncthreads();
   if (LAST) {
@@ -549,7 +552,7 @@ static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, co
   }
   LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
   k_text_pass2<MODE, LAST, MINB><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
-                                                                                          shift, epoch, err, koff);
+                                                                                          shift, epoch, err, koff, 256u);
   return 0;
 }
 template <int MODE, int LAST>
@@ -560,6 +563,16 @@ static int launch_text_pass(uint32_t nb, cudaStream_t st, const LbzGeom &g, cons
   if (!minb) { const char *ev = getenv("LBZ_TP_MINB"); minb = (ev && atoi(ev) == 2) ? 2 : 3; }
   if (minb == 3) return launch_text_pass_b<MODE, LAST, 3>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff);
   return launch_text_pass_b<MODE, LAST, 2>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff);
+}
+
+// One pass over the 32-bit-key pairs of every block's list L.
+static int launch_list_pass(uint32_t max_count, uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta,
+                            const uint2 *src, uint2 *dst, uint32_t *tstat, const uint32_t *gbase, uint32_t gstride,
+                            uint32_t shift, uint32_t epoch, uint32_t *err) {
+  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<0, 0, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
+  k_text_pass2<0, 0, 3, 1><<<dim3((max_count + 4095u) / 4096u, nb), 512, sizeof(TextSmem2), st>>>(
+      g, meta, nullptr, src, dst, nullptr, tstat, gbase, shift, epoch, err, 0u, gstride);
+  return 0;
 }
 
 // Digit bases of the text passes: every pass of the initial sort sees the same
@@ -632,7 +645,8 @@ __device__ __forceinline__ uint64_t text_key(const uint8_t *__restrict__ Tb, uin
 
 #define SMALL_GROUP 32u      // groups up to this size are refined by the local sort
 
-struct TileAgg { uint32_t small; uint32_t large; int last; uint32_t pad; };
+struct TileAgg { uint32_t small; uint32_t large; int last; uint32_t lheads; };   // lheads: heads of large tied groups
+#define ORD_LIMIT 4096u       // list-L group ordinals below this fit the 12 spare bits of a gs entry / a 32-bit round key
 
 __device__ __forceinline__ void list_sel(const LbzBlockMeta &m, uint32_t sel, uint32_t &base, uint32_t &cnt) {
   if (sel == 0) { base = 0; cnt = m.us; } else { base = m.lbase; cnt = m.ul; }
@@ -732,7 +746,7 @@ k_heads_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__r
   (void)cta_excl_sum(small, ws, &tots);
   (void)cta_excl_sum(large, ws, &totl);
   (void)cta_excl_max(last, -1, wsi, &tmax);
-  if (tid == 0) { TileAgg a; a.small = tots; a.large = totl; a.last = tmax; a.pad = 0; agg[(size_t)b * g.tiles1 + tile] = a; }
+  if (tid == 0) { TileAgg a; a.small = tots; a.large = totl; a.last = tmax; a.lheads = 0; agg[(size_t)b * g.tiles1 + tile] = a; }
 }
 
 // Tile-parallel pass B: ranks (rank[i] = first position of i's group) and
@@ -823,6 +837,7 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
     meta[b].us_next = total_s;                            // committed by k_round_commit
     meta[b].ul_next = total_l;
     meta[b].lbase = lbase;
+    meta[b].lbase_next = lbase;
     meta[b].depth = B.K;
     atomicMax(&B.counters[0], max(total_s, total_l));
     atomicAdd(&B.counters[1], total_s + total_l);
@@ -836,7 +851,7 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
 __global__ void __launch_bounds__(256)
 k_round_keys(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint32_t *__restrict__ val,
              const uint32_t *__restrict__ gs, const uint32_t *__restrict__ rank,
-             uint64_t *__restrict__ key, uint32_t *__restrict__ khist, uint32_t h, uint32_t sel, int hints) {
+             uint64_t *__restrict__ key, uint32_t *__restrict__ khist, uint32_t h, uint32_t sel, int hints, int pair) {
   const uint64_t pol = l2_policy_evict_last();
   const uint32_t b = blockIdx.y;
   uint32_t lb, U;
@@ -866,11 +881,19 @@ k_round_keys(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint32_t *_
   for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
     const uint32_t j = tbase + it * 256 + threadIdx.x;
     if (j < U) {
-      const uint64_t k = ((uint64_t)gg[it] << 20) | v[it];
-      key[lo + j] = k;
-      if (sel) {
+      if (sel && pair) {
+        // list L, 32-bit form: (group ordinal, rank of rotation i+h) next to the index
+        const uint32_t k32 = (gg[it] & 0xFFF00000u) | v[it];
+        reinterpret_cast<uint2 *>(key)[lo + j] = make_uint2(k32, val[lo + j]);
 #pragma unroll
-        for (int p = 0; p < 5; p++) atomicAdd(&sh[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
+        for (int p = 0; p < 4; p++) atomicAdd(&sh[p][(k32 >> (8 * p)) & 0xFFu], 1u);
+      } else {
+        const uint64_t k = ((uint64_t)(gg[it] & 0xFFFFFu) << 20) | v[it];
+        key[lo + j] = k;
+        if (sel) {
+#pragma unroll
+          for (int p = 0; p < 5; p++) atomicAdd(&sh[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
+        }
       }
     }
   }
@@ -980,7 +1003,7 @@ k_round_agg(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__
   (void)cta_excl_sum(uns, ws, &tot);
   (void)cta_excl_max(last, -1, wsi, &tmax);
   if (tid == 0) {
-    TileAgg a; a.small = tot; a.large = 0; a.last = tmax; a.pad = 0;
+    TileAgg a; a.small = tot; a.large = 0; a.last = tmax; a.lheads = 0;
     agg[((size_t)sel * gridDim.y + b) * g.tiles1 + tile] = a;
   }
 }
@@ -1132,7 +1155,7 @@ k_heads_bits(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   __syncthreads();
   const bool tracking = K < n;
   const uint32_t wordbase = (off + tbase) >> 5;
-  uint32_t small = 0, large = 0;
+  uint32_t small = 0, large = 0, lheads = 0;
   int last = -1;
 #pragma unroll 2
   for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
@@ -1151,16 +1174,18 @@ k_heads_bits(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
       cbits[wordbase + w] = bs;
       small += __popc(bs);
       large += __popc(bt & ~bs);
+      lheads += __popc(bt & ~bs & H);
       const uint32_t hv = H & valid_bits(tbase + w * 32, n);
       if (hv) last = max(last, (int)(tbase + w * 32 + 31u - (uint32_t)__clz(hv)));
     }
   }
-  uint32_t tots, totl;
+  uint32_t tots, totl, toth;
   int tmax;
   (void)cta_excl_sum(small, ws, &tots);
   (void)cta_excl_sum(large, ws, &totl);
+  (void)cta_excl_sum(lheads, ws, &toth);
   (void)cta_excl_max(last, -1, wsi, &tmax);
-  if (tid == 0) { TileAgg a; a.small = tots; a.large = totl; a.last = tmax; a.pad = 0; agg[(size_t)b * g.tiles1 + tile] = a; }
+  if (tid == 0) { TileAgg a; a.small = tots; a.large = totl; a.last = tmax; a.lheads = toth; agg[(size_t)b * g.tiles1 + tile] = a; }
 }
 
 // Tile-parallel pass B (replaces k_ranks_compact): ranks and compaction of the tied
@@ -1173,24 +1198,26 @@ k_ranks_compact2(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const
   if (tbase >= n) return;
   const uint32_t off = lbz_slot_off(g, b);
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  __shared__ uint32_t hb[130], sb[128], lbm[128], spre[128], lpre[128];
+  __shared__ uint32_t hb[130], sb[128], lbm[128], spre[128], lpre[128], hpre[128];
   __shared__ int lastpre[128];
   __shared__ uint32_t ws[40];
   __shared__ int wsi[40];
   const uint32_t ntiles = (n + LBZ_TILE - 1) / LBZ_TILE;
-  uint32_t cs = 0, cl = 0, alls = 0, alll = 0;
+  uint32_t cs = 0, cl = 0, ch = 0, alls = 0, alll = 0, allh = 0;
   int l = -1;
   for (uint32_t t = tid; t < ntiles; t += 256) {
     const TileAgg a = agg[(size_t)b * g.tiles1 + t];
-    alls += a.small; alll += a.large;
-    if (t < tile) { cs += a.small; cl += a.large; l = max(l, a.last); }
+    alls += a.small; alll += a.large; allh += a.lheads;
+    if (t < tile) { cs += a.small; cl += a.large; ch += a.lheads; l = max(l, a.last); }
   }
-  uint32_t carry_s, carry_l, total_s, total_l;
+  uint32_t carry_s, carry_l, carry_h, total_s, total_l, total_h;
   int carry_last;
   (void)cta_excl_sum(cs, ws, &carry_s);
   (void)cta_excl_sum(cl, ws, &carry_l);
+  (void)cta_excl_sum(ch, ws, &carry_h);
   (void)cta_excl_sum(alls, ws, &total_s);
   (void)cta_excl_sum(alll, ws, &total_l);
+  (void)cta_excl_sum(allh, ws, &total_h);
   (void)cta_excl_max(l, -1, wsi, &carry_last);
   const uint32_t lbase = total_s;
   const uint32_t wordbase = (off + tbase) >> 5;
@@ -1213,8 +1240,10 @@ k_ranks_compact2(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const
   int tmax;
   const uint32_t exs = cta_excl_sum(__popc(sw), ws, &tots);
   const uint32_t exl = cta_excl_sum(__popc(lw), ws, &totl);
+  uint32_t toth;
+  const uint32_t exh = cta_excl_sum(tid < 128 ? __popc(lw & hb[tid]) : 0u, ws, &toth);
   const int exm = cta_excl_max(lastw, -1, wsi, &tmax);
-  if (tid < 128) { spre[tid] = exs; lpre[tid] = exl; lastpre[tid] = max(exm, carry_last); }
+  if (tid < 128) { spre[tid] = exs; lpre[tid] = exl; hpre[tid] = exh; lastpre[tid] = max(exm, carry_last); }
   __syncthreads();
   const uint32_t lt = lanemask_lt(), le = lanemask_le();
   const uint64_t pol = l2_policy_evict_last();
@@ -1233,7 +1262,9 @@ k_ranks_compact2(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const
         B.pos[off + o] = p; B.val[off + o] = v; B.gs[off + o] = st;
       } else if ((lm >> lane) & 1u) {
         const uint32_t o = lbase + carry_l + lpre[w] + __popc(lm & lt);
-        B.pos[off + o] = p; B.val[off + o] = v; B.gs[off + o] = st;
+        // ordinal of the group inside list L (heads of large groups at or before p, minus one)
+        const uint32_t ord = min(carry_h + hpre[w] + __popc(lm & hb[w] & le) - 1u, ORD_LIMIT - 1u);
+        B.pos[off + o] = p; B.val[off + o] = v; B.gs[off + o] = st | (ord << 20);
       }
     }
   }
@@ -1241,37 +1272,79 @@ k_ranks_compact2(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const
     meta[b].us_next = total_s;                            // committed by k_round_commit
     meta[b].ul_next = total_l;
     meta[b].lbase = lbase;
+    meta[b].lbase_next = lbase;
     meta[b].depth = B.K;
     atomicMax(&B.counters[0], max(total_s, total_l));
     atomicAdd(&B.counters[1], total_s + total_l);
     atomicAdd(&B.counters[4], total_s);                   // diagnostics only (LBZ_ROUND_STATS)
+    atomicMax(&B.counters[5], total_h);                   // groups in list L: decides the 32-bit key path
   }
 }
 
-// Head bits of one tile of a sorted round list: hb[w] bit l = key of list index
-// tbase + 32w + l differs from its predecessor (or starts / lies beyond the list);
-// hb[128] bit 0 = the same for the element right after the tile.
+// Head bits of one tile of a sorted round list with a 32-position halo on both sides,
+// in the layout win_back()/win_fwd() expect: sb[0] = list indices tbase-32..tbase-1,
+// sb[1..128] = the tile, sb[129] = the 32 indices after it, sb[130..131] = all ones.
+// Bit = key differs from its predecessor's, or the index starts / lies beyond the list.
+// PAIR: the list holds (32-bit key, index) pairs in the same 8-byte slots; only the key half is compared.
+template <int PAIR>
+__device__ __forceinline__ uint64_t round_key_at(const uint64_t *__restrict__ skey, uint32_t idx) {
+  if (PAIR) return (uint64_t)reinterpret_cast<const uint2 *>(skey)[idx].x;
+  return skey[idx];
+}
+template <int PAIR>
 __device__ __forceinline__ void round_head_bits(const uint64_t *__restrict__ skey, uint32_t off, uint32_t tbase,
-                                                uint32_t U, uint32_t *hb) {
+                                                uint32_t U, uint32_t *sb) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 #pragma unroll 4
   for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
     const uint32_t j = tbase + it * 256 + tid;
-    const uint64_t k = (j < U) ? skey[off + j] : ~0ull;              // real keys have 40 bits
+    const uint64_t k = (j < U) ? round_key_at<PAIR>(skey, off + j) : ~0ull;      // real keys have <= 40 bits
     uint64_t kprev = __shfl_up_sync(0xffffffffu, k, 1);
-    if (lane == 0) kprev = (j > 0 && j < U) ? skey[off + j - 1] : ~0ull;
+    if (lane == 0) kprev = (j > 0 && j < U) ? round_key_at<PAIR>(skey, off + j - 1) : ~0ull;
     const bool hd = (j >= U) || (j == 0) || (k != kprev);
     const uint32_t bw = __ballot_sync(0xffffffffu, hd);
-    if (lane == 0) hb[it * 8 + warp] = bw;
+    if (lane == 0) sb[1 + it * 8 + warp] = bw;
   }
-  if (tid == 0) {
-    const uint32_t jn = tbase + LBZ_TILE;
-    hb[128] = (jn >= U) ? 1u : (uint32_t)(skey[off + jn] != skey[off + jn - 1]);
-    hb[129] = 0u;
+  if (tid < 64) {                                        // two whole warps: the halo words
+    const int64_t j = (warp == 0) ? (int64_t)tbase - 32 + lane : (int64_t)tbase + LBZ_TILE + lane;
+    bool f = true;
+    if (j > 0 && j < (int64_t)U)
+      f = round_key_at<PAIR>(skey, off + (uint32_t)j) != round_key_at<PAIR>(skey, off + (uint32_t)j - 1);
+    const uint32_t bw = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) sb[warp == 0 ? 0 : 129] = bw;
   }
+  if (tid == 64) { sb[130] = 0xFFFFFFFFu; sb[131] = 0xFFFFFFFFu; }
   __syncthreads();
 }
 
+// "Still tied" bits of the tile, split by the size of the (refined) group: mv = members of
+// groups of <= SMALL_GROUP (they belong in list S from now on), st = members of larger
+// groups.  CLS = 0 (list S: groups only shrink) skips the size test.  One word per
+// (it, warp), written by lane 0; the caller synchronises.
+template <int CLS>
+__device__ __forceinline__ void round_class_bits(const uint32_t *sb, uint32_t tbase, uint32_t U, bool more,
+                                                 uint32_t *mvb, uint32_t *stb) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+#pragma unroll 2
+  for (uint32_t it = 0; it < LBZ_TILE / 256; it++) {
+    const uint32_t w = it * 8 + warp;
+    const uint32_t H = sb[1 + w], Hn = (H >> 1) | (sb[2 + w] << 31);
+    const uint32_t tied = more ? (~(H & Hn) & valid_bits(tbase + w * 32, U)) : 0u;
+    uint32_t mv = tied, st = 0u;
+    if (CLS) {
+      const uint32_t x = 32u + w * 32 + lane;
+      bool sm = false;
+      if ((tied >> lane) & 1u) sm = (win_back(sb, x) + win_fwd(sb, x)) <= SMALL_GROUP;
+      mv = __ballot_sync(0xffffffffu, sm);
+      st = tied & ~mv;
+    }
+    if (lane == 0) { mvb[w] = mv; stb[w] = st; }
+  }
+}
+
+// Pass A of a round (per list): per tile, the numbers of members that stay tied in
+// small / large groups, the heads of the large ones, the last group head.
+template <int PAIR, int CLS>
 __global__ void __launch_bounds__(256)
 k_round_agg2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *__restrict__ skey,
              TileAgg *__restrict__ agg, uint32_t h, uint32_t sel) {
@@ -1284,32 +1357,41 @@ k_round_agg2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint64_t *_
   const uint32_t off = lbz_slot_off(g, b) + lb;
   const uint32_t tid = threadIdx.x;
   const bool more = (2u * h < n);
-  __shared__ uint32_t hb[130];
+  __shared__ uint32_t sb[132], mvb[128], stb[128];
   __shared__ uint32_t ws[40];
   __shared__ int wsi[40];
-  round_head_bits(skey, off, tbase, U, hb);
-  uint32_t uns = 0;
+  round_head_bits<PAIR>(skey, off, tbase, U, sb);
+  round_class_bits<CLS>(sb, tbase, U, more, mvb, stb);
+  __syncthreads();
+  uint32_t nmv = 0, nst = 0, nhd = 0;
   int last = -1;
   if (tid < 128) {
-    const uint32_t H = hb[tid], Hn = (H >> 1) | (hb[tid + 1] << 31);
+    const uint32_t H = sb[1 + tid];
     const uint32_t V = valid_bits(tbase + tid * 32, U);
-    if (more) uns = __popc(~(H & Hn) & V);
+    nmv = __popc(mvb[tid]); nst = __popc(stb[tid]); nhd = __popc(stb[tid] & H);
     if (H & V) last = (int)(tbase + tid * 32 + 31u - (uint32_t)__clz(H & V));
   }
-  uint32_t tot;
+  uint32_t tmv, tst, thd;
   int tmax;
-  (void)cta_excl_sum(uns, ws, &tot);
+  (void)cta_excl_sum(nmv, ws, &tmv);
+  (void)cta_excl_sum(nst, ws, &tst);
+  (void)cta_excl_sum(nhd, ws, &thd);
   (void)cta_excl_max(last, -1, wsi, &tmax);
   if (tid == 0) {
-    TileAgg a; a.small = tot; a.large = 0; a.last = tmax; a.pad = 0;
+    TileAgg a; a.small = tmv; a.large = tst; a.last = tmax; a.lheads = thd;
     agg[((size_t)sel * gridDim.y + b) * g.tiles1 + tile] = a;
   }
 }
 
+// Pass B of a round (per list): refine the groups, write final order entries and new
+// ranks, and compact the members that stay tied into next round's lists:
+//   S' = [survivors of list S | members of list-L groups that shrank to <= SMALL_GROUP]
+//   L' = the rest of list L, at list offset |S'|.
+template <int PAIR, int CLS>
 __global__ void __launch_bounds__(256, 4)
 k_round_apply2(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
                const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval,
-               const uint32_t *__restrict__ pos, uint32_t *__restrict__ nval,
+               const uint32_t *__restrict__ pos, const uint32_t *__restrict__ ogs, uint32_t *__restrict__ nval,
                uint32_t *__restrict__ npos, uint32_t *__restrict__ ngs,
                const TileAgg *__restrict__ agg, uint32_t h, uint32_t sel) {
   const uint32_t b = blockIdx.y, tile = blockIdx.x;
@@ -1318,39 +1400,63 @@ k_round_apply2(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
   const uint32_t tbase = tile * LBZ_TILE;
   if (tbase >= U) return;
   const uint32_t n = meta[b].n;
-  const uint32_t sa_off = lbz_slot_off(g, b);       // order / rank arrays
-  const uint32_t off = sa_off + lb;                  // list arrays
+  const uint32_t sa_off = lbz_slot_off(g, b);       // order / rank arrays, and the new lists
+  const uint32_t off = sa_off + lb;                  // this (old) list
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const bool more = (2u * h < n);
-  __shared__ uint32_t hb[130], ub[128], upre[128];
+  __shared__ uint32_t sb[132], mvb[128], stb[128], mpre[128], spre[128], hpre[128];
   __shared__ int lastpre[128];
   __shared__ uint32_t ws[40];
   __shared__ int wsi[40];
-  uint32_t c = 0;
+  // totals of both lists (list sizes of the next round) and this tile's carries
+  const uint32_t us = meta[b].us, ul = meta[b].ul;
+  const uint32_t tiles_s = (us + LBZ_TILE - 1) / LBZ_TILE, tiles_l = (ul + LBZ_TILE - 1) / LBZ_TILE;
+  const TileAgg *agg_s = agg + (size_t)b * g.tiles1;
+  const TileAgg *agg_l = agg + ((size_t)gridDim.y + b) * g.tiles1;
+  uint32_t s_tot = 0, l_mv = 0, l_st = 0, l_hd = 0, c_mv = 0, c_st = 0, c_hd = 0;
   int l = -1;
-  for (uint32_t t = tid; t < tile; t += 256) {
-    const TileAgg a = agg[((size_t)sel * gridDim.y + b) * g.tiles1 + t];
-    c += a.small; l = max(l, a.last);
+  for (uint32_t t = tid; t < tiles_s; t += 256) {
+    const TileAgg a = agg_s[t];
+    s_tot += a.small;
+    if (sel == 0 && t < tile) { c_mv += a.small; l = max(l, a.last); }
   }
-  uint32_t carry_cnt;
+  for (uint32_t t = tid; t < tiles_l; t += 256) {
+    const TileAgg a = agg_l[t];
+    l_mv += a.small; l_st += a.large; l_hd += a.lheads;
+    if (sel == 1 && t < tile) { c_mv += a.small; c_st += a.large; c_hd += a.lheads; l = max(l, a.last); }
+  }
+  uint32_t S_total, L_movers, L_stay, L_heads, carry_mv, carry_st, carry_hd;
   int carry_last;
-  (void)cta_excl_sum(c, ws, &carry_cnt);
+  (void)cta_excl_sum(s_tot, ws, &S_total);
+  (void)cta_excl_sum(l_mv, ws, &L_movers);
+  (void)cta_excl_sum(l_st, ws, &L_stay);
+  (void)cta_excl_sum(l_hd, ws, &L_heads);
+  (void)cta_excl_sum(c_mv, ws, &carry_mv);
+  (void)cta_excl_sum(c_st, ws, &carry_st);
+  (void)cta_excl_sum(c_hd, ws, &carry_hd);
   (void)cta_excl_max(l, -1, wsi, &carry_last);
-  round_head_bits(skey, off, tbase, U, hb);
-  uint32_t uw = 0;
+  const uint32_t us2 = S_total + L_movers;           // |S'| = list offset of L'
+  const uint32_t mv_base = (sel ? S_total : 0u) + carry_mv;
+  const uint32_t st_base = us2 + carry_st;
+
+  round_head_bits<PAIR>(skey, off, tbase, U, sb);
+  round_class_bits<CLS>(sb, tbase, U, more, mvb, stb);
+  __syncthreads();
+  uint32_t nmv = 0, nst = 0, nhd = 0;
   int lastw = -1;
   if (tid < 128) {
-    const uint32_t H = hb[tid], Hn = (H >> 1) | (hb[tid + 1] << 31);
+    const uint32_t H = sb[1 + tid];
     const uint32_t V = valid_bits(tbase + tid * 32, U);
-    if (more) uw = ~(H & Hn) & V;
-    ub[tid] = uw;
+    nmv = __popc(mvb[tid]); nst = __popc(stb[tid]); nhd = __popc(stb[tid] & H);
     if (H & V) lastw = (int)(tbase + tid * 32 + 31u - (uint32_t)__clz(H & V));
   }
-  uint32_t tot;
+  uint32_t tmv, tst, thd;
   int tmax;
-  const uint32_t exu = cta_excl_sum(__popc(uw), ws, &tot);
+  const uint32_t exmv = cta_excl_sum(nmv, ws, &tmv);
+  const uint32_t exst = cta_excl_sum(nst, ws, &tst);
+  const uint32_t exhd = cta_excl_sum(nhd, ws, &thd);
   const int exm = cta_excl_max(lastw, -1, wsi, &tmax);
-  if (tid < 128) { upre[tid] = exu; lastpre[tid] = max(exm, carry_last); }
+  if (tid < 128) { mpre[tid] = exmv; spre[tid] = exst; hpre[tid] = exhd; lastpre[tid] = max(exm, carry_last); }
   __syncthreads();
   const uint32_t lt = lanemask_lt(), le = lanemask_le();
   const uint64_t pol = l2_policy_evict_last();
@@ -1359,32 +1465,44 @@ k_round_apply2(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B,
     const uint32_t w = it * 8 + warp;
     const uint32_t j = tbase + w * 32 + lane;
     if (j < U) {
-      const uint64_t key = skey[off + j];
-      const uint32_t myp = pos[off + j], myv = sval[off + j];
-      const uint32_t m = hb[w] & le;
+      const uint32_t myp = pos[off + j];
+      const uint32_t myv = PAIR ? reinterpret_cast<const uint2 *>(skey)[off + j].y : sval[off + j];
+      // sorting permutes a group only inside its own list range, so the unsorted gs
+      // entry at this list index still names this element's old group
+      const uint32_t oldgs = ogs[off + j] & 0xFFFFFu;
+      const uint32_t H = sb[1 + w];
+      const uint32_t m = H & le;
       const uint32_t st = m ? (tbase + w * 32 + 31u - (uint32_t)__clz(m)) : (uint32_t)lastpre[w];
       const uint32_t mygs = pos[off + st];                 // SA position of the group's head element
-      const uint32_t um = ub[w];
-      const bool uns = (um >> lane) & 1u;
+      const uint32_t mm = mvb[w], sm = stb[w];
+      const bool mv = (mm >> lane) & 1u, stay = (sm >> lane) & 1u;
       // the order entry is only final once the rotation leaves the tied lists; the rank
       // only changes for rotations that are not in the first subgroup of their old group
-      if (!uns) B.sa[sa_off + myp] = myv;
-      if (mygs != (uint32_t)(key >> 20)) {
+      if (!mv && !stay) B.sa[sa_off + myp] = myv;
+      if (mygs != oldgs) {
         if (B.hints) st_u32_hint(&B.rank[sa_off + myv], mygs, pol); else B.rank[sa_off + myv] = mygs;
       }
-      if (uns) {
-        const uint32_t o = carry_cnt + upre[w] + __popc(um & lt);
-        npos[off + o] = myp; nval[off + o] = myv; ngs[off + o] = mygs;
+      if (mv) {
+        const uint32_t o = sa_off + mv_base + mpre[w] + __popc(mm & lt);
+        npos[o] = myp; nval[o] = myv; ngs[o] = mygs;
+      } else if (stay) {
+        const uint32_t o = sa_off + st_base + spre[w] + __popc(sm & lt);
+        // ordinal of the surviving large group inside L' (its heads at or before j, minus one)
+        const uint32_t ord = min(carry_hd + hpre[w] + __popc(sm & H & le) - 1u, ORD_LIMIT - 1u);
+        npos[o] = myp; nval[o] = myv; ngs[o] = mygs | (ord << 20);
       }
     }
   }
   if (tid == 0 && tbase + LBZ_TILE >= U) {                // last tile of this list
-    const uint32_t U2 = carry_cnt + tot;
-    if (sel) meta[b].ul_next = U2; else meta[b].us_next = U2;   // committed by k_round_commit
+    // every last tile writes the same next-round geometry (committed by k_round_commit)
+    meta[b].us_next = us2;
+    meta[b].ul_next = L_stay;
+    meta[b].lbase_next = us2;
     meta[b].depth = 2u * h;
-    atomicMax(&B.counters[0], U2);
-    atomicAdd(&B.counters[1], U2);
-    if (!sel) atomicAdd(&B.counters[4], U2);              // diagnostics only (LBZ_ROUND_STATS)
+    atomicMax(&B.counters[0], max(us2, L_stay));
+    atomicAdd(&B.counters[1], sel ? (L_movers + L_stay) : S_total);
+    atomicAdd(&B.counters[4], sel ? L_movers : S_total);  // diagnostics only (LBZ_ROUND_STATS)
+    if (sel) atomicMax(&B.counters[5], L_heads);          // groups in L': decides the 32-bit key path
   }
 }
 
@@ -1427,9 +1545,9 @@ __global__ void k_bwt_prep(LbzBlockMeta *__restrict__ meta, uint32_t nblocks, ui
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nblocks) {
     meta[i].tie_count = 0; meta[i].unsorted = 0;
-    meta[i].us = 0; meta[i].ul = 0; meta[i].lbase = 0; meta[i].us_next = 0; meta[i].ul_next = 0;
+    meta[i].us = 0; meta[i].ul = 0; meta[i].lbase = 0; meta[i].us_next = 0; meta[i].ul_next = 0; meta[i].lbase_next = 0;
   }
-  if (i == 0) { counters[0] = 0; counters[1] = 0; counters[3] = 0; counters[4] = 0; }
+  if (i == 0) { counters[0] = 0; counters[1] = 0; counters[3] = 0; counters[4] = 0; counters[5] = 0; }
 }
 // Between rounds: the tied-set size written by the last tile of a block becomes
 // the segment size of the next round (kept apart so that no kernel reads and
@@ -1438,11 +1556,11 @@ __global__ void k_round_commit(LbzBlockMeta *__restrict__ meta, uint32_t nblocks
                                uint32_t *__restrict__ khist) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nblocks) {
-    meta[i].us = meta[i].us_next; meta[i].ul = meta[i].ul_next;
+    meta[i].us = meta[i].us_next; meta[i].ul = meta[i].ul_next; meta[i].lbase = meta[i].lbase_next;
     meta[i].unsorted = meta[i].us + meta[i].ul;
   }
   if (i < nblocks * 5 * 256) khist[i] = 0;
-  if (i == 0) { counters[0] = 0; counters[1] = 0; counters[4] = 0; }
+  if (i == 0) { counters[0] = 0; counters[1] = 0; counters[4] = 0; counters[5] = 0; }
 }
 
 template <typename K, int COUNT_U, int GATHER, int THREADS, int ITEMS>
@@ -1540,51 +1658,74 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
 
   uint32_t rounds = 0;
   uint32_t h = K;
-  uint64_t *ksrc = B.key, *kdst = B.key2;
-  uint32_t *vsrc = B.val, *vdst = B.val2;
-  uint32_t *psrc = B.pos, *pdst = B.pos2;
-  uint32_t *gsrc = B.gs, *gdst = B.gs2;
+  // Per round: keys are built into kA from the lists (vA, gA); list S is sorted by
+  // k_small_sort into (kB, vB); list L either by four passes over 32-bit-key pairs
+  // (kA -> kB -> kA -> kB -> kA, while every block has fewer than ORD_LIMIT groups in L)
+  // or by five passes over 40-bit keys ((kA,vA) -> ... -> (kB,vB)); the survivors are
+  // compacted into (vA, pB, gB), which become the next round's lists.
+  uint64_t *kA = B.key, *kB = B.key2;
+  uint32_t *vA = B.val, *vB = B.val2;
+  uint32_t *pA = B.pos, *pB = B.pos2;
+  uint32_t *gA = B.gs, *gB = B.gs2;
+  static int l64 = -1;
+  if (l64 < 0) { const char *ev = getenv("LBZ_L64"); l64 = (ev && atoi(ev) != 0) ? 1 : 0; }
   for (;;) {
-    LBZ_CUDA_CHECK(cudaMemcpyAsync(h_counters, B.counters, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    LBZ_CUDA_CHECK(cudaMemcpyAsync(h_counters, B.counters, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     LBZ_CUDA_CHECK(cudaStreamSynchronize(st));
     if (h_counters[3]) {
       fprintf(stderr, "lbzip2_b200: chained scan timed out (tile scheduling assumption violated)\n");
       return -1;
     }
     const uint32_t maxU = h_counters[0];
+    const bool pair = !rv1 && !l64 && h_counters[5] <= ORD_LIMIT;
     static int round_stats = -1;
     if (round_stats < 0) round_stats = getenv("LBZ_ROUND_STATS") != nullptr;
-    if (round_stats) fprintf(stderr, "lbzip2_b200: sort depth %u: %u rotations still tied, %u of them in groups <= %u (largest list %u)\n", h, h_counters[1], h_counters[4], SMALL_GROUP, maxU);
+    if (round_stats)
+      fprintf(stderr, "lbzip2_b200: sort depth %u: %u rotations still tied, %u of them in groups <= %u (largest list %u, "
+              "at most %u groups in a list L: %s keys)\n", h, h_counters[1], h_counters[4], SMALL_GROUP, maxU, h_counters[5],
+              pair ? "32-bit" : "40-bit");
     if (maxU == 0) break;
     rounds++;
-    nl += 5 + 5 + 4;
+    nl += 5 + (pair ? 4 : 5) + 4;
     const dim3 grid_u((maxU + LBZ_TILE - 1) / LBZ_TILE, nb);
+    const uint32_t *gb1 = B.gbase + (size_t)nb * 256;
     k_round_commit<<<(nb * 5 * 256 + 255) / 256, 256, 0, st>>>(d_meta, nb, B.counters, B.khist);
-    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h, 0u, B.hints);
-    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vsrc, gsrc, B.rank, ksrc, B.khist, h, 1u, B.hints);
+    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vA, gA, B.rank, kA, B.khist, h, 0u, B.hints, 0);
+    k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vA, gA, B.rank, kA, B.khist, h, 1u, B.hints, pair ? 1 : 0);
     k_key_bases<<<nb, 256, 0, st>>>(d_meta, B.khist, B.gbase + (size_t)nb * 256);
-    // list S: one local pass straight into the buffers the five radix passes of list L end in
-    k_small_sort<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, vsrc, kdst, vdst);
-    for (uint32_t p = 0; p < 5; p++) {
-      if (launch_radix<uint64_t, 1>(cfg, false, maxU, nb, st, g, d_meta, nullptr, vsrc, vdst,
-                                    ksrc, kdst, B.tstat, B.gbase + (size_t)nb * 256 + p * 256, 5u * 256u, 8u * p,
-                                    next_epoch(B, nb, g, st), B.counters + 3)) return -1;
-      uint64_t *tk = ksrc; ksrc = kdst; kdst = tk;
-      uint32_t *tv = vsrc; vsrc = vdst; vdst = tv;
-    }
-    // sorted (key,val) of both lists now in ksrc/vsrc; compacted survivors go to vdst/pdst/gdst
-    for (uint32_t sel = 0; sel < 2; sel++) {
-      if (rv1) {
-        k_round_agg<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h, sel);
-        k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h, sel);
-      } else {
-        k_round_agg2<<<grid_u, 256, 0, st>>>(g, d_meta, ksrc, agg, h, sel);
-        k_round_apply2<<<grid_u, 256, 0, st>>>(g, d_meta, B, ksrc, vsrc, psrc, vdst, pdst, gdst, agg, h, sel);
+    k_small_sort<<<grid_u, 256, 0, st>>>(g, d_meta, kA, vA, kB, vB);
+    if (pair) {
+      uint2 *pa2 = reinterpret_cast<uint2 *>(kA), *pb2 = reinterpret_cast<uint2 *>(kB);
+      for (uint32_t p = 0; p < 4; p++) {
+        if (launch_list_pass(maxU, nb, st, g, d_meta, pa2, pb2, B.tstat, gb1 + p * 256, 5u * 256u, 8u * p,
+                             next_epoch(B, nb, g, st), B.counters + 3)) return -1;
+        uint2 *t = pa2; pa2 = pb2; pb2 = t;
+      }
+    } else {
+      uint64_t *ks = kA, *kd = kB;
+      uint32_t *vs = vA, *vd = vB;
+      for (uint32_t p = 0; p < 5; p++) {
+        if (launch_radix<uint64_t, 1>(cfg, false, maxU, nb, st, g, d_meta, nullptr, vs, vd, ks, kd, B.tstat, gb1 + p * 256,
+                                      5u * 256u, 8u * p, next_epoch(B, nb, g, st), B.counters + 3)) return -1;
+        uint64_t *tk = ks; ks = kd; kd = tk;
+        uint32_t *tv = vs; vs = vd; vd = tv;
       }
     }
-    { uint32_t *t = vsrc; vsrc = vdst; vdst = t; }
-    { uint32_t *t = psrc; psrc = pdst; pdst = t; }
-    { uint32_t *t = gsrc; gsrc = gdst; gdst = t; }
+    if (rv1) {
+      for (uint32_t sel = 0; sel < 2; sel++) {
+        k_round_agg<<<grid_u, 256, 0, st>>>(g, d_meta, kB, agg, h, sel);
+        k_round_apply<<<grid_u, 256, 0, st>>>(g, d_meta, B, kB, vB, pA, vA, pB, gB, agg, h, sel);
+      }
+    } else {
+      k_round_agg2<0, 0><<<grid_u, 256, 0, st>>>(g, d_meta, kB, agg, h, 0u);
+      if (pair) k_round_agg2<1, 1><<<grid_u, 256, 0, st>>>(g, d_meta, kA, agg, h, 1u);
+      else k_round_agg2<0, 1><<<grid_u, 256, 0, st>>>(g, d_meta, kB, agg, h, 1u);
+      k_round_apply2<0, 0><<<grid_u, 256, 0, st>>>(g, d_meta, B, kB, vB, pA, gA, vA, pB, gB, agg, h, 0u);
+      if (pair) k_round_apply2<1, 1><<<grid_u, 256, 0, st>>>(g, d_meta, B, kA, nullptr, pA, gA, vA, pB, gB, agg, h, 1u);
+      else k_round_apply2<0, 1><<<grid_u, 256, 0, st>>>(g, d_meta, B, kB, vB, pA, gA, vA, pB, gB, agg, h, 1u);
+    }
+    { uint32_t *t = pA; pA = pB; pB = t; }
+    { uint32_t *t = gA; gA = gB; gB = t; }
     h *= 2;
     LBZ_CUDA_CHECK(cudaGetLastError());
   }

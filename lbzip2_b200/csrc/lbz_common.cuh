@@ -59,7 +59,7 @@ struct LbzBlockMeta {
   // tied-rotation lists of the refinement rounds: list S holds groups of <= 32
   // members (sorted locally), list L the larger ones (radix passes); S lives at
   // list index [0, us), L at [lbase, lbase + ul); *_next are committed between rounds
-  uint32_t us, ul, lbase, us_next, ul_next, pad2_;
+  uint32_t us, ul, lbase, us_next, ul_next, lbase_next;
 };
 
 // Prefix-code description of one block (global memory, one per block slot).

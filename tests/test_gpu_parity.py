@@ -170,6 +170,30 @@ def test_bwt_adversarial_full_blocks():
     _check_bwt(eng, _oracle_blocks(inputs, cap))
 
 
+def _many_large_groups(cap, seed=9):
+    """3400 distinct 8-byte words ('a' + 7 letters), 33 copies each, shuffled: the rotations
+    at word offsets 0 and 1 form ~6800 tied groups of 33 after the 8-byte sort -- more than
+    the 4096 group ordinals the 32-bit round keys of list L can hold, so the refinement
+    starts on the 40-bit path and switches to the 32-bit one as groups resolve."""
+    rng = np.random.default_rng(seed)
+    words = set()
+    while len(words) < 3400:
+        words.add(b"a" + bytes(rng.integers(98, 123, 7, dtype=np.uint8)))
+    order = np.repeat(np.arange(3400), 33)
+    rng.shuffle(order)
+    wl = sorted(words)
+    return b"".join(wl[i] for i in order)[:cap]
+
+
+def test_bwt_many_large_groups_switches_key_width():
+    eng = engine(9, 4)
+    cap = eng.mbs
+    few = b"".join(bytes([65 + (i * 7) % 23]) * 3 + b"xyzwq" for i in range(40)) * 700     # < 4096 groups: 32-bit keys at once
+    inputs = [("many_groups", _many_large_groups(cap)), ("few_groups", few[:cap]),
+              ("many_groups_b", _many_large_groups(cap, seed=10)), ("text9b", synth.text(cap, offset=3))]
+    _check_bwt(eng, _oracle_blocks(inputs, cap))
+
+
 # -------------------------------------------------------------------- MTF ---
 def _check_mtf(eng, stages):
     for group in _batches(stages, eng.max_chunks):
