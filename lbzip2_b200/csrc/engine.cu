@@ -42,6 +42,9 @@ struct BwtBuffers {           // must match bwt.cu
 extern "C" {
 int lbz_launch_rle1(const LbzGeom *g, const uint8_t *d_in, const uint32_t *d_chunk_len, uint8_t *d_T,
                     LbzBlockMeta *d_meta, cudaStream_t st);
+size_t lbz_rle1_scratch_words(const LbzGeom *g, uint32_t max_chunks);
+int lbz_launch_rle1_tiles(const LbzGeom *g, const uint8_t *d_in, const uint32_t *d_chunk_len, uint8_t *d_T,
+                          LbzBlockMeta *d_meta, uint32_t *d_scratch, cudaStream_t st);
 int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B, uint32_t *h_counters,
                 uint32_t *rounds_out, uint64_t *launches, const LbzTimers *tm, cudaStream_t st);
 int lbz_launch_mtf(const LbzGeom *g, LbzBlockMeta *d_meta, const uint8_t *d_bwt, uint8_t *d_mtfrank,
@@ -72,6 +75,7 @@ struct lbz_engine {
   // device
   uint8_t *d_in = nullptr;     // max_chunks * mbs raw bytes
   uint32_t *d_chunk_len = nullptr;
+  uint32_t *d_rle_scratch = nullptr;   // tile tables of the RLE1 stage (rle1.cu)
   uint8_t *d_T = nullptr, *d_bwt = nullptr, *d_mtfrank = nullptr, *d_head = nullptr;
   uint32_t *d_sa = nullptr, *d_sa2 = nullptr, *d_rank = nullptr;
   uint64_t *d_key = nullptr, *d_key2 = nullptr;
@@ -85,7 +89,8 @@ struct lbz_engine {
   uint32_t *d_emitcnt = nullptr;
   LbzCoding *d_coding = nullptr;
   LbzBlockMeta *d_meta = nullptr;
-  uint8_t *d_out = nullptr, *d_packed = nullptr;
+  uint8_t *d_out = nullptr, *d_packed = nullptr, *d_packed2 = nullptr;   // packed2: second sub-batch of a lane
+  cudaStream_t st_copy = nullptr;      // copy-out of finished sub-batches (two-lane mode)
   uint32_t *d_out_off = nullptr;
   // pinned host
   uint32_t *h_chunk_len = nullptr;
@@ -184,6 +189,7 @@ static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   { const char *kv = getenv("LBZ_BWT_K"); const int k = kv ? atoi(kv) : 8; e->bwt_k = (uint32_t)(k < 5 ? 5 : (k > 8 ? 8 : k)); }
   rc |= dev_alloc(e, &e->d_in, (size_t)e->max_chunks * g.mbs);
   rc |= dev_alloc(e, &e->d_chunk_len, e->max_chunks);
+  rc |= dev_alloc(e, &e->d_rle_scratch, lbz_rle1_scratch_words(&g, e->max_chunks));
   rc |= dev_alloc(e, &e->d_T, E);
   rc |= dev_alloc(e, &e->d_bwt, E);
   rc |= dev_alloc(e, &e->d_mtfrank, E);
@@ -212,6 +218,8 @@ static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   rc |= dev_alloc(e, &e->d_meta, NB);
   rc |= dev_alloc(e, &e->d_out, NB * (size_t)g.out_cap);
   rc |= dev_alloc(e, &e->d_packed, lbz_bound((size_t)e->max_chunks * g.mbs));
+  rc |= dev_alloc(e, &e->d_packed2, lbz_bound((size_t)e->max_chunks * g.mbs));
+  rc |= cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess;
   rc |= dev_alloc(e, &e->d_out_off, NB);
   rc |= cudaHostAlloc((void **)&e->h_chunk_len, e->max_chunks * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess;
   rc |= cudaHostAlloc((void **)&e->h_meta, NB * sizeof(LbzBlockMeta), cudaHostAllocDefault) != cudaSuccess;
@@ -249,6 +257,7 @@ extern "C" void lbz_engine_destroy(lbz_engine *e) {
   if (e->ev_done) cudaEventDestroy(e->ev_done);
   cudaSetDevice(e->device);
   if (e->st) { cudaStreamSynchronize(e->st); cudaStreamDestroy(e->st); }
+  if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
   for (void *p : e->allocs) cudaFree(p);
   for (int i = 0; i <= LBZ_NSTAGE; i++) if (e->tm.stage[i]) cudaEventDestroy(e->tm.stage[i]);
   for (int i = 0; i < 2 * LBZ_NK0; i++) if (e->tm.k0[i]) cudaEventDestroy(e->tm.k0[i]);
@@ -319,9 +328,13 @@ static int run_stage(lbz_engine *e, int stage, const uint8_t *d_in, uint8_t *d_p
   const LbzGeom *g = &e->g;
   const uint32_t nb = 2 * g->nchunks;
   switch (stage) {
-    case LBZ_ST_RLE1:
-      e->launches += 1;
-      return lbz_launch_rle1(g, d_in, e->d_chunk_len, e->d_T, e->d_meta, e->st);
+    case LBZ_ST_RLE1: {
+      static int v1 = -1;
+      if (v1 < 0) { const char *ev = getenv("LBZ_RLE_V1"); v1 = (ev && atoi(ev) != 0) ? 1 : 0; }
+      if (v1) { e->launches += 1; return lbz_launch_rle1(g, d_in, e->d_chunk_len, e->d_T, e->d_meta, e->st); }
+      e->launches += 10;
+      return lbz_launch_rle1_tiles(g, d_in, e->d_chunk_len, e->d_T, e->d_meta, e->d_rle_scratch, e->st);
+    }
     case LBZ_ST_BWT:
       return lbz_run_bwt(g, e->d_meta, bwt_buffers(e), e->h_counters, &e->last_rounds, &e->launches, &e->tm, e->st);
     case LBZ_ST_MTF:
@@ -418,9 +431,8 @@ static void reset_call_stats(lbz_engine *e) {
 }
 
 // One lane: chunk table, (H2D,) all stages.  Leaves the packed blocks in
-// e->d_packed (or dst_dev if given) and the block records in e->h_meta.
-static int lane_run(lbz_engine *e, const uint8_t *src, bool src_on_device, size_t len, uint8_t *dst_dev, size_t *total,
-                    std::future<void> *after_upload = nullptr, cudaEvent_t wait_ev = nullptr) {
+// dst_dev (or e->d_packed) and the block records in e->h_meta.
+static int lane_run(lbz_engine *e, const uint8_t *src, bool src_on_device, size_t len, uint8_t *dst_dev, size_t *total) {
   if (cudaSetDevice(e->device) != cudaSuccess) return -1;
   if (set_chunks(e, len)) return -1;
   const uint8_t *d_in = src;
@@ -428,15 +440,49 @@ static int lane_run(lbz_engine *e, const uint8_t *src, bool src_on_device, size_
     ENG_CHECK(cudaMemcpyAsync(e->d_in, src, len, cudaMemcpyHostToDevice, e->st));
     d_in = e->d_in;
   }
-  if (after_upload) {                       // staggered lane: upload first, then wait for the other lane's sort
-    after_upload->wait();
-    cudaStreamWaitEvent(e->st, wait_ev, 0);
-  }
   return run_pipeline(e, d_in, dst_dev ? dst_dev : e->d_packed, total);
 }
 
+static size_t fill_recs_from(const LbzGeom &g, const LbzBlockMeta *metas, uint32_t nb, uint64_t raw_base,
+                             lbz_block_rec *recs, size_t max_recs, size_t have) {
+  size_t k = have;
+  for (uint32_t b = 0; b < nb; b++) {
+    const LbzBlockMeta &m = metas[b];
+    if (m.n == 0) continue;
+    if (recs && k < max_recs) {
+      lbz_block_rec &r = recs[k];
+      const uint64_t chunk_off = (uint64_t)(b >> 1) * g.mbs;
+      r.raw_offset = raw_base + chunk_off + ((b & 1) ? metas[b - 1].raw_len : 0u);
+      r.raw_len = m.raw_len; r.nblock = m.n; r.crc = m.crc; r.bwt_idx = m.bwt_idx; r.tie_count = m.tie_count;
+      r.nmtf = m.nmtf; r.num_trees = m.num_trees; r.num_selectors = m.num_selectors; r.out_len = m.out_len;
+      r.reserved = 0;
+    }
+    k++;
+  }
+  return k;
+}
+
 // Compress up to total_chunks chunks (one "super batch") from `src` into `dst`
-// (host or device memory, `on_device`).  Two lanes split the chunk range.
+// (host or device memory, `on_device`).
+//
+// Two-lane engines cut the batch into sub-batches in stream order, alternating between
+// the lanes (two host threads, two streams); the copy-out of a finished sub-batch and
+// the H2D of the other lane overlap the kernels.  Default: one sub-batch per lane.
+// LBZ_SPLIT4=1 cuts four unequal ones,
+//     sb0 (lane A, large)  sb1 (lane B, small)  sb2 (lane A, small)  sb3 (lane B, large),
+// meant to let the lanes drift out of phase (one lane's latency-bound RLE1/Huffman CTAs
+// next to the other's sort passes); on the benchmark batch the smaller launches cost
+// more than the overlap gains.
+struct SubBatch {
+  lbz_engine *lane = nullptr;
+  size_t in_off = 0, in_len = 0;
+  uint8_t *packed = nullptr;
+  size_t total = 0;
+  int rc = 0;
+  bool done = false;
+  std::vector<LbzBlockMeta> metas;
+};
+
 static int super_batch(lbz_engine *e, const uint8_t *src, size_t len, uint8_t *dst, size_t dst_cap, bool on_device,
                        uint64_t raw_base, size_t *written, lbz_block_rec *recs, size_t max_recs, size_t *nrec) {
   const size_t mbs = e->g.mbs;
@@ -452,58 +498,78 @@ static int super_batch(lbz_engine *e, const uint8_t *src, size_t len, uint8_t *d
     *written = total;
     return 0;
   }
-  const size_t ncA = (nc + 1) / 2;
-  const size_t lenA = ncA * mbs, lenB = len - lenA;
   lbz_engine *A = e, *B = e->sib;
-  std::promise<long long> totA_p;
-  std::future<long long> totA_f = totA_p.get_future();
-  int rcA = 0, rcB = 0;
-  size_t totA = 0, totB = 0;
-  // optional staggering: lane B's kernels wait until lane A has finished its
-  // initial sort, so that B's rle1/sort overlap A's latency-bound tail
-  static int stagger = -1;
-  if (stagger < 0) { const char *sv = getenv("LBZ_STAGGER"); stagger = sv ? atoi(sv) : 0; }
-  std::promise<void> sorted_p;
-  std::future<void> sorted_f = sorted_p.get_future();
-  struct Sig { std::promise<void> *p; bool done; } sig{&sorted_p, false};
-  if (stagger) {
-    A->on_sorted = [](void *a) { Sig *s = static_cast<Sig *>(a); if (!s->done) { s->done = true; s->p->set_value(); } };
-    A->on_sorted_arg = &sig;
+  const size_t nA = (nc + 1) / 2, nB = nc - nA;
+  static int split4 = -1;
+  // the four-way split measured slower on the 100 MB text batch (5.08 vs 5.90 GB/s): off by default
+  if (split4 < 0) { const char *ev = getenv("LBZ_SPLIT4"); split4 = ev ? atoi(ev) : 0; }
+  size_t cnt[4];
+  int nsub;
+  if (split4 && nc >= 16) {
+    const size_t a0 = (nA * 72 + 99) / 100, b0 = (nB * 28) / 100 ? (nB * 28) / 100 : 1;
+    cnt[0] = a0; cnt[1] = b0; cnt[2] = nA - a0; cnt[3] = nB - b0;
+    nsub = 4;
+  } else {
+    cnt[0] = nA; cnt[1] = nB;
+    nsub = 2;
   }
-  std::thread tb([&]() {
-    // staggered: B uploads, then waits until A has enqueued its initial sort and lets
-    // its stream wait for that point on the device
-    rcB = lane_run(B, src + lenA, on_device, lenB, nullptr, &totB, stagger ? &sorted_f : nullptr, A->tm.stage[2]);
-    const long long ta = totA_f.get();
-    if (rcB == 0 && ta >= 0) {
-      if ((size_t)ta + totB > dst_cap) { rcB = -2; return; }
-      if (cudaMemcpyAsync(dst + ta, B->d_packed, totB, kind, B->st) != cudaSuccess) { rcB = -1; return; }
-      cudaEventRecord(B->ev_done, B->st);
-      if (cudaStreamSynchronize(B->st) != cudaSuccess) rcB = -1;
+  SubBatch sub[4];
+  {
+    size_t c0 = 0;
+    for (int k = 0; k < nsub; k++) {
+      sub[k].lane = (k & 1) ? B : A;
+      sub[k].in_off = c0 * mbs;
+      sub[k].in_len = (c0 + cnt[k]) * mbs <= len ? cnt[k] * mbs : len - c0 * mbs;
+      sub[k].packed = (k < 2) ? sub[k].lane->d_packed : sub[k].lane->d_packed2;
+      c0 += cnt[k];
     }
-  });
-  rcA = lane_run(A, src, on_device, lenA, nullptr, &totA);
-  if (stagger) {
-    A->on_sorted = nullptr;
-    if (!sig.done) { sig.done = true; sorted_p.set_value(); }     // A failed before the sort: release B
   }
-  totA_p.set_value(rcA == 0 ? (long long)totA : -1LL);
-  if (rcA == 0) {
-    if (totA > dst_cap) rcA = -2;
-    else if (cudaMemcpyAsync(dst, A->d_packed, totA, kind, A->st) != cudaSuccess) rcA = -1;
-  }
+  // copy-out in stream order as soon as every earlier sub-batch's size is known
+  std::mutex mu;
+  int next_copy = 0;
+  size_t out_off = 0;
+  int copy_rc = 0;
+  auto advance_copies = [&]() {                    // called with `mu` held
+    while (next_copy < nsub && sub[next_copy].done && !copy_rc) {
+      SubBatch &sb = sub[next_copy];
+      if (sb.rc) { copy_rc = sb.rc; break; }
+      if (out_off + sb.total > dst_cap) { copy_rc = -2; break; }
+      if (sb.total && cudaMemcpyAsync(dst + out_off, sb.packed, sb.total, kind, A->st_copy) != cudaSuccess) { copy_rc = -1; break; }
+      out_off += sb.total;
+      next_copy++;
+    }
+  };
+  auto run_lane = [&](int first) {
+    for (int k = first; k < nsub; k += 2) {
+      SubBatch &sb = sub[k];
+      size_t total = 0;
+      int rc = 0;
+      if (sb.in_len) {
+        rc = lane_run(sb.lane, src + sb.in_off, on_device, sb.in_len, sb.packed, &total);
+        if (rc == 0) sb.metas.assign(sb.lane->h_meta, sb.lane->h_meta + 2 * sb.lane->g.nchunks);
+      }
+      std::lock_guard<std::mutex> lk(mu);
+      sb.rc = rc; sb.total = total; sb.done = true;
+      advance_copies();
+      if (rc) break;
+    }
+    std::lock_guard<std::mutex> lk(mu);             // a failed lane must not leave the other one waiting
+    for (int k = first; k < nsub; k += 2) if (!sub[k].done) { sub[k].rc = -1; sub[k].done = true; }
+    advance_copies();
+  };
+  std::thread tb(run_lane, 1);
+  run_lane(0);
   tb.join();
-  if (rcA == 0) {
-    cudaStreamWaitEvent(A->st, B->ev_done, 0);          // the call-level end event covers both lanes
-    if (cudaStreamSynchronize(A->st) != cudaSuccess) rcA = -1;
+  if (cudaSetDevice(A->device) != cudaSuccess) return -1;
+  if (copy_rc == 0 && next_copy == nsub && cudaStreamSynchronize(A->st_copy) != cudaSuccess) copy_rc = -1;
+  if (copy_rc || next_copy != nsub) {
+    if (copy_rc == -2) fprintf(stderr, "lbzip2_b200: output buffer too small\n");
+    cudaStreamSynchronize(A->st_copy);
+    return copy_rc ? copy_rc : -1;
   }
-  if (rcA || rcB) {
-    if (rcA == -2 || rcB == -2) fprintf(stderr, "lbzip2_b200: output buffer too small\n");
-    return rcA ? rcA : rcB;
-  }
-  *nrec = fill_recs(A, raw_base, recs, max_recs, *nrec);
-  *nrec = fill_recs(B, raw_base + lenA, recs, max_recs, *nrec);
-  *written = totA + totB;
+  for (int k = 0; k < nsub; k++)
+    *nrec = fill_recs_from(e->g, sub[k].metas.data(), (uint32_t)sub[k].metas.size(), raw_base + sub[k].in_off, recs, max_recs, *nrec);
+  *written = out_off;
   return 0;
 }
 

@@ -50,6 +50,10 @@ struct HufSmem {
   uint8_t hdepth[LBZ_MAX_TREES][520];
   uint8_t pm_len[LBZ_MAX_TREES][HUF_MAXH + 1][260];
   uint8_t selector[18008];
+  // E-step staging: every warp copies the 32 groups it is about to score (32 x 50 u16 = 800
+  // words, contiguous in HBM) with coalesced 128-bit loads; lane l then reads its group at a
+  // stride of 25 words, which hits 32 different banks (25 is odd).
+  __align__(16) uint32_t stage[HUF_THREADS / 32][800];
 };
 
 // Sort the alphabet of every tree: heaviest first, ties by lower symbol
@@ -292,28 +296,45 @@ k_huffman(LbzGeom g, LbzBlockMeta *__restrict__ meta, uint16_t *__restrict__ mtf
     }
     for (uint32_t i = tid; i < LBZ_MAX_TREES * 260; i += HUF_THREADS) (&S.freq[0][0])[i] = 0;
     __syncthreads();
-    for (uint32_t gi = tid; gi < ng; gi += HUF_THREADS) {
-      const uint32_t *gp = reinterpret_cast<const uint32_t *>(mtfv + gi * LBZ_GROUP);
-      uint32_t wv[LBZ_GROUP / 2];
-      unsigned long long cp = 0;
+    for (uint32_t g0 = 0; g0 < ng; g0 += HUF_THREADS) {            // warp-uniform trip count
+      const uint32_t gw = g0 + warp * 32;                          // first group of this warp
+      const uint32_t gi = gw + lane;
+      uint32_t *stg = S.stage[warp];
+      if (gw < ng) {
+        // only the block's own (padded) groups are read: the slot ends at most 64 symbols later
+        const uint4 *gsrc = reinterpret_cast<const uint4 *>(mtfv + (size_t)gw * LBZ_GROUP);
+        const uint32_t lim = (ng - gw) * LBZ_GROUP;                // symbols of this warp's valid groups
 #pragma unroll
-      for (int i = 0; i < LBZ_GROUP / 2; i++) {
-        wv[i] = gp[i];
-        cp += S.len_pack[wv[i] & 0xFFFFu];
-        cp += S.len_pack[wv[i] >> 16];
+        for (int q = 0; q < 7; q++) {
+          const uint32_t i4 = q * 32 + lane;
+          if (i4 < 200 && i4 * 8u < lim) reinterpret_cast<uint4 *>(stg)[i4] = gsrc[i4];
+        }
       }
-      uint32_t bc = (uint32_t)cp & 0x3FFu, bt = 0;
-      for (uint32_t t = 1; t < nt; t++) {
-        cp >>= 10;
-        const uint32_t c = (uint32_t)cp & 0x3FFu;
-        if (c < bc) { bc = c; bt = t; }
-      }
-      S.selector[gi] = (uint8_t)bt;
+      __syncwarp();
+      if (gi < ng) {
+        const uint32_t *gp = stg + lane * (LBZ_GROUP / 2);
+        uint32_t wv[LBZ_GROUP / 2];
+        unsigned long long cp = 0;
 #pragma unroll
-      for (int i = 0; i < LBZ_GROUP / 2; i++) {
-        atomicAdd(&S.freq[bt][wv[i] & 0xFFFFu], 1u);
-        atomicAdd(&S.freq[bt][wv[i] >> 16], 1u);
+        for (int i = 0; i < LBZ_GROUP / 2; i++) {
+          wv[i] = gp[i];
+          cp += S.len_pack[wv[i] & 0xFFFFu];
+          cp += S.len_pack[wv[i] >> 16];
+        }
+        uint32_t bc = (uint32_t)cp & 0x3FFu, bt = 0;
+        for (uint32_t t = 1; t < nt; t++) {
+          cp >>= 10;
+          const uint32_t c = (uint32_t)cp & 0x3FFu;
+          if (c < bc) { bc = c; bt = t; }
+        }
+        S.selector[gi] = (uint8_t)bt;
+#pragma unroll
+        for (int i = 0; i < LBZ_GROUP / 2; i++) {
+          atomicAdd(&S.freq[bt][wv[i] & 0xFFFFu], 1u);
+          atomicAdd(&S.freq[bt][wv[i] >> 16], 1u);
+        }
       }
+      __syncwarp();                                                // the staging words are reused next trip
     }
     __syncthreads();
     rank_symbols(S, nt, as, true);
