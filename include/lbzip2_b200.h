@@ -63,6 +63,12 @@ size_t encode(struct encoder_state *e, uint32_t *crc);
    (>= (size+3)/4*4 bytes).  Releases the device context: it is the last call
    the scheduler makes before free(e) (src/compress.c:220-223). */
 void *transmit(struct encoder_state *e, void *buf);
+/* src/encode.h:34  (src/encode.c:1005-1137).  In the reference this is a step inside
+   encode() (its only caller, src/encode.c:469) that builds the prefix codes of the block
+   held by the state and returns their transmission cost in bits.  Here the whole block
+   runs on the device in one go, so the call is valid after encode() and returns that
+   cost as computed by the Huffman kernel; before encode() it stops loudly. */
+unsigned generate_prefix_code(struct encoder_state *s);
 /* src/encode.h:36  (src/divbwt.c:1707-1726).  SA[i] receives the BWT byte
    widened to int32, returns the primary index; `bucket` is unused scratch. */
 int32_t divbwt(uint8_t *T, int32_t *SA, int32_t *bucket, int32_t n);

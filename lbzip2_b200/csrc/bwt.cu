@@ -817,8 +817,8 @@ k_ranks_compact(LbzGeom g, LbzBlockMeta *__restrict__ meta, BwtBuffers B, const 
       const uint4 x = *reinterpret_cast<const uint4 *>(&B.sa[off + p0 + 4 * q]);   // slot capacity covers the overread
       v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
     }
-#pragma unroll
     const uint64_t pol = l2_policy_evict_last();
+#pragma unroll
     for (int j = 0; j < 16; j++) {
       if (p0 + j < n) {
         if (B.hints) st_u32_hint(&B.rank[off + v[j]], starts[j], pol); else B.rank[off + v[j]] = starts[j];

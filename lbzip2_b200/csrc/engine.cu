@@ -695,6 +695,7 @@ struct encoder_state {
   int32_t rle_state;         // mirrors the reference's collect() state for resumed calls
   uint32_t rle_char;
   uint32_t staged_cap;
+  uint32_t tree_cost;        // bits: prefix-code transmission + payload cost reported by the Huffman kernel
   uint8_t *staged;           // pinned staging of the raw bytes of this block (lives after the struct)
 };
 
@@ -878,6 +879,7 @@ int run_batch(int level, std::vector<BReq *> &batch) {
     ENG_CHECK(cudaMemcpyAsync(s->staged, e->d_packed + off, m0.out_len, cudaMemcpyDeviceToHost, e->st));
     s->out_len = m0.out_len;
     s->crc = m0.crc;
+    s->tree_cost = m0.tree_cost;
     off += m0.out_len;
   }
   ENG_CHECK(cudaStreamSynchronize(e->st));
@@ -949,9 +951,16 @@ extern "C" size_t encode(struct encoder_state *s, uint32_t *crc) {
   if (m[0].pad_[0] != 8u * m[0].out_len) die("encode: internal size mismatch");
   s->out_len = m[0].out_len;
   s->crc = m[0].crc;
+  s->tree_cost = m[0].tree_cost;
   s->done = 1;
   if (crc) *crc = m[0].crc;
   return m[0].out_len;
+}
+
+extern "C" unsigned generate_prefix_code(struct encoder_state *s) {
+  if (!s || s->magic != ENC_MAGIC) die("generate_prefix_code: state not initialised");
+  if (!s->done) die("generate_prefix_code: only valid after encode() in this build (the block is coded on the device as a whole)");
+  return s->tree_cost;
 }
 
 extern "C" void *transmit(struct encoder_state *s, void *buf) {

@@ -345,6 +345,11 @@ def test_reference_shaped_api():
             assert consumed > 0
             crc = C.c_uint32(0)
             size = L.encode(st, C.byref(crc))
+            # src/encode.h:34: the prefix-code cost (bits of all codes + their tables) is the
+            # bulk of the block; the rest is header, bitmap and selectors (src/encode.c:473-534)
+            L.generate_prefix_code.restype = C.c_uint
+            cost = L.generate_prefix_code(st)
+            assert 0 < cost <= 8 * size and 8 * size - cost < 8 * (40 + 32 + 18002)
             out = C.create_string_buffer((size + 3) // 4 * 4)
             L.transmit(st, out)
             blocks.append(out.raw[:size])
