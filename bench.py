@@ -340,8 +340,13 @@ def run_ours(a):
             # decoded stream and compare every rank's part with the sha256 of its input
             plain = bz2.decompress(stream)
             ok = len(plain) == world * nbytes
+            # stream chunk i is chunk i // world of rank i % world; every rank's last chunk is short
+            lens = [min(mbs, nbytes - (i // world) * mbs) for i in range(world * nchunks)]
+            offs = [0]
+            for ln in lens:
+                offs.append(offs[-1] + ln)
             for r in range(world):
-                part = b"".join(plain[i * mbs:(i + 1) * mbs] for i in range(r, world * nchunks, world))
+                part = b"".join(plain[offs[i]:offs[i + 1]] for i in range(r, world * nchunks, world))
                 ok = ok and hashlib.sha256(part).hexdigest() == all_sha[r]
             verified["gathered_stream_roundtrip"] = ok
         verified["periodic_blocks"] = sum(1 for r in recs if r.tie_count > 1)

@@ -322,6 +322,25 @@ def test_stream_full_size_properties():
     assert got == want
 
 
+@pytest.mark.parametrize("workload", ["text", "random", "runs_fib"])
+def test_baseline_shaped_100mb_matches_reference_cli(workload):
+    """BASELINE.json configs 2/4/5 at 100 MB per shape (the bench batch: 112 chunks at -9):
+    byte-identical to the unmodified reference CLI, plus an independent round trip."""
+    import os
+    import subprocess
+    cpu_cli = os.path.join(orclib.REF_DIR, "lbzip2")
+    if not os.path.exists(cpu_cli):
+        pytest.skip("oracle/_ref/lbzip2 not present")
+    n = 100_000_000
+    data = {"text": lambda: synth.text(n), "random": lambda: synth.random_bytes(n, seed=1),
+            "runs_fib": lambda: synth.runs_and_fib(n)}[workload]()
+    eng = engine(9, 112)
+    got = eng.compress_stream(data)
+    want = subprocess.run([cpu_cli, "-9"], input=data, stdout=subprocess.PIPE, check=True).stdout
+    assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()
+    assert bz2.decompress(got) == data
+
+
 def test_empty_input():
     eng = engine(9, 4)
     assert eng.compress_stream(b"") == b"BZh9\x17\x72\x45\x38\x50\x90\x00\x00\x00\x00"
