@@ -98,6 +98,7 @@ __global__ void k_sa_init(LbzGeom g, const LbzBlockMeta *__restrict__ meta, cons
 #define TS_EPOCH_MASK 0x3FF00000u
 #define TS_VALUE_MASK 0x000FFFFFu
 #define TS_SPIN_LIMIT (1u << 27)
+#define TS_WINDOW 8                // status words fetched per look-back step (k_text_pass2)
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
   uint32_t v;
@@ -503,18 +504,36 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   if (half == 0) {
     uint32_t excl = 0;
     if (tile != 0) {
-      const uint32_t *look = mine - 256;
+      // Look-back over the preceding tiles of this block, a window of TS_WINDOW status
+      // words at a time: the loads of a window are independent and issued together, so
+      // the walk costs one memory round trip per window instead of one per tile (the
+      // predecessors are typically still in flight and only offer their aggregates).
+      const uint32_t *row0 = mine - (size_t)tile * 256;            // status word of tile 0, this digit
+      int t = (int)tile - 1;
       uint32_t spins = 0;
-      for (;;) {
-        const uint32_t sw = ld_volatile_u32(look);
-        if ((sw & TS_EPOCH_MASK) != ep || (sw >> 30) == 0u) {
+      bool done = false;
+      while (!done) {
+        uint32_t sw[TS_WINDOW];
+#pragma unroll
+        for (int k = 0; k < TS_WINDOW; k++)
+          sw[k] = (t - k >= 0) ? ld_volatile_u32(row0 + (size_t)(t - k) * 256) : (TS_FLAG_PREFIX | ep);
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < TS_WINDOW; k++) {
+          if (!done && used == k) {
+            const uint32_t w = sw[k];
+            if ((w & TS_EPOCH_MASK) == ep && (w >> 30) != 0u) {
+              excl += w & TS_VALUE_MASK;
+              used = k + 1;
+              if (w & TS_FLAG_PREFIX) done = true;
+            }
+          }
+        }
+        t -= used;
+        if (!done && used < TS_WINDOW) {                             // tile t has not published yet
           if (++spins > TS_SPIN_LIMIT) { *err = 1u; break; }
           __nanosleep(40);
-          continue;
         }
-        excl += sw & TS_VALUE_MASK;
-        if (sw & TS_FLAG_PREFIX) break;
-        look -= 256;
       }
       st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total) & TS_VALUE_MASK));
     }
