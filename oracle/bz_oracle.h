@@ -104,6 +104,53 @@ size_t orc_compress_stream(const uint8_t *in, size_t n, int level,
                            uint8_t *out, struct orc_block_info *infos,
                            size_t max_infos, size_t *num_blocks);
 
+/* ------------------------------------------------------------------------
+ * Decompression side (bz_unoracle.c): restatement of decode.c / parse.c and
+ * of the per-block checks of expand.c.  Status values are the reference's
+ * `enum error` (common.h:54-76) in the same order.
+ */
+enum {
+  ORC_OK = 0, ORC_MORE, ORC_FINISH,
+  ORC_ERR_MAGIC, ORC_ERR_HEADER, ORC_ERR_BITMAP, ORC_ERR_TREES, ORC_ERR_GROUPS,
+  ORC_ERR_SELECTOR, ORC_ERR_DELTA, ORC_ERR_PREFIX, ORC_ERR_INCOMPLT,
+  ORC_ERR_EMPTY, ORC_ERR_UNTERM, ORC_ERR_RUNLEN, ORC_ERR_BLKCRC,
+  ORC_ERR_STRMCRC, ORC_ERR_OVERFLOW, ORC_ERR_BWTIDX, ORC_ERR_EOF,
+  ORC_ERR_OUTCAP = 100          /* ours: caller's output buffer too small */
+};
+
+struct orc_dblock {
+  uint32_t status, rand, bwt_idx, block_size, alpha_size, num_trees,
+           num_selectors, pad;
+  uint64_t end_bit;             /* first bit after the block's EOB symbol */
+};
+
+struct orc_dstream {
+  uint32_t status, num_blocks, num_streams, bad_block, garbage, pad;
+  uint64_t end_bit;
+};
+
+/* retrieve() decode.c:518-791: header fields, byte map, selectors, code
+   lengths, prefix decoding, inverse MTF and zero-run expansion of ONE block
+   whose payload starts at absolute bit `bitpos` (right after the 32-bit block
+   CRC).  bwt must hold 900000 bytes.  Returns the status.  */
+int orc_d_retrieve(const uint8_t *in, size_t nbytes, uint64_t bitpos,
+                   uint8_t *bwt, struct orc_dblock *bi);
+
+/* decode() decode.c:840-917: inverse BWT (+ de-randomisation).  */
+void orc_d_ibwt(const uint8_t *bwt, uint32_t n, uint32_t idx, int rand,
+                uint8_t *out);
+
+/* emit() decode.c:936-1143: undo the initial run-length coding, CRC.  */
+int orc_d_unrle(const uint8_t *src, uint32_t n, uint8_t *out, size_t cap,
+                size_t *out_len, uint32_t *crc);
+
+/* Whole file: first header (main.c:664-683), parse() parse.c:147-263,
+   EOF rule expand.c:428-436, per-block checks expand.c:725-736.
+   On error *out_len counts the bytes of the blocks before the bad one.  */
+int orc_decompress_stream(const uint8_t *in, size_t n, uint8_t *out,
+                          size_t cap, size_t *out_len,
+                          struct orc_dstream *si);
+
 #ifdef __cplusplus
 }
 #endif

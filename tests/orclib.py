@@ -57,6 +57,30 @@ class RefDump(C.Structure):
     ]
 
 
+class OrcDBlock(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "status", "rand", "bwt_idx", "block_size", "alpha_size", "num_trees",
+        "num_selectors", "pad")] + [("end_bit", C.c_uint64)]
+
+
+class OrcDStream(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "status", "num_blocks", "num_streams", "bad_block", "garbage", "pad")] + [
+        ("end_bit", C.c_uint64)]
+
+
+# the reference's `enum error` (common.h:54-76) and err2str() texts (expand.c:70-88)
+ERR_NAMES = ["OK", "MORE", "FINISH", "ERR_MAGIC", "ERR_HEADER", "ERR_BITMAP", "ERR_TREES",
+             "ERR_GROUPS", "ERR_SELECTOR", "ERR_DELTA", "ERR_PREFIX", "ERR_INCOMPLT",
+             "ERR_EMPTY", "ERR_UNTERM", "ERR_RUNLEN", "ERR_BLKCRC", "ERR_STRMCRC",
+             "ERR_OVERFLOW", "ERR_BWTIDX", "ERR_EOF"]
+ERR_TEXT = {3: "not a valid bzip2 file", 4: "bad block header magic", 5: "empty source alphabet",
+            6: "bad number of trees", 7: "no coding groups", 8: "invalid selector",
+            9: "invalid delta code", 10: "invalid prefix code", 11: "incomplete prefix code",
+            12: "empty block", 13: "unterminated block", 14: "missing run length",
+            15: "block CRC mismatch", 16: "stream CRC mismatch", 17: "block overflow",
+            18: "primary index too large", 19: "unexpected end of file"}
+
 _oracle = None
 _ref = None
 
@@ -94,6 +118,15 @@ def oracle():
         L.orc_compress_stream.argtypes = [u8p, C.c_size_t, C.c_int, u8p,
                                           C.POINTER(OrcBlockInfo), C.c_size_t,
                                           C.POINTER(C.c_size_t)]
+        L.orc_d_retrieve.restype = C.c_int
+        L.orc_d_retrieve.argtypes = [u8p, C.c_size_t, C.c_uint64, u8p, C.POINTER(OrcDBlock)]
+        L.orc_d_ibwt.restype = None
+        L.orc_d_ibwt.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_int, u8p]
+        L.orc_d_unrle.restype = C.c_int
+        L.orc_d_unrle.argtypes = [u8p, C.c_uint32, u8p, C.c_size_t, C.POINTER(C.c_size_t), u32p]
+        L.orc_decompress_stream.restype = C.c_int
+        L.orc_decompress_stream.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t,
+                                            C.POINTER(C.c_size_t), C.POINTER(OrcDStream)]
         _oracle = L
     return _oracle
 
@@ -168,6 +201,58 @@ def orc_block_stages(data, cap):
     res.update(bwt=bwt, bwt_idx=idx, tie_count=tie.value, mtfv=mtfv[:nm].copy(), nmtf=nm,
                freq=freq, alpha_size=asz.value, coding=cd, bits=out[:ln].copy(), out_len=cd.out_len)
     return res
+
+
+def orc_decompress(z, cap=None):
+    """Whole-file decompression by the oracle: (status, output bytes, OrcDStream)."""
+    L = oracle()
+    a = as_u8(z)
+    if cap is None:
+        cap = max(1 << 20, 64 * a.size)
+    out = np.empty(cap, np.uint8)
+    n = C.c_size_t(0)
+    si = OrcDStream()
+    src = a if a.size else np.zeros(1, np.uint8)
+    st = L.orc_decompress_stream(_ptr(src, u8p), a.size, _ptr(out, u8p), cap, C.byref(n), C.byref(si))
+    return st, out[: n.value].tobytes(), si
+
+
+def orc_retrieve(z, bitpos):
+    """One block's payload at absolute bit `bitpos`: (OrcDBlock, bwt bytes)."""
+    L = oracle()
+    a = as_u8(z)
+    bwt = np.zeros(900000, np.uint8)
+    bi = OrcDBlock()
+    L.orc_d_retrieve(_ptr(a, u8p), a.size, bitpos, _ptr(bwt, u8p), C.byref(bi))
+    return bi, bwt[: bi.block_size].copy()
+
+
+def orc_ibwt(bwt, idx, rand=0):
+    L = oracle()
+    a = as_u8(bwt)
+    out = np.zeros(max(a.size, 1), np.uint8)
+    L.orc_d_ibwt(_ptr(a, u8p), a.size, idx, rand, _ptr(out, u8p))
+    return out[: a.size]
+
+
+def orc_unrle(src, cap=None):
+    L = oracle()
+    a = as_u8(src)
+    if cap is None:
+        cap = 64 * a.size + 1024
+    out = np.zeros(cap, np.uint8)
+    n = C.c_size_t(0)
+    crc = C.c_uint32(0)
+    s = a if a.size else np.zeros(1, np.uint8)
+    st = L.orc_d_unrle(_ptr(s, u8p), a.size, _ptr(out, u8p), cap, C.byref(n), C.byref(crc))
+    return st, out[: n.value].copy(), crc.value
+
+
+def ref_cli_decompress(z):
+    """(exit status, stdout, stderr) of the compiled reference `lbzip2 -d -n1`."""
+    p = subprocess.run([os.path.join(REF_DIR, "lbzip2"), "-d", "-c", "-n1"], input=bytes(z),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    return p.returncode, p.stdout, p.stderr.decode("latin1")
 
 
 # -------------------------------------------------------------- reference ---
