@@ -374,10 +374,14 @@ orc_decompress_stream(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
       size_t got = 0;
       strm_crc = ((strm_crc << 1) | (strm_crc >> 31)) ^ stored;
       rv = orc_d_retrieve(in, n, pos, bwt, &bi);
-      if (rv == ORC_OK) {
+      /* expand.c:725-726 tests the size before it looks at the block's status, so
+         an over-long block whose only other fault is its primary index (the one
+         retrieve() error that is raised after the size is known, decode.c:741-747)
+         is reported as an overflow */
+      if ((rv == ORC_OK || rv == ORC_ERR_BWTIDX) &&
+          bi.block_size > (uint32_t)bs100k * 100000u) rv = ORC_ERR_OVERFLOW;
+      if (rv == ORC_OK)
         orc_d_ibwt(bwt, bi.block_size, bi.bwt_idx, (int)bi.rand, txt);
-        if (bi.block_size > (uint32_t)bs100k * 100000u) rv = ORC_ERR_OVERFLOW;
-      }
       if (rv == ORC_OK) {
         rv = orc_d_unrle(txt, bi.block_size, out + o, cap - o, &got, &crc);
         if (rv == ORC_ERR_OVERFLOW) rv = ORC_ERR_OUTCAP;
