@@ -166,6 +166,99 @@ int lbz_dbg_write(lbz_engine *e, int array, uint32_t slot, const void *src, size
 uint32_t lbz_dbg_num_slots(const lbz_engine *e);
 int lbz_dbg_set_chunks(lbz_engine *e, uint32_t nchunks);   /* slots are then filled with lbz_dbg_write */
 
+/* ------------------------------------------------------------------------
+ * 4. Batch DECOMPRESSION.
+ *    Replaces, for a whole file at a time, the reference's scan()
+ *    (src/parse.c:281-342, src/decode.h:76), retrieve()/decode()/emit()
+ *    (src/decode.h:78-81, src/decode.c:518-1143) and the stream walk of
+ *    parse() (src/parse.c:147-263) with the per-block checks of
+ *    src/expand.c:725-736.  The per-block decode.h calls themselves are NOT
+ *    offered: retrieve() is a resumable bit-serial automaton fed 256 KiB at a
+ *    time that must return exactly at the block's last bit, which only the
+ *    decoding itself reveals; a device version has to see many whole blocks
+ *    at once.  Status values are the reference's
+ *    `enum error` (src/common.h:54-76), same numbering.
+ * ---------------------------------------------------------------------- */
+enum lbz_status {
+  LBZ_OK = 0, LBZ_MORE = 1, LBZ_FINISH = 2,
+  LBZ_ERR_MAGIC = 3, LBZ_ERR_HEADER = 4, LBZ_ERR_BITMAP = 5, LBZ_ERR_TREES = 6, LBZ_ERR_GROUPS = 7,
+  LBZ_ERR_SELECTOR = 8, LBZ_ERR_DELTA = 9, LBZ_ERR_PREFIX = 10, LBZ_ERR_INCOMPLT = 11,
+  LBZ_ERR_EMPTY = 12, LBZ_ERR_UNTERM = 13, LBZ_ERR_RUNLEN = 14, LBZ_ERR_BLKCRC = 15,
+  LBZ_ERR_STRMCRC = 16, LBZ_ERR_OVERFLOW = 17, LBZ_ERR_BWTIDX = 18, LBZ_ERR_EOF = 19,
+  LBZ_ERR_OUTCAP = 100       /* ours: the caller's output buffer is too small */
+};
+/* The reference's message for a status (src/expand.c:70-94, src/process.c:680). */
+const char *lbz_strerror(int status);
+
+typedef struct lbz_decoder lbz_decoder;
+
+typedef struct lbz_dstream_info {
+  uint32_t status;           /* same as the return value (>= 0)                        */
+  uint32_t num_blocks;       /* blocks decoded and verified                            */
+  uint32_t num_streams;      /* concatenated streams completed                         */
+  uint32_t bad_block;        /* index of the block the error belongs to                */
+  uint32_t garbage;          /* 1: trailing garbage after the last stream was ignored  */
+  uint32_t candidates;       /* block magics found by the scanner (any bit offset)     */
+  uint32_t false_candidates; /* ... that turned out to lie inside other blocks         */
+  uint32_t waves;            /* batches of candidates pushed through the kernels       */
+  uint64_t end_bit;          /* where the stream walk stopped                          */
+} lbz_dstream_info;
+
+/* A decoder on CUDA device `device` that works on waves of up to `max_blocks`
+   candidate blocks (about 6 MB of device memory each), accepts compressed
+   inputs of up to `in_cap` bytes and stages up to `out_cap` decoded bytes per
+   wave (>= 47 MB so that any single block fits).  NULL (and a message) on
+   failure; there is no CPU path. */
+lbz_decoder *lbz_decoder_create(int device, int max_blocks, size_t in_cap, size_t out_cap);
+void lbz_decoder_destroy(lbz_decoder *d);
+
+/* Decompress a whole .bz2 file (concatenated streams, trailing garbage and
+   bit-aligned blocks of foreign compressors included) from HOST memory into
+   HOST memory.  Returns LBZ_OK or the reference's error kind; negative for
+   CUDA / capacity failures.  On error *out_len counts the bytes of the blocks
+   that precede the bad one (those bytes are valid). */
+int lbz_decompress_stream(lbz_decoder *d, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
+                          size_t *out_len, lbz_dstream_info *info);
+
+/* Variants for measurements and pipelines: LBZ_D_RESIDENT_INPUT = the same n
+   bytes were already placed on the device by lbz_decoder_load (the host copy
+   is still needed for the framing walk, 10 bytes per block);
+   LBZ_D_DEVICE_OUTPUT = leave the decoded bytes in the decoder's device
+   buffer (out may be NULL; only the last wave's bytes remain readable with
+   lbz_decoder_read). */
+#define LBZ_D_RESIDENT_INPUT 1u
+#define LBZ_D_DEVICE_OUTPUT 2u
+int lbz_decoder_load(lbz_decoder *d, const uint8_t *in, size_t n);
+int lbz_decompress_ex(lbz_decoder *d, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
+                      size_t *out_len, lbz_dstream_info *info, unsigned flags);
+
+/* Block-boundary scanner alone (row f3): bit positions of every 48-bit block
+   magic 0x314159265359 in the input, ascending.  Returns the number found
+   (written up to cap), negative on failure. */
+long lbz_scan_blocks(lbz_decoder *d, const uint8_t *in, size_t n, uint64_t *bit_positions, size_t cap);
+
+/* Diagnostics / parity hooks: arrays of the LAST wave of the last call. */
+enum lbz_darray {
+  LBZ_DA_BLOCK = 0,    /* struct lbz_dblock of a slot                          */
+  LBZ_DA_BWT = 1,      /* u8  last column recovered by the prefix decoder      */
+  LBZ_DA_TEXT = 2,     /* u8  inverse BWT output (still run-length coded)      */
+  LBZ_DA_OUT = 3       /* u8  the wave's decoded bytes (slot = byte offset)    */
+};
+typedef struct lbz_dblock {
+  uint64_t pos, end_bit, out_len, out_off;
+  uint32_t status, rand, bwt_idx, block_size, alpha_size, num_trees, num_selectors;
+  uint32_t period, rl_state, crc_acc, crc, pad;
+} lbz_dblock;
+int lbz_decoder_read(lbz_decoder *d, int array, uint64_t slot, void *dst, size_t bytes);
+uint32_t lbz_decoder_last_wave_blocks(const lbz_decoder *d);
+uint64_t lbz_decoder_launches(const lbz_decoder *d);
+size_t lbz_decoder_device_bytes(const lbz_decoder *d);
+/* Device time of the last call (CUDA events on the decoder's stream): whole call and
+   {upload, scan, prefix decode + inverse MTF, successor table, splitter walks, run
+   expansion + CRC, tail}; stages are those of the last wave. */
+double lbz_decoder_last_ms(const lbz_decoder *d);
+void lbz_decoder_stage_ms(const lbz_decoder *d, double *out7);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,4 +7,4 @@ never falls back to a CPU implementation: importing :mod:`lbzip2_b200.api`
 raises if the library is missing, and creating an engine raises if there is
 no usable GPU.
 """
-from .api import Engine, LbzError, load_library, lib_path  # noqa: F401
+from .api import Decoder, Engine, LbzError, load_library, lib_path  # noqa: F401

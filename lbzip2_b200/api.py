@@ -37,6 +37,29 @@ class Coding(C.Structure):
                 ("selector", C.c_uint8 * 18008), ("selector_mtf", C.c_uint8 * 18008)]
 
 
+class DStreamInfo(C.Structure):
+    """Mirror of lbz_dstream_info."""
+    _fields_ = [(n, C.c_uint32) for n in (
+        "status", "num_blocks", "num_streams", "bad_block", "garbage", "candidates",
+        "false_candidates", "waves")] + [("end_bit", C.c_uint64)]
+
+
+class DBlock(C.Structure):
+    """Mirror of lbz_dblock."""
+    _fields_ = [(n, C.c_uint64) for n in ("pos", "end_bit", "out_len", "out_off")] + [
+        (n, C.c_uint32) for n in ("status", "rand", "bwt_idx", "block_size", "alpha_size", "num_trees",
+                                  "num_selectors", "period", "rl_state", "crc_acc", "crc", "pad")]
+
+
+# the reference's `enum error` (src/common.h:54-76)
+STATUS_NAMES = ["OK", "MORE", "FINISH", "ERR_MAGIC", "ERR_HEADER", "ERR_BITMAP", "ERR_TREES",
+                "ERR_GROUPS", "ERR_SELECTOR", "ERR_DELTA", "ERR_PREFIX", "ERR_INCOMPLT",
+                "ERR_EMPTY", "ERR_UNTERM", "ERR_RUNLEN", "ERR_BLKCRC", "ERR_STRMCRC",
+                "ERR_OVERFLOW", "ERR_BWTIDX", "ERR_EOF"]
+ERR_OUTCAP = 100
+D_RESIDENT_INPUT, D_DEVICE_OUTPUT = 1, 2
+DA_BLOCK, DA_BWT, DA_TEXT, DA_OUT = range(4)
+
 ST_RLE1, ST_BWT, ST_MTF, ST_HUFFMAN, ST_PACK = range(5)
 AR_TEXT, AR_BWT, AR_MTFV, AR_FREQ, AR_CODING, AR_OUT, AR_META, AR_SA = range(8)
 
@@ -51,6 +74,11 @@ EXPORTS = [
     # stage hooks
     "lbz_dbg_load", "lbz_dbg_run", "lbz_dbg_read", "lbz_dbg_write", "lbz_dbg_num_slots",
     "lbz_dbg_set_chunks",
+    # batch decompression (section 4 of the header)
+    "lbz_decoder_create", "lbz_decoder_destroy", "lbz_decompress_stream", "lbz_decompress_ex",
+    "lbz_decoder_load", "lbz_scan_blocks", "lbz_decoder_read", "lbz_decoder_last_wave_blocks",
+    "lbz_decoder_launches", "lbz_decoder_device_bytes", "lbz_decoder_last_ms", "lbz_decoder_stage_ms",
+    "lbz_strerror",
 ]
 
 
@@ -119,6 +147,33 @@ def load_library():
     L.transmit.argtypes = [vp, vp]
     L.divbwt.restype = C.c_int32
     L.divbwt.argtypes = [vp, vp, vp, C.c_int32]
+    # batch decompression
+    L.lbz_decoder_create.restype = vp
+    L.lbz_decoder_create.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t]
+    L.lbz_decoder_destroy.restype = None
+    L.lbz_decoder_destroy.argtypes = [vp]
+    L.lbz_decompress_stream.restype = C.c_int
+    L.lbz_decompress_stream.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp, C.POINTER(DStreamInfo)]
+    L.lbz_decompress_ex.restype = C.c_int
+    L.lbz_decompress_ex.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp, C.POINTER(DStreamInfo), C.c_uint]
+    L.lbz_decoder_load.restype = C.c_int
+    L.lbz_decoder_load.argtypes = [vp, vp, C.c_size_t]
+    L.lbz_scan_blocks.restype = C.c_long
+    L.lbz_scan_blocks.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_uint64), C.c_size_t]
+    L.lbz_decoder_read.restype = C.c_int
+    L.lbz_decoder_read.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_size_t]
+    L.lbz_decoder_last_wave_blocks.restype = C.c_uint32
+    L.lbz_decoder_last_wave_blocks.argtypes = [vp]
+    L.lbz_decoder_launches.restype = C.c_uint64
+    L.lbz_decoder_launches.argtypes = [vp]
+    L.lbz_decoder_device_bytes.restype = C.c_size_t
+    L.lbz_decoder_device_bytes.argtypes = [vp]
+    L.lbz_decoder_last_ms.restype = C.c_double
+    L.lbz_decoder_last_ms.argtypes = [vp]
+    L.lbz_decoder_stage_ms.restype = None
+    L.lbz_decoder_stage_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    L.lbz_strerror.restype = C.c_char_p
+    L.lbz_strerror.argtypes = [C.c_int]
     _LIB = L
     return L
 
@@ -253,3 +308,95 @@ class Engine:
 
     def meta(self, slot):
         return self.dbg_read_struct(AR_META, slot, BlockMeta)
+
+
+class Decoder:
+    """One GPU context for batch decompression (mirror of lbz_decoder)."""
+
+    def __init__(self, device=0, max_blocks=64, in_cap=1 << 24, out_cap=0):
+        self.L = load_library()
+        self.h = self.L.lbz_decoder_create(device, max_blocks, in_cap, out_cap)
+        if not self.h:
+            raise LbzError("lbz_decoder_create failed (no usable GPU? this package has no CPU path)")
+
+    def close(self):
+        if self.h:
+            self.L.lbz_decoder_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decompress(self, z, cap=None):
+        """(status, output bytes, DStreamInfo).  status: 0, the reference's error kind, or 100."""
+        a = _as_u8(z)
+        if cap is None:
+            cap = max(1 << 20, 64 * a.size)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        n = C.c_size_t(0)
+        info = DStreamInfo()
+        src = a if a.size else np.zeros(1, np.uint8)
+        st = self.L.lbz_decompress_stream(self.h, src.ctypes.data, a.size, out.ctypes.data, cap, C.byref(n),
+                                          C.byref(info))
+        if st < 0:
+            raise LbzError("lbz_decompress_stream failed (%d)" % st)
+        return st, out[: n.value].tobytes(), info
+
+    def decompress_ptr(self, in_ptr, n, out_ptr, out_cap, flags=0):
+        """Raw-pointer form; returns (status, out_len, info)."""
+        ln = C.c_size_t(0)
+        info = DStreamInfo()
+        st = self.L.lbz_decompress_ex(self.h, in_ptr, n, out_ptr, out_cap, C.byref(ln), C.byref(info), flags)
+        if st < 0:
+            raise LbzError("lbz_decompress_ex failed (%d)" % st)
+        return st, ln.value, info
+
+    def load(self, in_ptr, n):
+        if self.L.lbz_decoder_load(self.h, in_ptr, n):
+            raise LbzError("lbz_decoder_load failed")
+
+    def scan(self, z):
+        a = _as_u8(z)
+        cap = a.size // 6 + 64
+        pos = (C.c_uint64 * cap)()
+        src = a if a.size else np.zeros(1, np.uint8)
+        k = self.L.lbz_scan_blocks(self.h, src.ctypes.data, a.size, pos, cap)
+        if k < 0:
+            raise LbzError("lbz_scan_blocks failed")
+        return list(pos[:k])
+
+    def block(self, slot):
+        b = DBlock()
+        if self.L.lbz_decoder_read(self.h, DA_BLOCK, slot, C.byref(b), C.sizeof(b)):
+            raise LbzError("lbz_decoder_read failed")
+        return b
+
+    def array(self, which, slot, nbytes):
+        a = np.empty(max(nbytes, 1), np.uint8)
+        if self.L.lbz_decoder_read(self.h, which, slot, a.ctypes.data, nbytes):
+            raise LbzError("lbz_decoder_read failed")
+        return a[:nbytes]
+
+    @property
+    def last_wave_blocks(self):
+        return self.L.lbz_decoder_last_wave_blocks(self.h)
+
+    @property
+    def launches(self):
+        return self.L.lbz_decoder_launches(self.h)
+
+    @property
+    def last_ms(self):
+        return self.L.lbz_decoder_last_ms(self.h)
+
+    def stage_ms(self):
+        v = (C.c_double * 7)()
+        self.L.lbz_decoder_stage_ms(self.h, v)
+        return dict(zip(("upload", "scan", "retrieve", "successors", "walks", "expand", "tail"), list(v)))
+
+    @property
+    def device_bytes(self):
+        return self.L.lbz_decoder_device_bytes(self.h)

@@ -1,0 +1,649 @@
+// unbz_kernels.cuh -- device code of the bzip2 block DECOMPRESSOR.
+//
+// Replaces, for a whole batch of blocks at once, the reference's
+//   scan()      src/parse.c:281-342   -> k_ub_scan        (48-bit block magic at any bit offset)
+//   retrieve()  src/decode.c:518-791  -> k_ub_retrieve    (header, prefix decoding, inverse MTF, zero runs)
+//   decode()    src/decode.c:840-917  -> k_ub_lf_*, k_ub_walk1/rank/walk2, k_ub_period, k_ub_derand
+//   emit()      src/decode.c:936-1143 -> k_ub_rl_sum/scan/emit, k_ub_crc_fin
+//
+// Shape of the work.  Prefix decoding and the inverse MTF are serial inside a block (every code
+// length and every list state depends on the previous symbol), so k_ub_retrieve runs ONE thread per
+// block and gets its throughput from many blocks in flight.  Everything after it is re-stated so
+// that a block is worked on by thousands of threads:
+//   * the successor table of the inverse BWT is a stable counting sort by byte value
+//     (tile histograms -> per-value scan over tiles -> tile scatter);
+//   * the 900 k-step pointer chase is cut at ~3500 splitter nodes: every splitter walks to the next
+//     one (walk1), one thread ranks the splitters (rank), every splitter walks again and writes its
+//     piece of the text at its final position (walk2)  [Helman-JaJa list ranking];
+//   * undoing the initial run-length coding is a 5-state automaton; tiles publish their
+//     state-to-state maps and output sizes (rl_sum), one thread chains them (rl_scan), tiles then
+//     write their output and fold their CRC, shifted to the end of the block in GF(2), into one
+//     word per block (rl_emit, crc_fin).
+//
+// Every kernel here is written in a restricted style: no __syncthreads, no warp intrinsics, shared
+// memory only where a single thread of the CTA uses it.  That keeps the arithmetic identical when
+// the same source is compiled for the host by tests/simt_emul (UB_EMUL), which is how the logic is
+// checked on machines without a GPU.  The emulation is test infrastructure; the product library is
+// built from this file by nvcc only and has no host path.
+#ifndef UNBZ_KERNELS_CUH
+#define UNBZ_KERNELS_CUH
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef UB_EMUL
+#define UB_KERNEL static void
+#define UB_DEVICE static inline
+#define UB_SHARED static
+struct UbEmuIdx { unsigned gid, bid, tid; };
+extern UbEmuIdx ub_emu_idx;
+#define UB_GID ((uint64_t)ub_emu_idx.gid)
+#define UB_BID (ub_emu_idx.bid)
+#define UB_TID (ub_emu_idx.tid)
+static inline uint32_t ub_atomic_xor(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o ^ v; return o; }
+static inline uint32_t ub_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t ub_bswap32(uint32_t v) { return __builtin_bswap32(v); }
+#else
+#define UB_KERNEL __global__ void
+#define UB_DEVICE __device__ __forceinline__
+#define UB_SHARED __shared__
+#define UB_GID ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x)
+#define UB_BID (blockIdx.x)
+#define UB_TID (threadIdx.x)
+__device__ __forceinline__ uint32_t ub_atomic_xor(uint32_t *p, uint32_t v) { return atomicXor(p, v); }
+__device__ __forceinline__ uint32_t ub_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+__device__ __forceinline__ uint32_t ub_bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+#endif
+
+// ---- geometry ---------------------------------------------------------------------------------
+#define UB_MAXBLK 900000u                 // MAX_BLOCK_SIZE, src/common.h:50
+#define UB_STRIDE 900096u                 // per-slot stride of the byte / node arrays (multiple of 128)
+#define UB_SELCAP 18016u                  // selectors kept per block (18001 used, src/decode.c:631)
+#define UB_TL 2048u                       // counting-sort tile (bytes)
+#define UB_NTL ((UB_MAXBLK + UB_TL - 1) / UB_TL)          // 440
+#define UB_SPL_SHIFT 8u                   // a splitter every 256 nodes ...
+#define UB_KS ((UB_MAXBLK >> UB_SPL_SHIFT) + 2u)         // ... 3516 of them + 1 spare + the start node
+#define UB_TU 1024u                       // run-expansion tile (bytes of coded text)
+#define UB_NTU ((UB_MAXBLK + UB_TU - 1) / UB_TU)          // 879
+#define UB_UNSET 0xFFFFFFFFu
+#define UB_NOEMIT 0xFFFFFFFFFFFFFFFFull
+
+// status values = the reference's `enum error` (src/common.h:54-76), same order
+enum {
+  UB_OK = 0, UB_MORE, UB_FINISH, UB_ERR_MAGIC, UB_ERR_HEADER, UB_ERR_BITMAP, UB_ERR_TREES,
+  UB_ERR_GROUPS, UB_ERR_SELECTOR, UB_ERR_DELTA, UB_ERR_PREFIX, UB_ERR_INCOMPLT, UB_ERR_EMPTY,
+  UB_ERR_UNTERM, UB_ERR_RUNLEN, UB_ERR_BLKCRC, UB_ERR_STRMCRC, UB_ERR_OVERFLOW, UB_ERR_BWTIDX,
+  UB_ERR_EOF
+};
+
+// One block slot of a wave (plain data, shared by host and device).
+struct UbBlock {
+  uint64_t pos;          // bit position of the block magic in the input
+  uint64_t end_bit;      // first bit after the end-of-block symbol
+  uint64_t out_len;      // decoded bytes of the block
+  uint64_t out_off;      // where they go in the wave's output buffer; UB_NOEMIT = not emitted
+  uint32_t status;       // retrieve() status
+  uint32_t rand, bwt_idx, block_size;
+  uint32_t alpha_size, num_trees, num_selectors;
+  uint32_t period;       // length of the successor cycle through the primary index
+  uint32_t rl_state;     // run-expansion state after the last byte (4 = missing run length)
+  uint32_t crc_acc;      // XOR of the tiles' shifted CRC contributions
+  uint32_t crc;          // final block CRC
+  uint32_t pad;
+};
+
+// ---- bit reader (big-endian 32-bit words, as src/decode.c:372-426) -----------------------------
+struct UbBits {
+  const uint32_t *words;
+  uint64_t nwords;       // whole words of input, the tail zero-filled
+  uint64_t wi;           // next word to load
+  uint64_t v;            // live bits, left-justified
+  uint32_t w;            // number of live bits
+};
+
+// Position the reader on absolute bit p.  Returns false if p lies beyond the input.
+UB_DEVICE bool ub_bits_seek(UbBits &b, uint64_t p) {
+  b.wi = p >> 5;
+  b.v = 0; b.w = 0;
+  if (b.wi >= b.nwords) return false;
+  uint32_t off = (uint32_t)(p & 31u);
+  b.v = (uint64_t)ub_bswap32(b.words[b.wi]) << (32u + off);
+  b.w = 32u - off;
+  b.wi++;
+  return true;
+}
+// NEED(): at least 32 live bits, or report the end of input (src/decode.c:387-407).
+UB_DEVICE bool ub_bits_need(UbBits &b) {
+  if (b.w < 32u) {
+    if (b.wi >= b.nwords) return false;
+    b.v |= (uint64_t)ub_bswap32(b.words[b.wi]) << (32u - b.w);
+    b.w += 32u;
+    b.wi++;
+  }
+  return true;
+}
+UB_DEVICE uint32_t ub_bits_peek(const UbBits &b, uint32_t k) { return (uint32_t)(b.v >> (64u - k)); }
+UB_DEVICE void ub_bits_dump(UbBits &b, uint32_t k) { b.v <<= k; b.w -= k; }
+UB_DEVICE uint32_t ub_bits_take(UbBits &b, uint32_t k) { uint32_t x = ub_bits_peek(b, k); ub_bits_dump(b, k); return x; }
+UB_DEVICE uint64_t ub_bits_pos(const UbBits &b) { return (b.wi << 5) - b.w; }
+
+// ---- k_ub_scan: block magics at every bit offset (src/parse.c:281-342) --------------------------
+// One thread per input word: the 32 alignments that start inside it.
+UB_KERNEL k_ub_scan(const uint32_t *words, uint64_t nwords, uint64_t *hits, uint32_t *nhits, uint32_t hit_cap) {
+  uint64_t wi = UB_GID;
+  if (wi >= nwords) return;
+  uint64_t w0 = ub_bswap32(words[wi]);
+  uint64_t w1 = wi + 1 < nwords ? ub_bswap32(words[wi + 1]) : 0;
+  uint64_t w2 = wi + 2 < nwords ? ub_bswap32(words[wi + 2]) : 0;
+  uint64_t hi = (w0 << 32) | w1, lo = w2 << 32;
+  for (uint32_t s = 0; s < 32u; s++) {
+    uint64_t x = s ? ((hi << s) | (lo >> (64u - s))) : hi;
+    if ((x >> 16) == 0x314159265359ull) {
+      uint64_t p = (wi << 5) + s;
+      if (p + 48u <= (nwords << 5)) {
+        uint32_t k = ub_atomic_add(nhits, 1u);
+        if (k < hit_cap) hits[k] = p;
+      }
+    }
+  }
+}
+
+// ---- k_ub_retrieve ------------------------------------------------------------------------------
+#define UB_LUT_BITS 10u
+struct UbTree {
+  uint16_t lut[1u << UB_LUT_BITS];   // (symbol << 5) | length for codes <= 10 bits, 0 otherwise
+  uint32_t first[22];                // first code of each length (right-justified)
+  uint32_t count[22];
+  uint32_t offset[22];               // index into perm of the first symbol of each length
+  uint16_t perm[258];                // symbols in canonical order
+};
+
+// Move the byte at position r of a 256-entry list (packed little-endian in 64 words) to the front.
+UB_DEVICE uint32_t ub_mtf_front(uint32_t *lw, uint32_t r) {
+  uint32_t wr = r >> 2, sh = (r & 3u) * 8u;
+  uint32_t c = (lw[wr] >> sh) & 0xFFu;
+  uint32_t m = sh == 24u ? 0xFFFFFFFFu : ((1u << (sh + 8u)) - 1u);
+  uint32_t cur = lw[wr];
+  for (uint32_t k = wr; k > 0; k--) {
+    uint32_t below = lw[k - 1];
+    uint32_t shifted = (cur << 8) | (below >> 24);
+    lw[k] = (k == wr) ? ((shifted & m) | (cur & ~m)) : shifted;
+    cur = below;
+  }
+  {
+    uint32_t shifted = (cur << 8) | c;
+    lw[0] = (wr == 0) ? ((shifted & m) | (cur & ~m)) : shifted;
+  }
+  return c;
+}
+
+// One CTA of 32 threads per block slot; thread 0 does the work (see the file header).
+UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint32_t nblk,
+                        uint8_t *bwt_all, uint32_t *ftab_all, uint8_t *sel_all) {
+  UB_SHARED UbTree tree[6];
+  UB_SHARED uint32_t listw[64];
+  UB_SHARED uint32_t ftab[256];
+  if (UB_TID != 0) return;
+  const uint32_t b = UB_BID;
+  if (b >= nblk) return;
+  UbBlock &B = blk[b];
+  uint8_t *bwt = bwt_all + (size_t)b * UB_STRIDE;
+  uint8_t *sel = sel_all + (size_t)b * UB_SELCAP;
+  uint32_t status = UB_ERR_UNTERM;
+  uint32_t n = 0;
+  UbBits br;
+  br.words = words; br.nwords = nwords;
+
+  B.block_size = 0; B.end_bit = 0; B.rand = 0; B.bwt_idx = 0; B.alpha_size = 0;
+  B.num_trees = 0; B.num_selectors = 0;
+
+#define UB_FAIL(code) do { status = (code); goto finish; } while (0)
+#define UB_NEED() do { if (!ub_bits_need(br)) UB_FAIL(UB_ERR_EOF); } while (0)
+
+  {
+    uint32_t alpha, ntrees, nsel, nsym = 0;
+    uint32_t sl[6];
+    uint32_t run = 0, shift = 0, runch;
+
+    if (!ub_bits_seek(br, B.pos + 80u)) UB_FAIL(UB_ERR_EOF);
+    UB_NEED();
+    B.rand = ub_bits_take(br, 1);
+    B.bwt_idx = ub_bits_take(br, 24);
+
+    // byte map: 16 row flags, 16 bits per used row (src/decode.c:533-553)
+    UB_NEED();
+    {
+      uint32_t big = ub_bits_take(br, 16);
+      for (uint32_t i = 0; i < 64; i++) listw[i] = 0;
+      for (uint32_t i = 0; i < 16; i++) {
+        if (big & (0x8000u >> i)) {
+          uint32_t small = ub_bits_take(br, 16);
+          UB_NEED();
+          for (uint32_t j = 0; j < 16; j++)
+            if (small & (0x8000u >> j)) {
+              listw[nsym >> 2] |= (16u * i + j) << ((nsym & 3u) * 8u);
+              nsym++;
+            }
+        }
+      }
+    }
+    if (nsym == 0) UB_FAIL(UB_ERR_BITMAP);
+    alpha = nsym + 2u;
+    B.alpha_size = alpha;
+
+    ntrees = ub_bits_take(br, 3);
+    B.num_trees = ntrees;
+    if (ntrees < 2u || ntrees > 6u) UB_FAIL(UB_ERR_TREES);
+    nsel = ub_bits_take(br, 15);
+    B.num_selectors = nsel;
+    if (nsel == 0) UB_FAIL(UB_ERR_GROUPS);
+
+    // unary selector ranks, 6-bit look-ahead (src/decode.c:566-575)
+    for (uint32_t i = 0; i < nsel; i++) {
+      uint32_t x = ub_bits_peek(br, 6);
+      uint32_t k = 1;
+      while (k <= 6u && (x & (0x40u >> k))) k++;
+      if (k > ntrees) UB_FAIL(UB_ERR_SELECTOR);
+      if (i < UB_SELCAP) sel[i] = (uint8_t)(k - 1u);
+      ub_bits_dump(br, k);
+      UB_NEED();
+    }
+
+    // delta-coded lengths: up to three +-1 steps per 6-bit window, range checked once per
+    // window (src/decode.c:577-601 with its L[]/R[] tables)
+    for (uint32_t t = 0; t < ntrees; t++) {
+      UbTree &T = tree[t];
+      uint8_t len[258];
+      int cur = (int)ub_bits_take(br, 5);
+      uint32_t j = 0;
+      while (j < alpha) {
+        uint32_t x = ub_bits_peek(br, 6);
+        uint32_t used = 0;
+        bool done = false;
+        while (used + 2u <= 6u && (x & (0x20u >> used))) {
+          cur += (x & (0x20u >> (used + 1u))) ? -1 : 1;
+          used += 2u;
+        }
+        if (used < 6u) { used += 1u; done = true; }
+        if (cur < 1 || cur > 20) UB_FAIL(UB_ERR_DELTA);
+        if (done) len[j++] = (uint8_t)cur;
+        ub_bits_dump(br, used);
+        UB_NEED();
+      }
+      // make_tree(), src/decode.c:181-305: Kraft sum decides whether the tree is usable;
+      // a bad tree only matters if a group selects it
+      for (uint32_t k = 0; k < 22; k++) T.count[k] = 0;
+      for (uint32_t s = 0; s < alpha; s++) T.count[len[s]]++;
+      uint64_t kraft = 0;
+      for (uint32_t k = 1; k <= 20; k++) kraft += (uint64_t)T.count[k] << (20u - k);
+      if (kraft != (1u << 20)) {
+        sl[t] = kraft < (1u << 20) ? UB_ERR_INCOMPLT : UB_ERR_PREFIX;
+        continue;
+      }
+      sl[t] = t;
+      {
+        uint32_t code = 0, off = 0;
+        uint32_t fill[22];
+        for (uint32_t k = 1; k <= 20; k++) {
+          T.first[k] = code; T.offset[k] = off; fill[k] = off;
+          code = (code + T.count[k]) << 1;
+          off += T.count[k];
+        }
+        T.first[21] = 0; T.offset[21] = 0; fill[0] = 0; fill[21] = 0;
+        for (uint32_t s = 0; s < alpha; s++) T.perm[fill[len[s]]++] = (uint16_t)s;
+        for (uint32_t i = 0; i < (1u << UB_LUT_BITS); i++) T.lut[i] = 0;
+        for (uint32_t k = 1; k <= UB_LUT_BITS; k++) {
+          uint32_t span = 1u << (UB_LUT_BITS - k);
+          for (uint32_t q = 0; q < T.count[k]; q++) {
+            uint32_t s = T.perm[T.offset[k] + q];
+            uint32_t base = (T.first[k] + q) << (UB_LUT_BITS - k);
+            uint16_t e = (uint16_t)((s << 5) | k);
+            for (uint32_t z = 0; z < span; z++) T.lut[base + z] = e;
+          }
+        }
+      }
+    }
+
+    if (nsel > 18001u) nsel = 18001u;             // src/decode.c:631-632
+    for (uint32_t i = 0; i < 256; i++) ftab[i] = 0;
+    runch = listw[0] & 0xFFu;
+
+    for (uint32_t g = 0; g < nsel; g++) {
+      uint32_t r = sel[g];
+      uint32_t t = sl[r];
+      if (t >= 6u) UB_FAIL(t);                    // a bad tree is selected (src/decode.c:640-642)
+      for (; r > 0; r--) sl[r] = sl[r - 1];
+      sl[0] = t;
+      const UbTree &T = tree[t];
+
+      for (uint32_t j = 0; j < 50u; j++) {
+        UB_NEED();
+        uint32_t s, k;
+        uint32_t e = T.lut[ub_bits_peek(br, UB_LUT_BITS)];
+        if (e != 0) {
+          k = e & 31u; s = e >> 5;
+        } else {
+          uint32_t c20 = ub_bits_peek(br, 20);
+          k = UB_LUT_BITS + 1u;
+          for (;;) {
+            uint32_t c = c20 >> (20u - k);
+            if (c - T.first[k] < T.count[k]) { s = T.perm[T.offset[k] + c - T.first[k]]; break; }
+            if (++k > 20u) { s = 0; k = 20u; break; }   // unreachable for a complete code
+          }
+        }
+        ub_bits_dump(br, k);
+
+        if (s == alpha - 1u) {                    // end of block (src/decode.c:731-752)
+          if (run > UB_MAXBLK - n) UB_FAIL(UB_ERR_OVERFLOW);
+          ftab[runch] += run;
+          while (run--) bwt[n++] = (uint8_t)runch;
+          if (n == 0) UB_FAIL(UB_ERR_EMPTY);
+          if (B.bwt_idx >= n) UB_FAIL(UB_ERR_BWTIDX);
+          UB_FAIL(UB_OK);
+        }
+        if (s < 2u && run <= UB_MAXBLK) {         // RUNA / RUNB (src/decode.c:761-764)
+          run += (s + 1u) << shift++;
+          continue;
+        }
+        if (run > UB_MAXBLK - n) UB_FAIL(UB_ERR_OVERFLOW);
+        ftab[runch] += run;
+        while (run--) bwt[n++] = (uint8_t)runch;
+        runch = ub_mtf_front(listw, s - 1u);
+        shift = 0;
+        run = 1;
+      }
+    }
+    status = UB_ERR_UNTERM;
+  }
+finish:
+#undef UB_FAIL
+#undef UB_NEED
+  B.block_size = n;
+  B.end_bit = ub_bits_pos(br);
+  B.status = status;
+  B.period = n;
+  B.rl_state = 0;
+  B.crc_acc = 0;
+  B.crc = 0;
+  B.out_len = 0;
+  B.out_off = UB_NOEMIT;
+  if (status == UB_OK) {
+    uint32_t *f = ftab_all + (size_t)b * 256u;
+    for (uint32_t i = 0; i < 256; i++) f[i] = ftab[i];
+  }
+}
+
+// ---- successor table of the inverse BWT (src/decode.c:851-870) ---------------------------------
+// node[j] = (i << 8) | c  where i is the position of the q-th occurrence of byte c in the last
+// column and j = (#bytes < c) + q.  Walking x -> node[x] >> 8 from the primary index and reading
+// the low bytes spells the text forward.
+
+// thread per (slot, tile): byte histogram of the tile
+UB_KERNEL k_ub_lf_hist(const UbBlock *blk, uint32_t nblk, const uint8_t *bwt_all, uint32_t *tilehist) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_NTL), tile = (uint32_t)(g % UB_NTL);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t n = blk[b].block_size, lo = tile * UB_TL;
+  if (lo >= n) return;
+  uint32_t hi = lo + UB_TL < n ? lo + UB_TL : n;
+  const uint8_t *bwt = bwt_all + (size_t)b * UB_STRIDE;
+  uint32_t h[256];
+  for (uint32_t i = 0; i < 256; i++) h[i] = 0;
+  for (uint32_t i = lo; i < hi; i++) h[bwt[i]]++;
+  uint32_t *row = tilehist + ((size_t)b * UB_NTL + tile) * 256u;
+  for (uint32_t i = 0; i < 256; i++) row[i] = h[i];
+}
+
+// thread per (slot, byte value): running start of this value's bucket through the tiles
+UB_KERNEL k_ub_lf_scan(const UbBlock *blk, uint32_t nblk, const uint32_t *ftab_all, uint32_t *tilehist) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g >> 8), v = (uint32_t)(g & 255u);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  const uint32_t *f = ftab_all + (size_t)b * 256u;
+  uint32_t run = 0;
+  for (uint32_t i = 0; i < v; i++) run += f[i];
+  uint32_t n = blk[b].block_size, ntile = (n + UB_TL - 1u) / UB_TL;
+  uint32_t *col = tilehist + (size_t)b * UB_NTL * 256u + v;
+  for (uint32_t t = 0; t < ntile; t++) {
+    uint32_t c = col[(size_t)t * 256u];
+    col[(size_t)t * 256u] = run;
+    run += c;
+  }
+}
+
+// thread per (slot, tile): stable scatter
+UB_KERNEL k_ub_lf_scatter(const UbBlock *blk, uint32_t nblk, const uint8_t *bwt_all, const uint32_t *tilehist,
+                          uint32_t *node_all) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_NTL), tile = (uint32_t)(g % UB_NTL);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t n = blk[b].block_size, lo = tile * UB_TL;
+  if (lo >= n) return;
+  uint32_t hi = lo + UB_TL < n ? lo + UB_TL : n;
+  const uint8_t *bwt = bwt_all + (size_t)b * UB_STRIDE;
+  uint32_t *node = node_all + (size_t)b * UB_STRIDE;
+  const uint32_t *row = tilehist + ((size_t)b * UB_NTL + tile) * 256u;
+  uint32_t cnt[256];
+  for (uint32_t i = 0; i < 256; i++) cnt[i] = row[i];
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t c = bwt[i];
+    node[cnt[c]++] = (i << 8) | c;
+  }
+}
+
+// ---- the chase, cut at splitters ----------------------------------------------------------------
+// Splitter nodes: every node whose index is a multiple of 256, plus the primary index.  Slot k of a
+// block's splitter table stands for node k*256; the last slot (UB_KS-1) stands for the primary
+// index when that is not a multiple of 256.
+UB_DEVICE bool ub_is_split(uint32_t x, uint32_t idx) { return (x & ((1u << UB_SPL_SHIFT) - 1u)) == 0 || x == idx; }
+UB_DEVICE uint32_t ub_split_slot(uint32_t x, uint32_t idx) {
+  return (x == idx && (idx & ((1u << UB_SPL_SHIFT) - 1u)) != 0) ? UB_KS - 1u : (x >> UB_SPL_SHIFT);
+}
+UB_DEVICE bool ub_slot_node(uint32_t k, uint32_t n, uint32_t idx, uint32_t *x) {
+  if (k == UB_KS - 1u) {
+    if ((idx & ((1u << UB_SPL_SHIFT) - 1u)) == 0) return false;
+    *x = idx;
+    return true;
+  }
+  uint32_t node = k << UB_SPL_SHIFT;
+  if (node >= n) return false;
+  *x = node;
+  return true;
+}
+
+// thread per (slot, splitter): length of the piece that starts here and the splitter that ends it
+UB_KERNEL k_ub_walk1(const UbBlock *blk, uint32_t nblk, const uint32_t *node_all, uint32_t *segnext,
+                     uint32_t *seglen) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_KS), k = (uint32_t)(g % UB_KS);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t n = blk[b].block_size, idx = blk[b].bwt_idx, x;
+  if (!ub_slot_node(k, n, idx, &x)) return;
+  const uint32_t *node = node_all + (size_t)b * UB_STRIDE;
+  uint32_t len = 0;
+  do {
+    x = node[x] >> 8;
+    len++;
+  } while (!ub_is_split(x, idx));
+  segnext[(size_t)b * UB_KS + k] = ub_split_slot(x, idx);
+  seglen[(size_t)b * UB_KS + k] = len;
+}
+
+// thread per slot: text position of every splitter on the cycle through the primary index.
+// If the cycle closes before block_size steps the text is periodic (src/decode.c:866-868) and
+// `period` says how much of it the second walk produces.
+UB_KERNEL k_ub_rank(UbBlock *blk, uint32_t nblk, const uint32_t *segnext, const uint32_t *seglen,
+                    uint32_t *segpos) {
+  uint64_t b = UB_GID;
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t n = blk[b].block_size, idx = blk[b].bwt_idx;
+  uint32_t s = ub_split_slot(idx, idx);
+  uint32_t pos = 0;
+  const size_t base = (size_t)b * UB_KS;
+  while (pos < n && segpos[base + s] == UB_UNSET) {
+    segpos[base + s] = pos;
+    pos += seglen[base + s];
+    s = segnext[base + s];
+  }
+  blk[b].period = pos < n ? pos : n;
+}
+
+// thread per (slot, splitter): write the piece
+UB_KERNEL k_ub_walk2(const UbBlock *blk, uint32_t nblk, const uint32_t *node_all, const uint32_t *seglen,
+                     const uint32_t *segpos, uint8_t *txt_all) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_KS), k = (uint32_t)(g % UB_KS);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t p = segpos[(size_t)b * UB_KS + k];
+  if (p == UB_UNSET) return;
+  uint32_t n = blk[b].block_size, idx = blk[b].bwt_idx, x;
+  if (!ub_slot_node(k, n, idx, &x)) return;
+  const uint32_t *node = node_all + (size_t)b * UB_STRIDE;
+  uint8_t *txt = txt_all + (size_t)b * UB_STRIDE;
+  uint32_t len = seglen[(size_t)b * UB_KS + k];
+  for (uint32_t t = 0; t < len && p + t < n; t++) {
+    uint32_t v = node[x];
+    txt[p + t] = (uint8_t)v;
+    x = v >> 8;
+  }
+}
+
+// thread per (slot, 1024 text positions): repeat the period
+UB_KERNEL k_ub_period(const UbBlock *blk, uint32_t nblk, uint8_t *txt_all) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_NTU), tile = (uint32_t)(g % UB_NTU);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t n = blk[b].block_size, p = blk[b].period;
+  if (p >= n) return;
+  uint32_t lo = tile * UB_TU, hi = lo + UB_TU < n ? lo + UB_TU : n;
+  if (lo < p) lo = p;
+  uint8_t *txt = txt_all + (size_t)b * UB_STRIDE;
+  for (uint32_t i = lo; i < hi; i++) txt[i] = txt[i % p];
+}
+
+// thread per slot: undo the block randomisation of old bzip2 files (src/decode.c:893-899)
+UB_KERNEL k_ub_derand(const UbBlock *blk, uint32_t nblk, uint8_t *txt_all, const uint16_t *rtab) {
+  uint64_t b = UB_GID;
+  if (b >= nblk || blk[b].status != UB_OK || !blk[b].rand) return;
+  uint32_t n = blk[b].block_size;
+  uint8_t *txt = txt_all + (size_t)b * UB_STRIDE;
+  uint32_t k = 0, j = 617u;
+  while (j < n) {
+    txt[j] ^= 1u;
+    k = (k + 1u) & 511u;
+    j += rtab[k];
+  }
+}
+
+// ---- run expansion + CRC (src/decode.c:936-1143) ------------------------------------------------
+// State = number of equal literal bytes just seen (1..3), 4 = "the next byte is a repeat count",
+// 0 = "the previous byte was a count" (also the start state).
+struct UbTileSum {
+  uint32_t out[5];       // output bytes of the tile for each entry state
+  uint32_t end;          // exit state for each entry state, 3 bits each
+};
+
+UB_KERNEL k_ub_rl_sum(const UbBlock *blk, uint32_t nblk, const uint8_t *txt_all, UbTileSum *tsum) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_NTU), tile = (uint32_t)(g % UB_NTU);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t n = blk[b].block_size, lo = tile * UB_TU;
+  if (lo >= n) return;
+  uint32_t hi = lo + UB_TU < n ? lo + UB_TU : n;
+  const uint8_t *txt = txt_all + (size_t)b * UB_STRIDE;
+  uint32_t st[5], out[5];
+  for (uint32_t s = 0; s < 5; s++) { st[s] = s; out[s] = 0; }
+  uint32_t prev = lo ? txt[lo - 1] : 0x100u;
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t c = txt[i];
+    bool eq = (c == prev);
+    for (uint32_t s = 0; s < 5; s++) {
+      if (st[s] == 4u) { out[s] += c; st[s] = 0; }
+      else { out[s] += 1u; st[s] = (st[s] >= 1u && eq) ? st[s] + 1u : 1u; }
+    }
+    prev = c;
+  }
+  UbTileSum &T = tsum[(size_t)b * UB_NTU + tile];
+  uint32_t e = 0;
+  for (uint32_t s = 0; s < 5; s++) { T.out[s] = out[s]; e |= st[s] << (3u * s); }
+  T.end = e;
+}
+
+// thread per slot: entry state and output offset of every tile
+UB_KERNEL k_ub_rl_scan(UbBlock *blk, uint32_t nblk, const UbTileSum *tsum, uint32_t *tstate, uint64_t *toff) {
+  uint64_t b = UB_GID;
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t n = blk[b].block_size, ntile = (n + UB_TU - 1u) / UB_TU;
+  uint32_t st = 0;
+  uint64_t off = 0;
+  for (uint32_t t = 0; t < ntile; t++) {
+    const UbTileSum &T = tsum[(size_t)b * UB_NTU + t];
+    tstate[(size_t)b * UB_NTU + t] = st;
+    toff[(size_t)b * UB_NTU + t] = off;
+    off += T.out[st];
+    st = (T.end >> (3u * st)) & 7u;
+  }
+  blk[b].out_len = off;
+  blk[b].rl_state = st;
+}
+
+// a * b in GF(2)[x] / (CRC-32/BZIP2 polynomial); bit k of a word = coefficient of x^k
+UB_DEVICE uint32_t ub_gf_mul(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+  for (int i = 31; i >= 0; i--) {
+    r = (r << 1) ^ ((r & 0x80000000u) ? 0x04C11DB7u : 0u);
+    if ((b >> i) & 1u) r ^= a;
+  }
+  return r;
+}
+// a * x^(8*nbytes); pw[k] = x^(8 * 2^k)
+UB_DEVICE uint32_t ub_gf_shift(uint32_t a, uint64_t nbytes, const uint32_t *pw) {
+  for (uint32_t k = 0; nbytes; k++, nbytes >>= 1)
+    if (nbytes & 1u) a = ub_gf_mul(a, pw[k]);
+  return a;
+}
+
+// thread per (slot, tile): write the tile's output, fold its CRC into the block's accumulator
+UB_KERNEL k_ub_rl_emit(UbBlock *blk, uint32_t nblk, const uint8_t *txt_all, const UbTileSum *tsum,
+                       const uint32_t *tstate, const uint64_t *toff, uint8_t *out, const uint32_t *crctab,
+                       const uint32_t *pw) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_NTU), tile = (uint32_t)(g % UB_NTU);
+  if (b >= nblk || blk[b].status != UB_OK || blk[b].out_off == UB_NOEMIT) return;
+  uint32_t n = blk[b].block_size, lo = tile * UB_TU;
+  if (lo >= n) return;
+  uint32_t hi = lo + UB_TU < n ? lo + UB_TU : n;
+  const uint8_t *txt = txt_all + (size_t)b * UB_STRIDE;
+  uint32_t st = tstate[(size_t)b * UB_NTU + tile];
+  uint64_t off = toff[(size_t)b * UB_NTU + tile];
+  uint8_t *o = out + blk[b].out_off + off;
+  uint64_t w = 0;
+  uint32_t crc = 0;
+  uint32_t prev = lo ? txt[lo - 1] : 0x100u;
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t c = txt[i];
+    if (st == 4u) {
+      for (uint32_t k = 0; k < c; k++) {
+        o[w++] = (uint8_t)prev;
+        crc = (crc << 8) ^ crctab[(crc >> 24) ^ prev];
+      }
+      st = 0;
+    } else {
+      o[w++] = (uint8_t)c;
+      crc = (crc << 8) ^ crctab[(crc >> 24) ^ c];
+      st = (st >= 1u && c == prev) ? st + 1u : 1u;
+    }
+    prev = c;
+  }
+  uint64_t after = blk[b].out_len - (off + w);
+  ub_atomic_xor(&blk[b].crc_acc, ub_gf_shift(crc, after, pw));
+}
+
+// thread per slot: add the shifted initial register value, invert
+UB_KERNEL k_ub_crc_fin(UbBlock *blk, uint32_t nblk, const uint32_t *pw) {
+  uint64_t b = UB_GID;
+  if (b >= nblk || blk[b].status != UB_OK || blk[b].out_off == UB_NOEMIT) return;
+  blk[b].crc = ~(blk[b].crc_acc ^ ub_gf_shift(0xFFFFFFFFu, blk[b].out_len, pw));
+}
+
+#endif  // UNBZ_KERNELS_CUH

@@ -1,0 +1,110 @@
+"""ctypes bindings for tests/simt_emul/libunbz_emul.so -- TEST INFRASTRUCTURE ONLY.
+
+The library is the decompressor's device + orchestration source compiled for the host with every
+kernel launch run as a sequential loop (see tests/simt_emul/unbz_emul.cpp).  It exists so that the
+decode logic can be checked against the oracle where there is no GPU; the product never loads it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "simt_emul")
+CSRC = os.path.join(ROOT, "lbzip2_b200", "csrc")
+u8p = C.POINTER(C.c_uint8)
+
+
+class DStreamInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "status", "num_blocks", "num_streams", "bad_block", "garbage", "candidates",
+        "false_candidates", "waves")] + [("end_bit", C.c_uint64)]
+
+
+class DBlock(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("pos", "end_bit", "out_len", "out_off")] + [
+        (n, C.c_uint32) for n in ("status", "rand", "bwt_idx", "block_size", "alpha_size", "num_trees",
+                                  "num_selectors", "period", "rl_state", "crc_acc", "crc", "pad")]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(EMU_DIR, "libunbz_emul.so")
+        deps = [os.path.join(EMU_DIR, "unbz_emul.cpp"), os.path.join(CSRC, "unbz_kernels.cuh"),
+                os.path.join(CSRC, "unbz_engine.inc"), os.path.join(ROOT, "include", "lbzip2_b200.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + CSRC, "-o", so, deps[0]])
+        L = C.CDLL(so)
+        L.emu_decoder_create.restype = C.c_void_p
+        L.emu_decoder_create.argtypes = [C.c_int, C.c_size_t, C.c_size_t]
+        L.emu_decoder_destroy.argtypes = [C.c_void_p]
+        L.emu_decompress.restype = C.c_int
+        L.emu_decompress.argtypes = [C.c_void_p, u8p, C.c_size_t, u8p, C.c_size_t, C.POINTER(C.c_size_t),
+                                     C.POINTER(DStreamInfo), C.c_uint]
+        L.emu_scan_blocks.restype = C.c_long
+        L.emu_scan_blocks.argtypes = [C.c_void_p, u8p, C.c_size_t, C.POINTER(C.c_uint64), C.c_size_t]
+        L.emu_decoder_read.restype = C.c_int
+        L.emu_decoder_read.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_size_t]
+        L.emu_last_wave_blocks.restype = C.c_uint32
+        L.emu_last_wave_blocks.argtypes = [C.c_void_p]
+        L.emu_launches.restype = C.c_uint64
+        L.emu_launches.argtypes = [C.c_void_p]
+        L.emu_mtf_front.restype = C.c_uint32
+        L.emu_mtf_front.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
+        L.emu_gf_shift.restype = C.c_uint32
+        L.emu_gf_shift.argtypes = [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32)]
+        L.emu_set_reverse.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+class EmuDecoder:
+    """Same surface as lbzip2_b200.Decoder, over the emulation."""
+
+    def __init__(self, max_blocks=8, in_cap=1 << 22, out_cap=0):
+        self.L = lib()
+        self.h = self.L.emu_decoder_create(max_blocks, in_cap, out_cap)
+        assert self.h
+
+    def close(self):
+        if self.h:
+            self.L.emu_decoder_destroy(self.h)
+            self.h = None
+
+    def decompress(self, z, cap=None):
+        a = np.frombuffer(bytes(z), dtype=np.uint8) if len(z) else np.zeros(1, np.uint8)
+        if cap is None:
+            cap = max(1 << 20, 64 * len(z))
+        out = np.empty(max(cap, 1), np.uint8)
+        n = C.c_size_t(0)
+        info = DStreamInfo()
+        st = self.L.emu_decompress(self.h, a.ctypes.data_as(u8p), len(z), out.ctypes.data_as(u8p), cap,
+                                   C.byref(n), C.byref(info), 0)
+        return st, out[: n.value].tobytes(), info
+
+    def scan(self, z):
+        a = np.frombuffer(bytes(z), dtype=np.uint8) if len(z) else np.zeros(1, np.uint8)
+        cap = len(z) // 6 + 64
+        pos = (C.c_uint64 * cap)()
+        k = self.L.emu_scan_blocks(self.h, a.ctypes.data_as(u8p), len(z), pos, cap)
+        assert k >= 0
+        return list(pos[:k])
+
+    def block(self, slot):
+        b = DBlock()
+        assert self.L.emu_decoder_read(self.h, 0, slot, C.byref(b), C.sizeof(b)) == 0
+        return b
+
+    def array(self, which, slot, nbytes):
+        a = np.empty(max(nbytes, 1), np.uint8)
+        assert self.L.emu_decoder_read(self.h, which, slot, a.ctypes.data_as(C.c_void_p), nbytes) == 0
+        return a[:nbytes]
+
+    @property
+    def last_wave_blocks(self):
+        return self.L.emu_last_wave_blocks(self.h)

@@ -33,6 +33,22 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(lbzip2_b200.LbzError):
         lbzip2_b200.Engine(device=0, level=1, max_chunks=1)
+    with pytest.raises(lbzip2_b200.LbzError):
+        lbzip2_b200.Decoder(device=0, max_blocks=1, in_cap=1 << 16)
+
+
+def test_product_is_not_built_with_the_host_emulation():
+    # tests/simt_emul compiles the decompressor's kernels for the host to check their logic where
+    # there is no GPU; the product build must never define that switch nor export emulation symbols
+    mk = open(os.path.join(ROOT, "lbzip2_b200", "csrc", "Makefile")).read()
+    assert "UB_EMUL" not in mk and "simt_emul" not in mk
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", lbzip2_b200.lib_path()], capture_output=True, text=True).stdout
+    assert "emu_" not in syms
+    for root, _, files in os.walk(os.path.join(ROOT, "lbzip2_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "emul" not in open(os.path.join(root, f)).read(), f
 
 
 def test_product_does_not_link_oracle():
