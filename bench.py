@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--workload", default="text", choices=["text", "random", "runs_fib"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-decompress", action="store_true", help="skip the decompression leg")
     return ap.parse_args()
 
 
@@ -188,6 +189,94 @@ def run_reference(a):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ decompress leg ---
+def decompress_leg(a, lbzip2_b200, L, local, stream, data, recs):
+    """Output MB/s of lbz_decompress_stream on the .bz2 the compress leg produced (same 100 MB).
+    value: compressed bytes already in HBM, decoded bytes left in HBM; e2e: pinned host in/out."""
+    import torch
+    from lbzip2_b200 import api
+    nz, nbytes = len(stream), len(data)
+    steps, warm = min(a.steps, 5), min(a.warmup, 3)
+    dec = lbzip2_b200.Decoder(device=local, max_blocks=len(recs) + 8, in_cap=nz + 64, out_cap=nbytes + (1 << 20))
+    h_z = L.lbz_host_alloc(nz)
+    h_o = L.lbz_host_alloc(nbytes + 64)
+    C.memmove(h_z, stream, nz)
+    hbm_peak, peak_kind = peaks()
+
+    def run(flags, out_ptr):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        st, n, info = dec.decompress_ptr(h_z, nz, out_ptr, nbytes + 64, flags)
+        ev1.record()
+        ev1.synchronize()
+        if st != 0 or n != nbytes:
+            raise RuntimeError("decoder returned status %d, %d bytes" % (st, n))
+        return ev0.elapsed_time(ev1), info
+
+    def timed(flags, out_ptr):
+        for _ in range(warm):
+            run(flags, out_ptr)
+        torch.cuda.synchronize()
+        l0 = dec.launches
+        ms, stage, info = [], {}, None
+        for _ in range(steps):
+            t, info = run(flags, out_ptr)
+            ms.append(t)
+            for k, v in dec.stage_ms().items():
+                stage[k] = stage.get(k, 0.0) + v / steps
+        torch.cuda.synchronize()
+        return sum(ms) / steps, stage, info, (dec.launches - l0) // steps
+
+    dec.load(h_z, nz)
+    ms_dev, stage, info, launches = timed(api.D_RESIDENT_INPUT | api.D_DEVICE_OUTPUT, None)
+    dev_sha = hashlib.sha256(dec.array(api.DA_OUT, 0, nbytes).tobytes()).hexdigest()
+    ms_host, _, _, _ = timed(0, h_o)
+    host_out = bytes((C.c_uint8 * nbytes).from_address(h_o))
+    want = hashlib.sha256(data).hexdigest()
+    # stage-interface bytes of the decode path: z + n' (prefix decode: bits in, last column out)
+    # + 5n' (successor table) + 5n' (walks: nodes in, text out) + n' + n (run expansion)
+    nprime = sum(r.nblock for r in recs)
+    path_bytes = nz + 12 * nprime + nbytes
+    res = {
+        "metric": "output MB/s of batch decompression of the same stream", "unit": "MB/s",
+        "value": round(nbytes / MB / (ms_dev / 1e3), 2), "ms_per_step": round(ms_dev, 3),
+        "e2e": {"value": round(nbytes / MB / (ms_host / 1e3), 2), "unit": "MB/s", "ms_per_step": round(ms_host, 3),
+                "h2d_bytes_per_step": nz, "d2h_bytes_per_step": nbytes, "api": "lbz_decompress_stream (pinned host in/out)"},
+        "steps": steps, "warmup": warm, "gpu_launches": int(launches),
+        "blocks": int(info.num_blocks), "candidates": int(info.candidates), "waves": int(info.waves),
+        "stage_ms": {k: round(v, 3) for k, v in stage.items()},
+        "path_roofline": {"model": "z + 12n' + n per block", "bytes_per_step": int(path_bytes),
+                          "achieved": round(path_bytes / (ms_dev / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                          "frac": round(path_bytes / (ms_dev / 1e3) / 1e9 / hbm_peak, 5), "peak_kind": peak_kind},
+        "verified": {"device_output_sha256_equals_input": dev_sha == want,
+                     "host_output_equals_input": host_out == data},
+        "device_bytes": int(dec.device_bytes),
+    }
+    binp = ref_binary()
+    if binp and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        path = os.path.join(tmp, "lbz_bench_%d.bz2" % os.getpid())
+        with open(path, "wb") as f:
+            f.write(stream)
+        try:
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                with open(os.devnull, "wb") as dn:
+                    subprocess.run([binp, "-d", "-n%d" % cores, "-c", path], stdout=dn, check=True)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+        finally:
+            os.unlink(path)
+        res["cpu_baseline"] = {"value": round(nbytes / MB / best, 2), "unit": "MB/s", "cores": cores, "kind": "reference",
+                               "sample": "the whole stream, lbzip2 -d -n%d, /dev/shm -> /dev/null, best of 3" % cores}
+    L.lbz_host_free(h_z)
+    L.lbz_host_free(h_o)
+    dec.close()
+    return res
 
 
 # ------------------------------------------------------------------------ our arm ---
@@ -351,6 +440,15 @@ def run_ours(a):
             verified["gathered_stream_roundtrip"] = ok
         verified["periodic_blocks"] = sum(1 for r in recs if r.tie_count > 1)
 
+    # ---- decompression leg: the stream just produced, back through the
+    # batch decompressor; reported under "decompress", the headline stays the compressor ----
+    decomp = None
+    if world == 1 and rank == 0 and not a.no_verify and not a.no_decompress:
+        try:
+            decomp = decompress_leg(a, lbzip2_b200, L, local, stream, data, recs)
+        except Exception as ex:  # the compressor's line must survive a decoder problem
+            decomp = {"error": "%s: %s" % (type(ex).__name__, ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -399,6 +497,8 @@ def run_ours(a):
         "wall_ms_per_step": round(rd["wall_ms"] / a.steps, 3), "verified": verified,
         "compressed_ratio": round(nbytes / max(n_out, 1), 3),
     }
+    if decomp is not None:
+        line["decompress"] = decomp
     if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
         binp = ref_binary()
