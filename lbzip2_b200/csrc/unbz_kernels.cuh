@@ -2,14 +2,18 @@
 //
 // Replaces, for a whole batch of blocks at once, the reference's
 //   scan()      src/parse.c:281-342   -> k_ub_scan        (48-bit block magic at any bit offset)
-//   retrieve()  src/decode.c:518-791  -> k_ub_retrieve    (header, prefix decoding, inverse MTF, zero runs)
+//   retrieve()  src/decode.c:518-791  -> k_ub_retrieve    (header, prefix decoding, zero-run arithmetic)
+//                                        k_ub_mtf_tile/scan/fill (inverse MTF, run expansion)
 //   decode()    src/decode.c:840-917  -> k_ub_lf_*, k_ub_walk1/rank/walk2, k_ub_period, k_ub_derand
 //   emit()      src/decode.c:936-1143 -> k_ub_rl_sum/scan/emit, k_ub_crc_fin
 //
-// Shape of the work.  Prefix decoding and the inverse MTF are serial inside a block (every code
-// length and every list state depends on the previous symbol), so k_ub_retrieve runs ONE thread per
-// block and gets its throughput from many blocks in flight.  Everything after it is re-stated so
-// that a block is worked on by thousands of threads:
+// Shape of the work.  Prefix decoding is serial inside a block (where a code starts depends on every
+// code before it), so k_ub_retrieve runs ONE thread per block, does nothing but decode, and gets its
+// throughput from many blocks in flight: it leaves a token per list move (rank, start of the new
+// byte's run).  Everything after it is re-stated so that a block is worked on by thousands of threads:
+//   * the inverse MTF is a product of list permutations: tiles of 1024 tokens compute their own
+//     permutation (mtf_tile), one thread per block chains them into the list at every tile start
+//     (mtf_scan), tiles then replay their tokens and fill the runs of the last column (mtf_fill);
 //   * the successor table of the inverse BWT is a stable counting sort by byte value
 //     (tile histograms -> per-value scan over tiles -> tile scatter);
 //   * the 900 k-step pointer chase is cut at ~3500 splitter nodes: every splitter walks to the next
@@ -89,36 +93,39 @@ struct UbBlock {
   uint32_t rl_state;     // run-expansion state after the last byte (4 = missing run length)
   uint32_t crc_acc;      // XOR of the tiles' shifted CRC contributions
   uint32_t crc;          // final block CRC
-  uint32_t pad;
+  uint32_t ntok;         // list moves recorded by k_ub_retrieve
 };
 
 // ---- bit reader (big-endian 32-bit words, as src/decode.c:372-426) -----------------------------
 struct UbBits {
   const uint32_t *words;
   uint64_t nwords;       // whole words of input, the tail zero-filled
-  uint64_t wi;           // next word to load
+  uint64_t wi;           // next word to append
   uint64_t v;            // live bits, left-justified
   uint32_t w;            // number of live bits
+  uint32_t ahead;        // words[wi], loaded one refill early so that its latency is hidden
 };
 
 // Position the reader on absolute bit p.  Returns false if p lies beyond the input.
 UB_DEVICE bool ub_bits_seek(UbBits &b, uint64_t p) {
   b.wi = p >> 5;
-  b.v = 0; b.w = 0;
+  b.v = 0; b.w = 0; b.ahead = 0;
   if (b.wi >= b.nwords) return false;
   uint32_t off = (uint32_t)(p & 31u);
   b.v = (uint64_t)ub_bswap32(b.words[b.wi]) << (32u + off);
   b.w = 32u - off;
   b.wi++;
+  b.ahead = b.wi < b.nwords ? b.words[b.wi] : 0u;
   return true;
 }
 // NEED(): at least 32 live bits, or report the end of input (src/decode.c:387-407).
 UB_DEVICE bool ub_bits_need(UbBits &b) {
   if (b.w < 32u) {
     if (b.wi >= b.nwords) return false;
-    b.v |= (uint64_t)ub_bswap32(b.words[b.wi]) << (32u - b.w);
+    b.v |= (uint64_t)ub_bswap32(b.ahead) << (32u - b.w);
     b.w += 32u;
     b.wi++;
+    b.ahead = b.wi < b.nwords ? b.words[b.wi] : 0u;
   }
   return true;
 }
@@ -178,19 +185,22 @@ UB_DEVICE uint32_t ub_mtf_front(uint32_t *lw, uint32_t r) {
 }
 
 // One CTA of 32 threads per block slot; thread 0 does the work (see the file header).
+// Output per block: the initial list (list0, 64 packed words), and one token per list move:
+// tok_rank[k] = rank moved to the front, tok_pos[k] = position in the last column where the run of
+// the byte that arrives at the front begins.  The byte at the front of list0 fills [0, tok_pos[0]).
 UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint32_t nblk,
-                        uint8_t *bwt_all, uint32_t *ftab_all, uint8_t *sel_all) {
+                        uint8_t *rank_all, uint32_t *pos_all, uint32_t *list0_all, uint8_t *sel_all) {
   UB_SHARED UbTree tree[6];
   UB_SHARED uint32_t listw[64];
-  UB_SHARED uint32_t ftab[256];
   if (UB_TID != 0) return;
   const uint32_t b = UB_BID;
   if (b >= nblk) return;
   UbBlock &B = blk[b];
-  uint8_t *bwt = bwt_all + (size_t)b * UB_STRIDE;
+  uint8_t *tok_rank = rank_all + (size_t)b * UB_STRIDE;
+  uint32_t *tok_pos = pos_all + (size_t)b * UB_STRIDE;
   uint8_t *sel = sel_all + (size_t)b * UB_SELCAP;
   uint32_t status = UB_ERR_UNTERM;
-  uint32_t n = 0;
+  uint32_t n = 0, ntok = 0;
   UbBits br;
   br.words = words; br.nwords = nwords;
 
@@ -203,7 +213,7 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
   {
     uint32_t alpha, ntrees, nsel, nsym = 0;
     uint32_t sl[6];
-    uint32_t run = 0, shift = 0, runch;
+    uint32_t run = 0, shift = 0;
 
     if (!ub_bits_seek(br, B.pos + 80u)) UB_FAIL(UB_ERR_EOF);
     UB_NEED();
@@ -305,8 +315,10 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
     }
 
     if (nsel > 18001u) nsel = 18001u;             // src/decode.c:631-632
-    for (uint32_t i = 0; i < 256; i++) ftab[i] = 0;
-    runch = listw[0] & 0xFFu;
+    {
+      uint32_t *l0 = list0_all + (size_t)b * 256u;
+      for (uint32_t i = 0; i < 64; i++) l0[i] = listw[i];
+    }
 
     for (uint32_t g = 0; g < nsel; g++) {
       uint32_t r = sel[g];
@@ -335,8 +347,7 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
 
         if (s == alpha - 1u) {                    // end of block (src/decode.c:731-752)
           if (run > UB_MAXBLK - n) UB_FAIL(UB_ERR_OVERFLOW);
-          ftab[runch] += run;
-          while (run--) bwt[n++] = (uint8_t)runch;
+          n += run;
           if (n == 0) UB_FAIL(UB_ERR_EMPTY);
           if (B.bwt_idx >= n) UB_FAIL(UB_ERR_BWTIDX);
           UB_FAIL(UB_OK);
@@ -346,9 +357,10 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
           continue;
         }
         if (run > UB_MAXBLK - n) UB_FAIL(UB_ERR_OVERFLOW);
-        ftab[runch] += run;
-        while (run--) bwt[n++] = (uint8_t)runch;
-        runch = ub_mtf_front(listw, s - 1u);
+        n += run;
+        tok_rank[ntok] = (uint8_t)(s - 1u);
+        tok_pos[ntok] = n;
+        ntok++;
         shift = 0;
         run = 1;
       }
@@ -367,9 +379,76 @@ finish:
   B.crc = 0;
   B.out_len = 0;
   B.out_off = UB_NOEMIT;
-  if (status == UB_OK) {
-    uint32_t *f = ftab_all + (size_t)b * 256u;
-    for (uint32_t i = 0; i < 256; i++) f[i] = ftab[i];
+  B.ntok = ntok;
+}
+
+// ---- inverse MTF + run expansion (src/decode.c:428-516 mtf_one, :766-775) -----------------------
+#define UB_TM 1024u                                        // tokens per tile
+#define UB_NTM ((UB_MAXBLK + UB_TM) / UB_TM)              // 879 (a block has at most 900001 tokens)
+UB_DEVICE uint32_t ub_mtf_ntile(uint32_t ntok) { return ntok ? (ntok + UB_TM - 1u) / UB_TM : 1u; }
+
+// Per slot and tile, 128 words of scratch: [0,64) the tile's move product as a position map
+// ("what stood at position p before the tile stands at inv[p] after it", one byte per position),
+// [64,128) the list at the tile's start (filled by k_ub_mtf_scan).
+#define UB_TPW 128u
+
+// thread per (slot, tile): product of the tile's moves
+UB_KERNEL k_ub_mtf_tile(const UbBlock *blk, uint32_t nblk, const uint8_t *rank_all, uint32_t *tileperm) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_NTM), tile = (uint32_t)(g % UB_NTM);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t ntok = blk[b].ntok;
+  if (tile >= ub_mtf_ntile(ntok)) return;
+  uint32_t lo = tile * UB_TM, hi = lo + UB_TM < ntok ? lo + UB_TM : ntok;
+  const uint8_t *rk = rank_all + (size_t)b * UB_STRIDE;
+  uint32_t lw[64];
+  for (uint32_t i = 0; i < 64; i++) lw[i] = (4u * i) | ((4u * i + 1u) << 8) | ((4u * i + 2u) << 16) | ((4u * i + 3u) << 24);
+  for (uint32_t k = lo; k < hi; k++) ub_mtf_front(lw, rk[k]);
+  // lw: position i now holds what stood at position lw[i]; store the inverse map
+  uint8_t *inv = (uint8_t *)(tileperm + ((size_t)b * UB_NTM + tile) * UB_TPW);
+  for (uint32_t i = 0; i < 256; i++) inv[(lw[i >> 2] >> ((i & 3u) * 8u)) & 0xFFu] = (uint8_t)i;
+}
+
+// thread per (slot, list element): follow the element through the tiles and write it into the
+// start list of every tile at the position it has there
+UB_KERNEL k_ub_mtf_scan(const UbBlock *blk, uint32_t nblk, const uint32_t *list0_all, uint32_t *tileperm) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g >> 8), e = (uint32_t)(g & 255u);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t ntile = ub_mtf_ntile(blk[b].ntok);
+  uint8_t val = (uint8_t)((list0_all[(size_t)b * 256u + (e >> 2)] >> ((e & 3u) * 8u)) & 0xFFu);
+  uint32_t p = e;
+  for (uint32_t t = 0; t < ntile; t++) {
+    uint8_t *base = (uint8_t *)(tileperm + ((size_t)b * UB_NTM + t) * UB_TPW);
+    base[256u + p] = val;
+    p = base[p];
+  }
+}
+
+// thread per (slot, tile): replay the tile's moves from its start list and fill the runs
+UB_KERNEL k_ub_mtf_fill(const UbBlock *blk, uint32_t nblk, const uint8_t *rank_all, const uint32_t *pos_all,
+                        const uint32_t *tileperm, uint8_t *bwt_all) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_NTM), tile = (uint32_t)(g % UB_NTM);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t ntok = blk[b].ntok, n = blk[b].block_size;
+  if (tile >= ub_mtf_ntile(ntok)) return;
+  uint32_t lo = tile * UB_TM, hi = lo + UB_TM < ntok ? lo + UB_TM : ntok;
+  const uint8_t *rk = rank_all + (size_t)b * UB_STRIDE;
+  const uint32_t *ps = pos_all + (size_t)b * UB_STRIDE;
+  uint8_t *bwt = bwt_all + (size_t)b * UB_STRIDE;
+  const uint32_t *start = tileperm + ((size_t)b * UB_NTM + tile) * UB_TPW + 64u;
+  uint32_t lw[64];
+  for (uint32_t i = 0; i < 64; i++) lw[i] = start[i];
+  if (tile == 0) {
+    uint8_t c0 = (uint8_t)(lw[0] & 0xFFu);
+    uint32_t e = ntok ? ps[0] : n;
+    for (uint32_t j = 0; j < e; j++) bwt[j] = c0;
+  }
+  for (uint32_t k = lo; k < hi; k++) {
+    uint8_t c = (uint8_t)ub_mtf_front(lw, rk[k]);
+    uint32_t s0 = ps[k], e = (k + 1u < ntok) ? ps[k + 1u] : n;
+    for (uint32_t j = s0; j < e; j++) bwt[j] = c;
   }
 }
 
@@ -392,6 +471,18 @@ UB_KERNEL k_ub_lf_hist(const UbBlock *blk, uint32_t nblk, const uint8_t *bwt_all
   for (uint32_t i = lo; i < hi; i++) h[bwt[i]]++;
   uint32_t *row = tilehist + ((size_t)b * UB_NTL + tile) * 256u;
   for (uint32_t i = 0; i < 256; i++) row[i] = h[i];
+}
+
+// thread per (slot, byte value): occurrences of the value in the block
+UB_KERNEL k_ub_lf_total(const UbBlock *blk, uint32_t nblk, const uint32_t *tilehist, uint32_t *ftab_all) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g >> 8), v = (uint32_t)(g & 255u);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t n = blk[b].block_size, ntile = (n + UB_TL - 1u) / UB_TL;
+  const uint32_t *col = tilehist + (size_t)b * UB_NTL * 256u + v;
+  uint32_t tot = 0;
+  for (uint32_t t = 0; t < ntile; t++) tot += col[(size_t)t * 256u];
+  ftab_all[(size_t)b * 256u + v] = tot;
 }
 
 // thread per (slot, byte value): running start of this value's bucket through the tiles
