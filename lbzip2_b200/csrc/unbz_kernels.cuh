@@ -47,6 +47,7 @@ extern UbEmuIdx ub_emu_idx;
 static inline uint32_t ub_atomic_xor(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o ^ v; return o; }
 static inline uint32_t ub_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline uint32_t ub_bswap32(uint32_t v) { return __builtin_bswap32(v); }
+static inline uint32_t ub_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << (sh & 31u)) >> 32); }
 #else
 #define UB_KERNEL __global__ void
 #define UB_DEVICE __device__ __forceinline__
@@ -57,11 +58,13 @@ static inline uint32_t ub_bswap32(uint32_t v) { return __builtin_bswap32(v); }
 __device__ __forceinline__ uint32_t ub_atomic_xor(uint32_t *p, uint32_t v) { return atomicXor(p, v); }
 __device__ __forceinline__ uint32_t ub_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
 __device__ __forceinline__ uint32_t ub_bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+__device__ __forceinline__ uint32_t ub_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_l(lo, hi, sh); }
 #endif
 
 // ---- geometry ---------------------------------------------------------------------------------
 #define UB_MAXBLK 900000u                 // MAX_BLOCK_SIZE, src/common.h:50
 #define UB_STRIDE 900096u                 // per-slot stride of the byte / node arrays (multiple of 128)
+#define UB_SYMSTRIDE 900096u              // symbols kept per block (18001 groups of 50 at most)
 #define UB_SELCAP 18016u                  // selectors kept per block (18001 used, src/decode.c:631)
 #define UB_TL 2048u                       // counting-sort tile (bytes)
 #define UB_NTL ((UB_MAXBLK + UB_TL - 1) / UB_TL)          // 440
@@ -93,7 +96,9 @@ struct UbBlock {
   uint32_t rl_state;     // run-expansion state after the last byte (4 = missing run length)
   uint32_t crc_acc;      // XOR of the tiles' shifted CRC contributions
   uint32_t crc;          // final block CRC
-  uint32_t ntok;         // list moves recorded by k_ub_retrieve
+  uint32_t ntok;         // list moves (k_ub_tok_scan)
+  uint32_t nsym;         // symbols decoded by k_ub_retrieve (incl. the end-of-block symbol)
+  uint32_t pad;
 };
 
 // ---- bit reader (big-endian 32-bit words, as src/decode.c:372-426) -----------------------------
@@ -185,22 +190,24 @@ UB_DEVICE uint32_t ub_mtf_front(uint32_t *lw, uint32_t r) {
 }
 
 // One CTA of 32 threads per block slot; thread 0 does the work (see the file header).
-// Output per block: the initial list (list0, 64 packed words), and one token per list move:
-// tok_rank[k] = rank moved to the front, tok_pos[k] = position in the last column where the run of
-// the byte that arrives at the front begins.  The byte at the front of list0 fills [0, tok_pos[0]).
+// Output per block: the initial list (list0, 64 packed words) and the decoded symbols sym[0..nsym)
+// (0 = RUNA, 1 = RUNB, 2..alpha-2 = list rank + 1, alpha-1 = end of block).  The status left here is
+// the SERIAL one (what stopped the decoding: end-of-block symbol, end of input, a bad tree, no
+// end-of-block in the last group); k_ub_tok_scan turns it into retrieve()'s status.
 UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint32_t nblk,
-                        uint8_t *rank_all, uint32_t *pos_all, uint32_t *list0_all, uint8_t *sel_all) {
+                        uint16_t *sym_all, uint32_t *list0_all, uint8_t *sel_all) {
   UB_SHARED UbTree tree[6];
   UB_SHARED uint32_t listw[64];
   if (UB_TID != 0) return;
   const uint32_t b = UB_BID;
   if (b >= nblk) return;
   UbBlock &B = blk[b];
-  uint8_t *tok_rank = rank_all + (size_t)b * UB_STRIDE;
-  uint32_t *tok_pos = pos_all + (size_t)b * UB_STRIDE;
+  uint16_t *sym = sym_all + (size_t)b * UB_SYMSTRIDE;
   uint8_t *sel = sel_all + (size_t)b * UB_SELCAP;
   uint32_t status = UB_ERR_UNTERM;
-  uint32_t n = 0, ntok = 0;
+  uint32_t nout = 0;
+  uint64_t pos = 0;
+  bool br_live = true;
   UbBits br;
   br.words = words; br.nwords = nwords;
 
@@ -213,7 +220,6 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
   {
     uint32_t alpha, ntrees, nsel, nsym = 0;
     uint32_t sl[6];
-    uint32_t run = 0, shift = 0;
 
     if (!ub_bits_seek(br, B.pos + 80u)) UB_FAIL(UB_ERR_EOF);
     UB_NEED();
@@ -320,6 +326,12 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
       for (uint32_t i = 0; i < 64; i++) l0[i] = listw[i];
     }
 
+    // Two code paths, as in the reference (src/decode.c:644-661): while a whole group (50 codes
+    // of at most 20 bits = 32 words) is certain to lie inside the input, a lean window reader
+    // without end-of-input tests is used; the last groups go through the exact reader.
+    pos = ub_bits_pos(br);
+    br_live = false;
+    const uint32_t eob = alpha - 1u;
     for (uint32_t g = 0; g < nsel; g++) {
       uint32_t r = sel[g];
       uint32_t t = sl[r];
@@ -328,6 +340,41 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
       sl[0] = t;
       const UbTree &T = tree[t];
 
+      if ((pos >> 5) + 36u <= nwords) {
+        uint64_t wi = pos >> 5;
+        uint32_t bp = (uint32_t)(pos & 31u);
+        uint32_t hi = ub_bswap32(words[wi]), lo = ub_bswap32(words[wi + 1]), ahead = words[wi + 2];
+        bool done = false;
+        for (uint32_t j = 0; j < 50u; j++) {
+          uint32_t win = ub_funnel_l(lo, hi, bp);          // the 32 bits that start at bit bp of hi
+          uint32_t s, k;
+          uint32_t e = T.lut[win >> (32u - UB_LUT_BITS)];
+          if (e != 0) {
+            k = e & 31u; s = e >> 5;
+          } else {
+            uint32_t c20 = win >> 12;
+            k = UB_LUT_BITS + 1u;
+            for (;;) {
+              uint32_t c = c20 >> (20u - k);
+              if (c - T.first[k] < T.count[k]) { s = T.perm[T.offset[k] + c - T.first[k]]; break; }
+              if (++k > 20u) { s = 0; k = 20u; break; }   // unreachable for a complete code
+            }
+          }
+          bp += k;
+          if (bp >= 32u) {
+            bp -= 32u; wi++;
+            hi = lo; lo = ub_bswap32(ahead); ahead = words[wi + 2];
+          }
+          sym[nout++] = (uint16_t)s;
+          if (s == eob) { done = true; break; }
+        }
+        pos = (wi << 5) + bp;
+        if (done) UB_FAIL(UB_OK);
+        continue;
+      }
+
+      br_live = true;
+      if (!ub_bits_seek(br, pos)) UB_FAIL(UB_ERR_EOF);
       for (uint32_t j = 0; j < 50u; j++) {
         UB_NEED();
         uint32_t s, k;
@@ -345,41 +392,159 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
         }
         ub_bits_dump(br, k);
 
-        if (s == alpha - 1u) {                    // end of block (src/decode.c:731-752)
-          if (run > UB_MAXBLK - n) UB_FAIL(UB_ERR_OVERFLOW);
-          n += run;
-          if (n == 0) UB_FAIL(UB_ERR_EMPTY);
-          if (B.bwt_idx >= n) UB_FAIL(UB_ERR_BWTIDX);
-          UB_FAIL(UB_OK);
-        }
-        if (s < 2u && run <= UB_MAXBLK) {         // RUNA / RUNB (src/decode.c:761-764)
-          run += (s + 1u) << shift++;
-          continue;
-        }
-        if (run > UB_MAXBLK - n) UB_FAIL(UB_ERR_OVERFLOW);
-        n += run;
-        tok_rank[ntok] = (uint8_t)(s - 1u);
-        tok_pos[ntok] = n;
-        ntok++;
-        shift = 0;
-        run = 1;
+        sym[nout++] = (uint16_t)s;
+        if (s == eob) UB_FAIL(UB_OK);             // end of block
       }
+      pos = ub_bits_pos(br);
+      br_live = false;
     }
     status = UB_ERR_UNTERM;
   }
 finish:
 #undef UB_FAIL
 #undef UB_NEED
-  B.block_size = n;
-  B.end_bit = ub_bits_pos(br);
+  B.block_size = 0;
+  B.end_bit = br_live ? ub_bits_pos(br) : pos;
   B.status = status;
-  B.period = n;
+  B.period = 0;
   B.rl_state = 0;
   B.crc_acc = 0;
   B.crc = 0;
   B.out_len = 0;
   B.out_off = UB_NOEMIT;
-  B.ntok = ntok;
+  B.ntok = 0;
+  B.nsym = nout;
+}
+
+// ---- zero-run arithmetic (src/decode.c:756-775) as prefix sums over the symbols -----------------
+// Every symbol adds to the length of the last column: a list-move symbol 1 (the first byte of its
+// run), the k-th digit d of a zero run (d+1) << k.  P(i) = sum of what symbols 0..i-1 add.  The
+// reference's overflow tests become: a digit is refused when the run it extends already exceeds
+// 900000; a list-move / end-of-block symbol at index i overflows when P(i) > 900000.  The run a
+// digit extends is found by looking back over at most 21 symbols, so tiles need no carry.
+#define UB_TS 1024u                                        // symbols per tile
+#define UB_NTS ((UB_SYMSTRIDE + UB_TS - 1) / UB_TS)       // 879
+#define UB_RUN_INF 0x7FFFFFFFu
+
+struct UbRunState { uint32_t run, k; };                    // pending run and number of its digits
+
+// State just before symbol i (what the reference's `run` / `shift` hold there).
+UB_DEVICE UbRunState ub_run_state_at(const uint16_t *sym, uint32_t i) {
+  UbRunState st;
+  uint32_t k = 0;
+  while (k < i && k < 22u && sym[i - 1u - k] < 2u) k++;
+  if (k >= 22u) { st.run = UB_RUN_INF; st.k = 22u; return st; }
+  uint32_t run = (i - k) > 0 ? 1u : 0u;               // a list-move symbol precedes the digits, or the block starts
+  for (uint32_t j = 0; j < k; j++) {
+    if (run > UB_MAXBLK) { run = UB_RUN_INF; break; }  // the digit would have been refused
+    run += ((uint32_t)sym[i - k + j] + 1u) << j;
+  }
+  st.run = run; st.k = k;
+  return st;
+}
+// Advance over symbol s; returns what it adds to the column length.
+UB_DEVICE uint32_t ub_run_step(UbRunState &st, uint32_t s) {
+  if (s < 2u) {
+    if (st.run > UB_MAXBLK) { st.run = UB_RUN_INF; return 0; }
+    uint32_t add = (s + 1u) << st.k;
+    st.run += add; st.k++;
+    return add;
+  }
+  st.run = 1u; st.k = 0;
+  return 1u;
+}
+
+struct UbTokTile { uint32_t add, moves; };                 // column bytes added / list moves in the tile
+
+// thread per (slot, tile)
+UB_KERNEL k_ub_tok_sum(const UbBlock *blk, uint32_t nblk, const uint16_t *sym_all, UbTokTile *tt) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_NTS), tile = (uint32_t)(g % UB_NTS);
+  if (b >= nblk) return;
+  uint32_t nsym = blk[b].nsym, alpha = blk[b].alpha_size, lo = tile * UB_TS;
+  if (lo >= nsym) return;
+  uint32_t hi = lo + UB_TS < nsym ? lo + UB_TS : nsym;
+  const uint16_t *sym = sym_all + (size_t)b * UB_SYMSTRIDE;
+  UbRunState st = ub_run_state_at(sym, lo);
+  uint32_t add = 0, moves = 0;
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t s = sym[i];
+    if (s == alpha - 1u) break;                        // end of block: adds nothing
+    uint32_t a = ub_run_step(st, s);
+    add = add + a < add ? 0xFFFFFFFFu : add + a;       // saturate
+    moves += s >= 2u;
+  }
+  tt[(size_t)b * UB_NTS + tile].add = add;
+  tt[(size_t)b * UB_NTS + tile].moves = moves;
+}
+
+// thread per slot: tile offsets, the first overflow (if any), retrieve()'s final status
+UB_KERNEL k_ub_tok_scan(UbBlock *blk, uint32_t nblk, const uint16_t *sym_all, const UbTokTile *tt,
+                        uint32_t *tile_pos, uint32_t *tile_tok) {
+  uint64_t b = UB_GID;
+  if (b >= nblk) return;
+  UbBlock &B = blk[b];
+  uint32_t nsym = B.nsym, alpha = B.alpha_size;
+  uint32_t ntile = (nsym + UB_TS - 1u) / UB_TS;
+  const uint16_t *sym = sym_all + (size_t)b * UB_SYMSTRIDE;
+  uint64_t P = 0;
+  uint32_t M = 0;
+  bool overflow = false;
+  for (uint32_t t = 0; t < ntile && !overflow; t++) {
+    tile_pos[(size_t)b * UB_NTS + t] = (uint32_t)P;
+    tile_tok[(size_t)b * UB_NTS + t] = M;
+    uint64_t after = P + tt[(size_t)b * UB_NTS + t].add;
+    if (after > UB_MAXBLK) {
+      // P(i) passes 900000 inside this tile: replay from the tile start until the reference
+      // would have raised the overflow, or the symbols end
+      UbRunState st = ub_run_state_at(sym, t * UB_TS);
+      uint64_t Pi = P;
+      for (uint32_t i = t * UB_TS; i < nsym; i++) {
+        uint32_t s = sym[i];
+        if (s < 2u) {
+          if (st.run > UB_MAXBLK) { overflow = true; break; }
+        } else if (Pi > UB_MAXBLK) { overflow = true; break; }
+        if (s == alpha - 1u) break;
+        Pi += ub_run_step(st, s);
+      }
+      if (!overflow) { P = UB_MAXBLK + 1u; break; }    // symbols ended first: the serial status stands
+    }
+    P = after;
+    M += tt[(size_t)b * UB_NTS + t].moves;
+  }
+  uint32_t status = B.status;
+  if (overflow) status = UB_ERR_OVERFLOW;
+  else if (status == UB_OK) {
+    if (P == 0) status = UB_ERR_EMPTY;
+    else if (B.bwt_idx >= P) status = UB_ERR_BWTIDX;
+  }
+  uint32_t n = P > UB_MAXBLK ? 0u : (uint32_t)P;
+  B.status = status;
+  B.block_size = n;
+  B.period = n;
+  B.ntok = M;
+}
+
+// thread per (slot, tile): the tile's list moves as tokens (rank, start of the new byte's run)
+UB_KERNEL k_ub_tok_write(const UbBlock *blk, uint32_t nblk, const uint16_t *sym_all, const uint32_t *tile_pos,
+                         const uint32_t *tile_tok, uint8_t *rank_all, uint32_t *pos_all) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / UB_NTS), tile = (uint32_t)(g % UB_NTS);
+  if (b >= nblk || blk[b].status != UB_OK) return;
+  uint32_t nsym = blk[b].nsym, alpha = blk[b].alpha_size, lo = tile * UB_TS;
+  if (lo >= nsym) return;
+  uint32_t hi = lo + UB_TS < nsym ? lo + UB_TS : nsym;
+  const uint16_t *sym = sym_all + (size_t)b * UB_SYMSTRIDE;
+  uint8_t *tok_rank = rank_all + (size_t)b * UB_STRIDE;
+  uint32_t *tok_pos = pos_all + (size_t)b * UB_STRIDE;
+  UbRunState st = ub_run_state_at(sym, lo);
+  uint32_t P = tile_pos[(size_t)b * UB_NTS + tile], m = tile_tok[(size_t)b * UB_NTS + tile];
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t s = sym[i];
+    if (s == alpha - 1u) break;
+    if (s >= 2u) { tok_rank[m] = (uint8_t)(s - 1u); tok_pos[m] = P; m++; }
+    P += ub_run_step(st, s);
+  }
 }
 
 // ---- inverse MTF + run expansion (src/decode.c:428-516 mtf_one, :766-775) -----------------------

@@ -167,3 +167,36 @@ def test_false_candidates_are_rejected():
     assert st == 0 and hashlib.sha256(out).hexdigest() == c["out_sha256"]
     assert info.candidates > info.num_blocks and info.false_candidates >= 1
     d.close()
+
+
+def _mutations(count, seed):
+    rng = np.random.default_rng(seed)
+    small = [load(c) for c in MANIFEST if 8 < os.path.getsize(os.path.join(GOLD, c["file"])) < 6000]
+    for i in range(count):
+        z = bytearray(small[int(rng.integers(len(small)))])
+        kind = i % 4
+        if kind == 0:
+            z = z[: int(rng.integers(4, len(z)))]
+        elif kind == 3:
+            a, b = sorted(int(x) for x in rng.integers(4, len(z), 2))
+            z[a:b] = bytes(rng.integers(0, 256, b - a, dtype=np.uint8))
+        else:
+            for _ in range(1 + kind):
+                bit = int(rng.integers(32, 8 * len(z)))
+                z[bit >> 3] ^= 0x80 >> (bit & 7)
+        yield bytes(z)
+
+
+def test_fuzz_against_oracle():
+    """Damaged inputs: same status, same surviving output and same block count as the oracle
+    (which is pinned on the reference CLI for exactly this kind of input, tools/pin_unoracle.py)."""
+    d = emulib.EmuDecoder(max_blocks=6, in_cap=1 << 16)
+    seen = {}
+    for z in _mutations(int(os.environ.get("LBZ_FUZZ", "700")), 99):
+        ost, oout, osi = orclib.orc_decompress(z, cap=48 << 20)
+        st, out, info = d.decompress(z, cap=48 << 20)
+        assert st == ost, (orclib.ERR_NAMES[st] if st < 20 else st, orclib.ERR_NAMES[ost] if ost < 20 else ost, z.hex()[:80])
+        assert out == oout and info.num_blocks == osi.num_blocks
+        seen[st] = seen.get(st, 0) + 1
+    assert len(seen) >= 10, seen
+    d.close()
