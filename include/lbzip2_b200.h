@@ -247,7 +247,8 @@ enum lbz_darray {
 typedef struct lbz_dblock {
   uint64_t pos, end_bit, out_len, out_off;
   uint32_t status, rand, bwt_idx, block_size, alpha_size, num_trees, num_selectors;
-  uint32_t period, rl_state, crc_acc, crc, ntok, nsym, pad;
+  uint32_t period, rl_state, crc_acc, crc, ntok, nsym, ngrp;
+  uint64_t sym_bit;
 } lbz_dblock;
 int lbz_decoder_read(lbz_decoder *d, int array, uint64_t slot, void *dst, size_t bytes);
 uint32_t lbz_decoder_last_wave_blocks(const lbz_decoder *d);

@@ -2,15 +2,19 @@
 //
 // Replaces, for a whole batch of blocks at once, the reference's
 //   scan()      src/parse.c:281-342   -> k_ub_scan        (48-bit block magic at any bit offset)
-//   retrieve()  src/decode.c:518-791  -> k_ub_retrieve    (header, prefix decoding, zero-run arithmetic)
+//   retrieve()  src/decode.c:518-791  -> k_ub_header, k_ub_tree_*, k_ub_chain, k_ub_symbols (prefix decoding)
+//                                        k_ub_tok_sum/scan/write (zero-run arithmetic, status)
 //                                        k_ub_mtf_tile/scan/fill (inverse MTF, run expansion)
 //   decode()    src/decode.c:840-917  -> k_ub_lf_*, k_ub_walk1/rank/walk2, k_ub_period, k_ub_derand
 //   emit()      src/decode.c:936-1143 -> k_ub_rl_sum/scan/emit, k_ub_crc_fin
 //
-// Shape of the work.  Prefix decoding is serial inside a block (where a code starts depends on every
-// code before it), so k_ub_retrieve runs ONE thread per block, does nothing but decode, and gets its
-// throughput from many blocks in flight: it leaves a token per list move (rank, start of the new
-// byte's run).  Everything after it is re-stated so that a block is worked on by thousands of threads:
+// Shape of the work.  Where a prefix code starts depends on every code before it, so ONE thread per
+// block (k_ub_chain) walks the code lengths -- up to four codes per table look-up -- and does nothing
+// else; throughput comes from many blocks in flight.  Everything else is re-stated so that a block
+// is worked on by thousands of threads:
+//   * symbol values are decoded per 50-code group from the positions the walk left (symbols);
+//   * the zero-run digits become prefix sums over symbol tiles, which also reproduces the
+//     reference's overflow tests and their precedence over later errors (tok_sum/scan/write);
 //   * the inverse MTF is a product of list permutations: tiles of 1024 tokens compute their own
 //     permutation (mtf_tile), one thread per block chains them into the list at every tile start
 //     (mtf_scan), tiles then replay their tokens and fill the runs of the last column (mtf_fill);
@@ -97,8 +101,9 @@ struct UbBlock {
   uint32_t crc_acc;      // XOR of the tiles' shifted CRC contributions
   uint32_t crc;          // final block CRC
   uint32_t ntok;         // list moves (k_ub_tok_scan)
-  uint32_t nsym;         // symbols decoded by k_ub_retrieve (incl. the end-of-block symbol)
-  uint32_t pad;
+  uint32_t nsym;         // symbols walked by k_ub_chain (incl. the end-of-block symbol)
+  uint32_t ngrp;         // 50-symbol groups k_ub_chain started
+  uint64_t sym_bit;      // first bit of the symbol data (k_ub_header)
 };
 
 // ---- bit reader (big-endian 32-bit words, as src/decode.c:372-426) -----------------------------
@@ -160,14 +165,28 @@ UB_KERNEL k_ub_scan(const uint32_t *words, uint64_t nwords, uint64_t *hits, uint
   }
 }
 
-// ---- k_ub_retrieve ------------------------------------------------------------------------------
-#define UB_LUT_BITS 10u
-struct UbTree {
-  uint16_t lut[1u << UB_LUT_BITS];   // (symbol << 5) | length for codes <= 10 bits, 0 otherwise
-  uint32_t first[22];                // first code of each length (right-justified)
+// ---- prefix decoding ----------------------------------------------------------------------------
+// retrieve() (src/decode.c:518-791) is split so that the one thing that is serial inside a block --
+// finding where every code starts -- is all the serial thread does:
+//   k_ub_header      1 thread/block   header fields, byte map, selectors, code lengths
+//   k_ub_tree_canon  thread/tree      Kraft check, canonical code tables (make_tree, decode.c:181-305)
+//   k_ub_tree_l1     thread/symbol    12-bit table: window -> (symbol, length)
+//   k_ub_tree_multi  thread/window    12-bit table: window -> cumulative lengths of up to 4 whole codes
+//   k_ub_chain       1 thread/block   walks the code LENGTHS, up to 4 codes per table step, and leaves
+//                                     the bit position and tree of every 50-code group
+//   k_ub_symbols     thread/group     decodes the group's symbol values
+#define UB_WBITS 12u
+#define UB_WSIZE (1u << UB_WBITS)
+#define UB_PENDING 0xFFFFFFFFu            // header parsed, symbols not walked yet
+#define UB_MAXGRP 18001u                  // src/decode.c:631
+
+struct UbTreeG {                          // one prefix code (global memory)
+  uint32_t first[22];                     // first code of each length (right-justified)
   uint32_t count[22];
-  uint32_t offset[22];               // index into perm of the first symbol of each length
-  uint16_t perm[258];                // symbols in canonical order
+  uint32_t offset[22];                    // index into perm of the first symbol of each length
+  uint16_t perm[258];                     // symbols in canonical order
+  uint16_t status;                        // tree number, or UB_ERR_PREFIX / UB_ERR_INCOMPLT
+  uint8_t len[260];                       // code lengths as transmitted
 };
 
 // Move the byte at position r of a 256-entry list (packed little-endian in 64 words) to the front.
@@ -189,38 +208,28 @@ UB_DEVICE uint32_t ub_mtf_front(uint32_t *lw, uint32_t r) {
   return c;
 }
 
-// One CTA of 32 threads per block slot; thread 0 does the work (see the file header).
-// Output per block: the initial list (list0, 64 packed words) and the decoded symbols sym[0..nsym)
-// (0 = RUNA, 1 = RUNB, 2..alpha-2 = list rank + 1, alpha-1 = end of block).  The status left here is
-// the SERIAL one (what stopped the decoding: end-of-block symbol, end of input, a bad tree, no
-// end-of-block in the last group); k_ub_tok_scan turns it into retrieve()'s status.
-UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint32_t nblk,
-                        uint16_t *sym_all, uint32_t *list0_all, uint8_t *sel_all) {
-  UB_SHARED UbTree tree[6];
-  UB_SHARED uint32_t listw[64];
+// One CTA of 32 threads per block slot; thread 0 does the work.  Leaves status = UB_PENDING and
+// sym_bit = first bit of the symbol data, or the error retrieve() would report.
+UB_KERNEL k_ub_header(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint32_t nblk,
+                      uint32_t *list0_all, uint8_t *sel_all, UbTreeG *tree_all) {
   if (UB_TID != 0) return;
   const uint32_t b = UB_BID;
   if (b >= nblk) return;
   UbBlock &B = blk[b];
-  uint16_t *sym = sym_all + (size_t)b * UB_SYMSTRIDE;
   uint8_t *sel = sel_all + (size_t)b * UB_SELCAP;
-  uint32_t status = UB_ERR_UNTERM;
-  uint32_t nout = 0;
-  uint64_t pos = 0;
-  bool br_live = true;
+  uint32_t *listw = list0_all + (size_t)b * 256u;
+  uint32_t status = UB_PENDING;
   UbBits br;
   br.words = words; br.nwords = nwords;
 
   B.block_size = 0; B.end_bit = 0; B.rand = 0; B.bwt_idx = 0; B.alpha_size = 0;
-  B.num_trees = 0; B.num_selectors = 0;
+  B.num_trees = 0; B.num_selectors = 0; B.period = 0; B.rl_state = 0; B.crc_acc = 0; B.crc = 0;
+  B.out_len = 0; B.out_off = UB_NOEMIT; B.ntok = 0; B.nsym = 0; B.ngrp = 0; B.sym_bit = 0;
 
 #define UB_FAIL(code) do { status = (code); goto finish; } while (0)
 #define UB_NEED() do { if (!ub_bits_need(br)) UB_FAIL(UB_ERR_EOF); } while (0)
-
   {
     uint32_t alpha, ntrees, nsel, nsym = 0;
-    uint32_t sl[6];
-
     if (!ub_bits_seek(br, B.pos + 80u)) UB_FAIL(UB_ERR_EOF);
     UB_NEED();
     B.rand = ub_bits_take(br, 1);
@@ -230,6 +239,7 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
     UB_NEED();
     {
       uint32_t big = ub_bits_take(br, 16);
+      uint32_t acc = 0;
       for (uint32_t i = 0; i < 64; i++) listw[i] = 0;
       for (uint32_t i = 0; i < 16; i++) {
         if (big & (0x8000u >> i)) {
@@ -237,11 +247,13 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
           UB_NEED();
           for (uint32_t j = 0; j < 16; j++)
             if (small & (0x8000u >> j)) {
-              listw[nsym >> 2] |= (16u * i + j) << ((nsym & 3u) * 8u);
+              acc |= (16u * i + j) << ((nsym & 3u) * 8u);
               nsym++;
+              if ((nsym & 3u) == 0) { listw[(nsym >> 2) - 1u] = acc; acc = 0; }
             }
         }
       }
+      if (nsym & 3u) listw[nsym >> 2] = acc;
     }
     if (nsym == 0) UB_FAIL(UB_ERR_BITMAP);
     alpha = nsym + 2u;
@@ -268,8 +280,7 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
     // delta-coded lengths: up to three +-1 steps per 6-bit window, range checked once per
     // window (src/decode.c:577-601 with its L[]/R[] tables)
     for (uint32_t t = 0; t < ntrees; t++) {
-      UbTree &T = tree[t];
-      uint8_t len[258];
+      uint8_t *len = tree_all[(size_t)b * 6u + t].len;
       int cur = (int)ub_bits_take(br, 5);
       uint32_t j = 0;
       while (j < alpha) {
@@ -286,134 +297,225 @@ UB_KERNEL k_ub_retrieve(const uint32_t *words, uint64_t nwords, UbBlock *blk, ui
         ub_bits_dump(br, used);
         UB_NEED();
       }
-      // make_tree(), src/decode.c:181-305: Kraft sum decides whether the tree is usable;
-      // a bad tree only matters if a group selects it
-      for (uint32_t k = 0; k < 22; k++) T.count[k] = 0;
-      for (uint32_t s = 0; s < alpha; s++) T.count[len[s]]++;
-      uint64_t kraft = 0;
-      for (uint32_t k = 1; k <= 20; k++) kraft += (uint64_t)T.count[k] << (20u - k);
-      if (kraft != (1u << 20)) {
-        sl[t] = kraft < (1u << 20) ? UB_ERR_INCOMPLT : UB_ERR_PREFIX;
-        continue;
-      }
-      sl[t] = t;
-      {
-        uint32_t code = 0, off = 0;
-        uint32_t fill[22];
-        for (uint32_t k = 1; k <= 20; k++) {
-          T.first[k] = code; T.offset[k] = off; fill[k] = off;
-          code = (code + T.count[k]) << 1;
-          off += T.count[k];
-        }
-        T.first[21] = 0; T.offset[21] = 0; fill[0] = 0; fill[21] = 0;
-        for (uint32_t s = 0; s < alpha; s++) T.perm[fill[len[s]]++] = (uint16_t)s;
-        for (uint32_t i = 0; i < (1u << UB_LUT_BITS); i++) T.lut[i] = 0;
-        for (uint32_t k = 1; k <= UB_LUT_BITS; k++) {
-          uint32_t span = 1u << (UB_LUT_BITS - k);
-          for (uint32_t q = 0; q < T.count[k]; q++) {
-            uint32_t s = T.perm[T.offset[k] + q];
-            uint32_t base = (T.first[k] + q) << (UB_LUT_BITS - k);
-            uint16_t e = (uint16_t)((s << 5) | k);
-            for (uint32_t z = 0; z < span; z++) T.lut[base + z] = e;
-          }
-        }
-      }
     }
-
-    if (nsel > 18001u) nsel = 18001u;             // src/decode.c:631-632
-    {
-      uint32_t *l0 = list0_all + (size_t)b * 256u;
-      for (uint32_t i = 0; i < 64; i++) l0[i] = listw[i];
-    }
-
-    // Two code paths, as in the reference (src/decode.c:644-661): while a whole group (50 codes
-    // of at most 20 bits = 32 words) is certain to lie inside the input, a lean window reader
-    // without end-of-input tests is used; the last groups go through the exact reader.
-    pos = ub_bits_pos(br);
-    br_live = false;
-    const uint32_t eob = alpha - 1u;
-    for (uint32_t g = 0; g < nsel; g++) {
-      uint32_t r = sel[g];
-      uint32_t t = sl[r];
-      if (t >= 6u) UB_FAIL(t);                    // a bad tree is selected (src/decode.c:640-642)
-      for (; r > 0; r--) sl[r] = sl[r - 1];
-      sl[0] = t;
-      const UbTree &T = tree[t];
-
-      if ((pos >> 5) + 36u <= nwords) {
-        uint64_t wi = pos >> 5;
-        uint32_t bp = (uint32_t)(pos & 31u);
-        uint32_t hi = ub_bswap32(words[wi]), lo = ub_bswap32(words[wi + 1]), ahead = words[wi + 2];
-        bool done = false;
-        for (uint32_t j = 0; j < 50u; j++) {
-          uint32_t win = ub_funnel_l(lo, hi, bp);          // the 32 bits that start at bit bp of hi
-          uint32_t s, k;
-          uint32_t e = T.lut[win >> (32u - UB_LUT_BITS)];
-          if (e != 0) {
-            k = e & 31u; s = e >> 5;
-          } else {
-            uint32_t c20 = win >> 12;
-            k = UB_LUT_BITS + 1u;
-            for (;;) {
-              uint32_t c = c20 >> (20u - k);
-              if (c - T.first[k] < T.count[k]) { s = T.perm[T.offset[k] + c - T.first[k]]; break; }
-              if (++k > 20u) { s = 0; k = 20u; break; }   // unreachable for a complete code
-            }
-          }
-          bp += k;
-          if (bp >= 32u) {
-            bp -= 32u; wi++;
-            hi = lo; lo = ub_bswap32(ahead); ahead = words[wi + 2];
-          }
-          sym[nout++] = (uint16_t)s;
-          if (s == eob) { done = true; break; }
-        }
-        pos = (wi << 5) + bp;
-        if (done) UB_FAIL(UB_OK);
-        continue;
-      }
-
-      br_live = true;
-      if (!ub_bits_seek(br, pos)) UB_FAIL(UB_ERR_EOF);
-      for (uint32_t j = 0; j < 50u; j++) {
-        UB_NEED();
-        uint32_t s, k;
-        uint32_t e = T.lut[ub_bits_peek(br, UB_LUT_BITS)];
-        if (e != 0) {
-          k = e & 31u; s = e >> 5;
-        } else {
-          uint32_t c20 = ub_bits_peek(br, 20);
-          k = UB_LUT_BITS + 1u;
-          for (;;) {
-            uint32_t c = c20 >> (20u - k);
-            if (c - T.first[k] < T.count[k]) { s = T.perm[T.offset[k] + c - T.first[k]]; break; }
-            if (++k > 20u) { s = 0; k = 20u; break; }   // unreachable for a complete code
-          }
-        }
-        ub_bits_dump(br, k);
-
-        sym[nout++] = (uint16_t)s;
-        if (s == eob) UB_FAIL(UB_OK);             // end of block
-      }
-      pos = ub_bits_pos(br);
-      br_live = false;
-    }
-    status = UB_ERR_UNTERM;
   }
 finish:
 #undef UB_FAIL
 #undef UB_NEED
-  B.block_size = 0;
-  B.end_bit = br_live ? ub_bits_pos(br) : pos;
+  B.end_bit = ub_bits_pos(br);
+  B.sym_bit = B.end_bit;
   B.status = status;
-  B.period = 0;
-  B.rl_state = 0;
-  B.crc_acc = 0;
-  B.crc = 0;
-  B.out_len = 0;
-  B.out_off = UB_NOEMIT;
-  B.ntok = 0;
-  B.nsym = nout;
+}
+
+// thread per (slot, tree): make_tree(), src/decode.c:181-305.  A bad tree only matters if a group
+// selects it, so its kind is kept as the tree's status.
+UB_KERNEL k_ub_tree_canon(const UbBlock *blk, uint32_t nblk, UbTreeG *tree_all) {
+  uint64_t g = UB_GID;
+  uint32_t b = (uint32_t)(g / 6u), t = (uint32_t)(g % 6u);
+  if (b >= nblk || blk[b].status != UB_PENDING || t >= blk[b].num_trees) return;
+  UbTreeG &T = tree_all[(size_t)b * 6u + t];
+  const uint32_t alpha = blk[b].alpha_size;
+  uint32_t count[22];
+  for (uint32_t k = 0; k < 22; k++) count[k] = 0;
+  for (uint32_t s = 0; s < alpha; s++) count[T.len[s]]++;
+  uint64_t kraft = 0;
+  for (uint32_t k = 1; k <= 20; k++) kraft += (uint64_t)count[k] << (20u - k);
+  if (kraft != (1u << 20)) {
+    T.status = (uint16_t)(kraft < (1u << 20) ? UB_ERR_INCOMPLT : UB_ERR_PREFIX);
+    return;
+  }
+  T.status = (uint16_t)t;
+  uint32_t code = 0, off = 0;
+  uint32_t fill[22];
+  for (uint32_t k = 1; k <= 20; k++) {
+    T.first[k] = code; T.offset[k] = off; T.count[k] = count[k]; fill[k] = off;
+    code = (code + count[k]) << 1;
+    off += count[k];
+  }
+  T.first[0] = 0; T.count[0] = 0; T.offset[0] = 0; T.first[21] = 0; T.count[21] = 0; T.offset[21] = 0;
+  for (uint32_t s = 0; s < alpha; s++) T.perm[fill[T.len[s]]++] = (uint16_t)s;
+}
+
+// thread per (slot, tree, symbol): the symbol's code, left-justified in 12 bits, owns a span of the
+// window table.  Entries no short code reaches stay 0 (the table is cleared before every wave).
+UB_KERNEL k_ub_tree_l1(const UbBlock *blk, uint32_t nblk, const UbTreeG *tree_all, uint16_t *l1_all) {
+  uint64_t g = UB_GID;
+  uint32_t s = (uint32_t)(g % 258u), t = (uint32_t)((g / 258u) % 6u), b = (uint32_t)(g / (258u * 6u));
+  if (b >= nblk || blk[b].status != UB_PENDING || t >= blk[b].num_trees || s >= blk[b].alpha_size) return;
+  const UbTreeG &T = tree_all[(size_t)b * 6u + t];
+  if (T.status >= 6u) return;
+  uint32_t len = T.len[s];
+  if (len > UB_WBITS) return;
+  uint32_t q = 0;                                   // rank of s among the symbols of its length
+  for (uint32_t x = 0; x < s; x++) q += (T.len[x] == len);
+  uint32_t base = (T.first[len] + q) << (UB_WBITS - len), span = 1u << (UB_WBITS - len);
+  uint16_t e = (uint16_t)((s << 5) | len);
+  uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
+  for (uint32_t z = 0; z < span; z++) l1[base + z] = e;
+}
+
+// thread per (slot, tree, window): how far up to four whole codes reach into the window.
+//   bits  0..15  cumulative length after the 1st..4th code (4 bits each)
+//   bits 16..18  number of codes (0: the first code is longer than the window)
+//   bits 19..21  1-based index of the end-of-block symbol among them, 0 if absent
+UB_KERNEL k_ub_tree_multi(const UbBlock *blk, uint32_t nblk, const UbTreeG *tree_all, const uint16_t *l1_all,
+                          uint32_t *ml_all) {
+  uint64_t g = UB_GID;
+  uint32_t idx = (uint32_t)(g % UB_WSIZE), t = (uint32_t)((g / UB_WSIZE) % 6u), b = (uint32_t)(g / (UB_WSIZE * 6u));
+  if (b >= nblk || blk[b].status != UB_PENDING || t >= blk[b].num_trees) return;
+  if (tree_all[(size_t)b * 6u + t].status >= 6u) return;
+  const uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
+  const uint32_t eob = blk[b].alpha_size - 1u;
+  uint32_t cum = 0, cnt = 0, lens = 0, eobk = 0, cur = idx;
+  for (uint32_t c = 0; c < 4u; c++) {
+    uint32_t x = l1[cur];
+    uint32_t len = x & 31u;
+    if (x == 0 || cum + len > UB_WBITS) break;   // the next code is not wholly inside the known bits
+    cum += len;
+    lens |= cum << (4u * c);
+    cnt++;
+    if ((x >> 5) == eob) { eobk = cnt; break; }
+    cur = (idx << cum) & (UB_WSIZE - 1u);
+  }
+  ml_all[((size_t)b * 6u + t) * UB_WSIZE + idx] = lens | (cnt << 16) | (eobk << 19);
+}
+
+// One code by its canonical tables, for windows the 12-bit tables do not resolve.  c20 = the next
+// 20 bits.  Returns the symbol, *k = its length.
+UB_DEVICE uint32_t ub_canon_decode(const UbTreeG &T, uint32_t c20, uint32_t *k) {
+  for (uint32_t len = 1; len <= 20u; len++) {
+    uint32_t c = c20 >> (20u - len);
+    if (c - T.first[len] < T.count[len]) { *k = len; return T.perm[T.offset[len] + c - T.first[len]]; }
+  }
+  *k = 20u;                                          // unreachable for a complete code
+  return 0;
+}
+
+// One CTA of 32 threads per block slot; thread 0 walks the code lengths.  Leaves the SERIAL status
+// (what stopped the walk: the end-of-block symbol, the end of the input, a bad tree, no end-of-block
+// in the last group); k_ub_tok_scan turns it into retrieve()'s status.
+UB_KERNEL k_ub_chain(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint32_t nblk, const uint8_t *sel_all,
+                     const UbTreeG *tree_all, const uint16_t *l1_all, const uint32_t *ml_all, uint64_t *gpos_all,
+                     uint8_t *gtree_all) {
+  if (UB_TID != 0) return;
+  const uint32_t b = UB_BID;
+  if (b >= nblk) return;
+  UbBlock &B = blk[b];
+  if (B.status != UB_PENDING) return;
+  const uint8_t *sel = sel_all + (size_t)b * UB_SELCAP;
+  uint64_t *gpos = gpos_all + (size_t)b * (UB_MAXGRP + 1u);
+  uint8_t *gtree = gtree_all + (size_t)b * (UB_MAXGRP + 1u);
+  const uint32_t eob = B.alpha_size - 1u;
+  uint32_t nsel = B.num_selectors > UB_MAXGRP ? UB_MAXGRP : B.num_selectors;   // src/decode.c:631-632
+  uint32_t sl[6];
+  for (uint32_t t = 0; t < 6u; t++) sl[t] = t < B.num_trees ? tree_all[(size_t)b * 6u + t].status : 0u;
+  uint64_t pos = B.sym_bit;
+  uint32_t status = UB_ERR_UNTERM, nsym = 0, g = 0;
+  UbBits br;
+  br.words = words; br.nwords = nwords;
+
+  for (; g < nsel; g++) {
+    uint32_t r = sel[g];
+    uint32_t t = sl[r];
+    if (t >= 6u) { status = t; break; }              // a bad tree is selected (src/decode.c:640-642)
+    for (; r > 0; r--) sl[r] = sl[r - 1];
+    sl[0] = t;
+    gpos[g] = pos;
+    gtree[g] = (uint8_t)t;
+    const UbTreeG &T = tree_all[(size_t)b * 6u + t];
+    const uint32_t *ml = ml_all + ((size_t)b * 6u + t) * UB_WSIZE;
+    bool done = false;
+
+    // Two code paths, as in the reference (src/decode.c:644-661): while a whole group (50 codes of
+    // at most 20 bits = 32 words) is certain to lie inside the input, a lean window reader without
+    // end-of-input tests is used; the last groups go through the exact reader.
+    if ((pos >> 5) + 36u <= nwords) {
+      uint64_t wi = pos >> 5;
+      uint32_t bp = (uint32_t)(pos & 31u);
+      uint32_t hi = ub_bswap32(words[wi]), lo = ub_bswap32(words[wi + 1]), ahead = words[wi + 2];
+      uint32_t rem = 50u;
+      while (rem) {
+        uint32_t win = ub_funnel_l(lo, hi, bp);        // the 32 bits that start at bit bp of hi
+        uint32_t e = ml[win >> (32u - UB_WBITS)];
+        uint32_t len;
+        uint32_t cnt = (e >> 16) & 7u;
+        if (cnt) {
+          uint32_t take = cnt < rem ? cnt : rem;
+          uint32_t eobk = e >> 19;
+          if (eobk && eobk <= take) { take = eobk; done = true; }
+          len = (e >> (4u * (take - 1u))) & 15u;
+          rem -= take;
+        } else {
+          uint32_t s = ub_canon_decode(T, win >> 12, &len);
+          rem -= 1u;
+          if (s == eob) done = true;
+        }
+        bp += len;
+        if (bp >= 32u) {
+          bp -= 32u; wi++;
+          hi = lo; lo = ub_bswap32(ahead); ahead = words[wi + 2];
+        }
+        if (done) break;
+      }
+      nsym += 50u - rem;
+      pos = (wi << 5) + bp;
+    } else {
+      const uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
+      bool eof = !ub_bits_seek(br, pos);
+      for (uint32_t j = 0; j < 50u && !eof && !done; j++) {
+        if (!ub_bits_need(br)) { eof = true; break; }  // NEED(), src/decode.c:387-407
+        uint32_t c20 = ub_bits_peek(br, 20);
+        uint32_t x = l1[c20 >> (20u - UB_WBITS)];
+        uint32_t s, k;
+        if (x) { s = x >> 5; k = x & 31u; } else s = ub_canon_decode(T, c20, &k);
+        ub_bits_dump(br, k);
+        nsym++;
+        if (s == eob) done = true;
+      }
+      if (!eof || done) pos = ub_bits_pos(br);
+      if (eof && !done) { pos = ub_bits_pos(br); status = UB_ERR_EOF; g++; break; }
+    }
+    if (done) { status = UB_OK; g++; break; }
+  }
+  B.nsym = nsym;
+  B.ngrp = g;
+  B.end_bit = pos;
+  B.status = status;
+}
+
+// thread per (slot, group): the group's symbol values (0 = RUNA, 1 = RUNB, 2..alpha-2 = list rank
+// + 1, alpha-1 = end of block), decoded from the position k_ub_chain left
+UB_KERNEL k_ub_symbols(const uint32_t *words, uint64_t nwords, const UbBlock *blk, uint32_t nblk,
+                       const UbTreeG *tree_all, const uint16_t *l1_all, const uint64_t *gpos_all,
+                       const uint8_t *gtree_all, uint16_t *sym_all) {
+  uint64_t gid = UB_GID;
+  uint32_t b = (uint32_t)(gid / (UB_MAXGRP + 1u)), g = (uint32_t)(gid % (UB_MAXGRP + 1u));
+  if (b >= nblk || g >= blk[b].ngrp) return;
+  uint32_t nsym = blk[b].nsym, lo_s = g * 50u;
+  if (lo_s >= nsym) return;
+  uint32_t cnt = nsym - lo_s < 50u ? nsym - lo_s : 50u;
+  uint32_t t = gtree_all[(size_t)b * (UB_MAXGRP + 1u) + g];
+  const UbTreeG &T = tree_all[(size_t)b * 6u + t];
+  const uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
+  uint16_t *sym = sym_all + (size_t)b * UB_SYMSTRIDE + lo_s;
+  uint64_t pos = gpos_all[(size_t)b * (UB_MAXGRP + 1u) + g];
+  uint64_t wi = pos >> 5;
+  uint32_t bp = (uint32_t)(pos & 31u);
+  uint32_t hi = wi < nwords ? ub_bswap32(words[wi]) : 0u;
+  uint32_t lo = wi + 1 < nwords ? ub_bswap32(words[wi + 1]) : 0u;
+  for (uint32_t j = 0; j < cnt; j++) {
+    uint32_t win = ub_funnel_l(lo, hi, bp);
+    uint32_t x = l1[win >> (32u - UB_WBITS)];
+    uint32_t s, k;
+    if (x) { s = x >> 5; k = x & 31u; } else s = ub_canon_decode(T, win >> 12, &k);
+    sym[j] = (uint16_t)s;
+    bp += k;
+    if (bp >= 32u) {
+      bp -= 32u; wi++;
+      hi = lo;
+      lo = wi + 1 < nwords ? ub_bswap32(words[wi + 1]) : 0u;
+    }
+  }
 }
 
 // ---- zero-run arithmetic (src/decode.c:756-775) as prefix sums over the symbols -----------------

@@ -25,7 +25,8 @@ class DStreamInfo(C.Structure):
 class DBlock(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("pos", "end_bit", "out_len", "out_off")] + [
         (n, C.c_uint32) for n in ("status", "rand", "bwt_idx", "block_size", "alpha_size", "num_trees",
-                                  "num_selectors", "period", "rl_state", "crc_acc", "crc", "ntok", "nsym", "pad")]
+                                  "num_selectors", "period", "rl_state", "crc_acc", "crc", "ntok", "nsym", "ngrp")] + [
+        ("sym_bit", C.c_uint64)]
 
 
 _lib = None
