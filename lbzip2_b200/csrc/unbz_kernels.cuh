@@ -50,6 +50,7 @@ extern UbEmuIdx ub_emu_idx;
 #define UB_TID (ub_emu_idx.tid)
 static inline uint32_t ub_atomic_xor(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o ^ v; return o; }
 static inline uint32_t ub_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+struct uint2 { uint32_t x, y; };
 static inline uint32_t ub_bswap32(uint32_t v) { return __builtin_bswap32(v); }
 static inline uint32_t ub_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << (sh & 31u)) >> 32); }
 #else
@@ -355,9 +356,11 @@ UB_KERNEL k_ub_tree_l1(const UbBlock *blk, uint32_t nblk, const UbTreeG *tree_al
 }
 
 // thread per (slot, tree, window): how far up to four whole codes reach into the window.
-//   bits  0..15  cumulative length after the 1st..4th code (4 bits each)
-//   bits 16..18  number of codes (0: the first code is longer than the window)
-//   bits 19..21  1-based index of the end-of-block symbol among them, 0 if absent
+//   bits  0..3   length of all of them together      } all the walk needs in the common case
+//   bits  4..6   number of codes (0: the first code is longer than the window)
+//   bit   7      set if the entry needs care: no code, or the end-of-block symbol is among them
+//   bits  8..23  cumulative length after the 1st..4th code (4 bits each)
+//   bits 24..26  1-based index of the end-of-block symbol among them, 0 if absent
 UB_KERNEL k_ub_tree_multi(const UbBlock *blk, uint32_t nblk, const UbTreeG *tree_all, const uint16_t *l1_all,
                           uint32_t *ml_all) {
   uint64_t g = UB_GID;
@@ -377,7 +380,8 @@ UB_KERNEL k_ub_tree_multi(const UbBlock *blk, uint32_t nblk, const UbTreeG *tree
     if ((x >> 5) == eob) { eobk = cnt; break; }
     cur = (idx << cum) & (UB_WSIZE - 1u);
   }
-  ml_all[((size_t)b * 6u + t) * UB_WSIZE + idx] = lens | (cnt << 16) | (eobk << 19);
+  uint32_t care = (cnt == 0 || eobk != 0) ? 0x80u : 0u;
+  ml_all[((size_t)b * 6u + t) * UB_WSIZE + idx] = cum | (cnt << 4) | care | (lens << 8) | (eobk << 24);
 }
 
 // One code by its canonical tables, for windows the 12-bit tables do not resolve.  c20 = the next
@@ -430,35 +434,40 @@ UB_KERNEL k_ub_chain(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint3
     // at most 20 bits = 32 words) is certain to lie inside the input, a lean window reader without
     // end-of-input tests is used; the last groups go through the exact reader.
     if ((pos >> 5) + 36u <= nwords) {
-      uint64_t wi = pos >> 5;
+      const uint32_t *wp = words + (pos >> 5);         // hi = wp[0], lo = wp[1], ahead = wp[2]
       uint32_t bp = (uint32_t)(pos & 31u);
-      uint32_t hi = ub_bswap32(words[wi]), lo = ub_bswap32(words[wi + 1]), ahead = words[wi + 2];
+      uint32_t hi = ub_bswap32(wp[0]), lo = ub_bswap32(wp[1]), ahead = wp[2];
       uint32_t rem = 50u;
       while (rem) {
         uint32_t win = ub_funnel_l(lo, hi, bp);        // the 32 bits that start at bit bp of hi
         uint32_t e = ml[win >> (32u - UB_WBITS)];
         uint32_t len;
-        uint32_t cnt = (e >> 16) & 7u;
-        if (cnt) {
-          uint32_t take = cnt < rem ? cnt : rem;
-          uint32_t eobk = e >> 19;
-          if (eobk && eobk <= take) { take = eobk; done = true; }
-          len = (e >> (4u * (take - 1u))) & 15u;
-          rem -= take;
+        if (rem >= 4u && !(e & 0x80u)) {               // common case: all codes of the entry, no end of block
+          len = e & 15u;
+          rem -= (e >> 4) & 7u;
         } else {
-          uint32_t s = ub_canon_decode(T, win >> 12, &len);
-          rem -= 1u;
-          if (s == eob) done = true;
+          uint32_t cnt = (e >> 4) & 7u;
+          if (cnt) {
+            uint32_t take = cnt < rem ? cnt : rem;
+            uint32_t eobk = e >> 24;
+            if (eobk && eobk <= take) { take = eobk; done = true; }
+            len = (e >> (4u + 4u * take)) & 15u;
+            rem -= take;
+          } else {
+            uint32_t s = ub_canon_decode(T, win >> 12, &len);
+            rem -= 1u;
+            if (s == eob) done = true;
+          }
         }
         bp += len;
         if (bp >= 32u) {
-          bp -= 32u; wi++;
-          hi = lo; lo = ub_bswap32(ahead); ahead = words[wi + 2];
+          bp -= 32u; wp++;
+          hi = lo; lo = ub_bswap32(ahead); ahead = wp[2];
         }
         if (done) break;
       }
       nsym += 50u - rem;
-      pos = (wi << 5) + bp;
+      pos = ((uint64_t)(wp - words) << 5) + bp;
     } else {
       const uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
       bool eof = !ub_bits_seek(br, pos);
@@ -810,8 +819,7 @@ UB_DEVICE bool ub_slot_node(uint32_t k, uint32_t n, uint32_t idx, uint32_t *x) {
 }
 
 // thread per (slot, splitter): length of the piece that starts here and the splitter that ends it
-UB_KERNEL k_ub_walk1(const UbBlock *blk, uint32_t nblk, const uint32_t *node_all, uint32_t *segnext,
-                     uint32_t *seglen) {
+UB_KERNEL k_ub_walk1(const UbBlock *blk, uint32_t nblk, const uint32_t *node_all, uint2 *seg) {
   uint64_t g = UB_GID;
   uint32_t b = (uint32_t)(g / UB_KS), k = (uint32_t)(g % UB_KS);
   if (b >= nblk || blk[b].status != UB_OK) return;
@@ -823,31 +831,33 @@ UB_KERNEL k_ub_walk1(const UbBlock *blk, uint32_t nblk, const uint32_t *node_all
     x = node[x] >> 8;
     len++;
   } while (!ub_is_split(x, idx));
-  segnext[(size_t)b * UB_KS + k] = ub_split_slot(x, idx);
-  seglen[(size_t)b * UB_KS + k] = len;
+  uint2 v;
+  v.x = ub_split_slot(x, idx);                         // the splitter that ends the piece
+  v.y = len;
+  seg[(size_t)b * UB_KS + k] = v;
 }
 
-// thread per slot: text position of every splitter on the cycle through the primary index.
-// If the cycle closes before block_size steps the text is periodic (src/decode.c:866-868) and
-// `period` says how much of it the second walk produces.
-UB_KERNEL k_ub_rank(UbBlock *blk, uint32_t nblk, const uint32_t *segnext, const uint32_t *seglen,
-                    uint32_t *segpos) {
+// thread per slot: text position of every splitter on the cycle through the primary index (one
+// 8-byte load per step).  If the cycle closes before block_size steps the text is periodic
+// (src/decode.c:866-868) and `period` says how much of it the second walk produces.
+UB_KERNEL k_ub_rank(UbBlock *blk, uint32_t nblk, const uint2 *seg, uint32_t *segpos) {
   uint64_t b = UB_GID;
   if (b >= nblk || blk[b].status != UB_OK) return;
   uint32_t n = blk[b].block_size, idx = blk[b].bwt_idx;
-  uint32_t s = ub_split_slot(idx, idx);
-  uint32_t pos = 0;
+  const uint32_t s0 = ub_split_slot(idx, idx);
+  uint32_t s = s0, pos = 0;
   const size_t base = (size_t)b * UB_KS;
-  while (pos < n && segpos[base + s] == UB_UNSET) {
+  do {
+    uint2 v = seg[base + s];
     segpos[base + s] = pos;
-    pos += seglen[base + s];
-    s = segnext[base + s];
-  }
+    pos += v.y;
+    s = v.x;
+  } while (pos < n && s != s0);
   blk[b].period = pos < n ? pos : n;
 }
 
 // thread per (slot, splitter): write the piece
-UB_KERNEL k_ub_walk2(const UbBlock *blk, uint32_t nblk, const uint32_t *node_all, const uint32_t *seglen,
+UB_KERNEL k_ub_walk2(const UbBlock *blk, uint32_t nblk, const uint32_t *node_all, const uint2 *seg,
                      const uint32_t *segpos, uint8_t *txt_all) {
   uint64_t g = UB_GID;
   uint32_t b = (uint32_t)(g / UB_KS), k = (uint32_t)(g % UB_KS);
@@ -858,7 +868,7 @@ UB_KERNEL k_ub_walk2(const UbBlock *blk, uint32_t nblk, const uint32_t *node_all
   if (!ub_slot_node(k, n, idx, &x)) return;
   const uint32_t *node = node_all + (size_t)b * UB_STRIDE;
   uint8_t *txt = txt_all + (size_t)b * UB_STRIDE;
-  uint32_t len = seglen[(size_t)b * UB_KS + k];
+  uint32_t len = seg[(size_t)b * UB_KS + k].y;
   for (uint32_t t = 0; t < len && p + t < n; t++) {
     uint32_t v = node[x];
     txt[p + t] = (uint8_t)v;
