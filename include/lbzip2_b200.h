@@ -232,6 +232,17 @@ int lbz_decoder_load(lbz_decoder *d, const uint8_t *in, size_t n);
 int lbz_decompress_ex(lbz_decoder *d, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
                       size_t *out_len, lbz_dstream_info *info, unsigned flags);
 
+/* The same work one wave at a time, for callers that stream the output (the
+   expansion task graph, lbzip2_b200/host/expand_b200.c): open = upload, scan,
+   first framing; every next call decodes one wave of up to max_blocks
+   candidates into `out` and returns LBZ_MORE while blocks remain, LBZ_OK at
+   the clean end of the file, or the error kind -- in every case *out_len bytes
+   of `out` are valid.  LBZ_ERR_OUTCAP: not even the next block fits out_cap
+   (a single block can expand to 46.6 MB).  `in` must stay valid until the
+   last call. */
+int lbz_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags);
+int lbz_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info);
+
 /* Block-boundary scanner alone (row f3): bit positions of every 48-bit block
    magic 0x314159265359 in the input, ascending.  Returns the number found
    (written up to cap), negative on failure. */

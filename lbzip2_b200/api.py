@@ -79,7 +79,7 @@ EXPORTS = [
     "lbz_decoder_create", "lbz_decoder_destroy", "lbz_decompress_stream", "lbz_decompress_ex",
     "lbz_decoder_load", "lbz_scan_blocks", "lbz_decoder_read", "lbz_decoder_last_wave_blocks",
     "lbz_decoder_launches", "lbz_decoder_device_bytes", "lbz_decoder_last_ms", "lbz_decoder_stage_ms",
-    "lbz_strerror",
+    "lbz_strerror", "lbz_decoder_open", "lbz_decoder_next",
 ]
 
 
@@ -173,6 +173,10 @@ def load_library():
     L.lbz_decoder_last_ms.argtypes = [vp]
     L.lbz_decoder_stage_ms.restype = None
     L.lbz_decoder_stage_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    L.lbz_decoder_open.restype = C.c_int
+    L.lbz_decoder_open.argtypes = [vp, vp, C.c_size_t, C.c_uint]
+    L.lbz_decoder_next.restype = C.c_int
+    L.lbz_decoder_next.argtypes = [vp, vp, C.c_size_t, szp, C.POINTER(DStreamInfo)]
     L.lbz_strerror.restype = C.c_char_p
     L.lbz_strerror.argtypes = [C.c_int]
     _LIB = L
@@ -345,6 +349,27 @@ class Decoder:
         if st < 0:
             raise LbzError("lbz_decompress_stream failed (%d)" % st)
         return st, out[: n.value].tobytes(), info
+
+    def decompress_waves(self, z, wave_cap):
+        """Generator over (status, bytes) of lbz_decoder_open / lbz_decoder_next."""
+        a = _as_u8(z)
+        src = a if a.size else np.zeros(1, np.uint8)
+        st = self.L.lbz_decoder_open(self.h, src.ctypes.data, a.size, 0)
+        if st < 0:
+            raise LbzError("lbz_decoder_open failed")
+        if st != 0:
+            yield st, b""
+            return
+        buf = np.empty(max(wave_cap, 1), dtype=np.uint8)
+        while True:
+            n = C.c_size_t(0)
+            info = DStreamInfo()
+            st = self.L.lbz_decoder_next(self.h, buf.ctypes.data, wave_cap, C.byref(n), C.byref(info))
+            if st < 0:
+                raise LbzError("lbz_decoder_next failed")
+            yield st, buf[: n.value].tobytes()
+            if st != 1:
+                return
 
     def decompress_ptr(self, in_ptr, n, out_ptr, out_cap, flags=0):
         """Raw-pointer form; returns (status, out_len, info)."""

@@ -144,6 +144,17 @@ extern "C" int lbz_decompress_stream(lbz_decoder *d, const uint8_t *in, size_t n
   return lbz_decompress_ex(d, in, n, out, out_cap, out_len, info, 0);
 }
 
+extern "C" int lbz_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags) {
+  if (cudaSetDevice(d->be.device) != cudaSuccess) return -1;
+  return ub_open(d, in, n, flags);
+}
+
+extern "C" int lbz_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info) {
+  if (cudaSetDevice(d->be.device) != cudaSuccess) return -1;
+  size_t dummy = 0;
+  return ub_next(d, out, out_cap, out_len ? out_len : &dummy, info);
+}
+
 extern "C" long lbz_scan_blocks(lbz_decoder *d, const uint8_t *in, size_t n, uint64_t *bit_positions, size_t cap) {
   if (cudaSetDevice(d->be.device) != cudaSuccess) return -1;
   if (ub_upload(d, in, n) != 0) return -1;

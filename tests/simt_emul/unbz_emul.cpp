@@ -72,6 +72,10 @@ int emu_decompress(lbz_decoder *d, const uint8_t *in, size_t n, uint8_t *out, si
                    lbz_dstream_info *info, unsigned flags) {
   return ub_decompress(d, in, n, out, out_cap, out_len, info, flags);
 }
+int emu_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags) { return ub_open(d, in, n, flags); }
+int emu_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info) {
+  return ub_next(d, out, out_cap, out_len, info);
+}
 long emu_scan_blocks(lbz_decoder *d, const uint8_t *in, size_t n, uint64_t *pos, size_t cap) {
   if (ub_upload(d, in, n) != 0 || ub_scan(d, (n + 3) / 4) != 0) return -1;
   for (size_t i = 0; i < d->hits.size() && i < cap; i++) pos[i] = d->hits[i];
@@ -94,3 +98,27 @@ uint64_t emu_launches(const lbz_decoder *d) { return d->launches; }
 uint32_t emu_mtf_front(uint32_t *lw, uint32_t r) { return ub_mtf_front(lw, r); }
 uint32_t emu_gf_shift(uint32_t a, uint64_t nbytes, const uint32_t *pw) { return ub_gf_shift(a, nbytes, pw); }
 }
+
+#ifdef UB_EMUL_ABI
+// The product's decoder entry points over the emulation, for the CPU-only check of the expansion
+// task graph (oracle/Makefile target _ref/lbzip2_b200_hosttest).  Never part of libbz2b200.so.
+extern "C" {
+lbz_decoder *lbz_decoder_create(int, int max_blocks, size_t in_cap, size_t out_cap) { return emu_decoder_create(max_blocks, in_cap, out_cap); }
+void lbz_decoder_destroy(lbz_decoder *d) { emu_decoder_destroy(d); }
+int lbz_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags) { return ub_open(d, in, n, flags); }
+int lbz_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info) {
+  return ub_next(d, out, out_cap, out_len, info);
+}
+const char *lbz_strerror(int status) {
+  static const char *const text[] = {
+    "not a valid bzip2 file", "bad block header magic", "empty source alphabet", "bad number of trees",
+    "no coding groups", "invalid selector", "invalid delta code", "invalid prefix code",
+    "incomplete prefix code", "empty block", "unterminated block", "missing run length",
+    "block CRC mismatch", "stream CRC mismatch", "block overflow", "primary index too large",
+    "unexpected end of file"};
+  if (status == LBZ_OK) return "ok";
+  if (status >= LBZ_ERR_MAGIC && status <= LBZ_ERR_EOF) return text[status - LBZ_ERR_MAGIC];
+  return "internal error";
+}
+}
+#endif

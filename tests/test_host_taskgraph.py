@@ -75,3 +75,65 @@ def test_batch_cli_on_the_gpu_matches_reference_cli(batch, engines, nthreads, gp
     for name, data in ins.items():
         level = 9 if name == "text_9" else (1 if len(data) < 1_000_000 else 3)
         assert _run(GPU_CLI, level, nthreads, data, env) == _reference(level, data), name
+
+
+# ---- expansion task graph (lbzip2_b200/host/expand_b200.c) ---------------------
+# CPU: the same C file + the reference scheduler, the decoder entry points coming from the host
+# emulation of the decoder's own source (tests/simt_emul, test infrastructure).  GPU: the real
+# binary.  Expectations: the committed decode goldens (= the reference CLI's behaviour).
+import hashlib
+import json
+
+_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decode")
+
+
+def _decode_cases():
+    return json.load(open(os.path.join(_GOLD, "manifest.json")))["cases"]
+
+
+def _check_expand(cli, cases, env_extra, nthreads):
+    env = dict(os.environ, **env_extra)
+    for c in cases:
+        z = open(os.path.join(_GOLD, c["file"]), "rb").read()
+        r = subprocess.run([cli, "-d", "-c", "-n%d" % nthreads], input=z, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, env=env, timeout=300)
+        if c["status"] == "OK":
+            assert r.returncode == 0, (c["file"], c["name"], r.stderr[-200:])
+            assert hashlib.sha256(r.stdout).hexdigest() == c["out_sha256"], (c["file"], c["name"])
+        else:
+            text = orclib.ERR_TEXT[orclib.ERR_NAMES.index(c["status"])]
+            assert r.returncode != 0 and text.encode() in r.stderr, (c["file"], c["name"], r.stderr[-200:])
+
+
+@pytest.mark.parametrize("blocks,nthreads", [(320, 2), (2, 5)])
+def test_expansion_task_graph_host_logic(blocks, nthreads):
+    if not os.path.exists(HOSTTEST):
+        pytest.skip("oracle/_ref binaries not present")
+    cases = _decode_cases()
+    cases = cases[:: 3] + [c for c in cases if c["status"] == "OK"][:12]
+    _check_expand(HOSTTEST, cases, {"LBZIP2_B200_DBLOCKS": str(blocks), "LBZIP2_B200_DWAVE_MB": "48"}, nthreads)
+
+
+def test_expansion_task_graph_round_trip_with_reference_cli():
+    if not (os.path.exists(HOSTTEST) and os.path.exists(CPU_CLI)):
+        pytest.skip("oracle/_ref binaries not present")
+    data = synth.text(1_300_000, offset=41) + b"\0" * 300_000 + synth.random_bytes(200_000, seed=41)
+    z = _reference(1, data) + _reference(3, data[:400_000])          # two streams, 20 blocks
+    want = subprocess.run([CPU_CLI, "-d", "-c"], input=z, stdout=subprocess.PIPE, check=True).stdout
+    for blocks in ("3", "64"):
+        r = subprocess.run([HOSTTEST, "-d", "-c", "-n4"], input=z, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           env=dict(os.environ, LBZIP2_B200_DBLOCKS=blocks, LBZIP2_B200_DWAVE_MB="48"), timeout=600)
+        assert r.returncode == 0 and r.stdout == want == data + data[:400_000], r.stderr[-200:]
+
+
+@pytest.mark.gpu
+def test_expansion_cli_on_the_gpu_matches_goldens_and_reference_cli():
+    if not os.path.exists(GPU_CLI):
+        pytest.skip("oracle/_ref binaries not present")
+    cases = _decode_cases()
+    _check_expand(GPU_CLI, cases[:: 2], {}, 4)
+    _check_expand(GPU_CLI, [c for c in cases if c["num_blocks"] >= 2], {"LBZIP2_B200_DBLOCKS": "2"}, 3)
+    data = synth.text(12_000_000, offset=42)
+    z = _reference(9, data)
+    r = subprocess.run([GPU_CLI, "-d", "-c", "-n8"], input=z, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0 and r.stdout == data, r.stderr[-200:]
