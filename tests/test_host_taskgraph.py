@@ -131,8 +131,8 @@ def test_expansion_cli_on_the_gpu_matches_goldens_and_reference_cli():
     if not os.path.exists(GPU_CLI):
         pytest.skip("oracle/_ref binaries not present")
     cases = _decode_cases()
-    _check_expand(GPU_CLI, cases[:: 2], {}, 4)
-    _check_expand(GPU_CLI, [c for c in cases if c["num_blocks"] >= 2], {"LBZIP2_B200_DBLOCKS": "2"}, 3)
+    _check_expand(GPU_CLI, cases[:: 12], {"LBZIP2_B200_DBLOCKS": "16"}, 4)
+    _check_expand(GPU_CLI, [c for c in cases if c["num_blocks"] >= 2][:8], {"LBZIP2_B200_DBLOCKS": "2"}, 3)
     data = synth.text(12_000_000, offset=42)
     z = _reference(9, data)
     r = subprocess.run([GPU_CLI, "-d", "-c", "-n8"], input=z, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
