@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/lbzip2_b200.h"
 #include "unbz_kernels.cuh"
@@ -63,6 +64,27 @@ static void ub_mark(lbz_decoder *d, int i) {
       ub_count_launch(d);                                                                           \
     }                                                                                               \
   } while (0)
+
+// Same, with dynamic shared memory the kernel does not touch: a way to bound how many CTAs of a
+// latency-bound one-thread-per-CTA kernel share an SM's L1 (LBZ_CHAIN_SMEM_KB, 0 = no bound).
+#define UB_LAUNCH_SMEM(d, kern, nthreads, cta, smem, ...)                                           \
+  do {                                                                                              \
+    uint64_t nt_ = (nthreads);                                                                      \
+    if (nt_) {                                                                                      \
+      unsigned grid_ = (unsigned)((nt_ + (cta) - 1) / (cta));                                       \
+      size_t sm_ = (smem);                                                                          \
+      if (sm_ > 48u * 1024u) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_); \
+      kern<<<grid_, (cta), sm_, ub_stream(d)>>>(__VA_ARGS__);                                       \
+      cudaError_t le_ = cudaGetLastError();                                                         \
+      if (le_ != cudaSuccess) return ub_cuda_fail(le_, #kern, __LINE__);                            \
+      ub_count_launch(d);                                                                           \
+    }                                                                                               \
+  } while (0)
+static size_t ub_chain_smem() {
+  static long kb = -1;
+  if (kb < 0) { const char *s = getenv("LBZ_CHAIN_SMEM_KB"); kb = s ? atol(s) : 0; if (kb < 0 || kb > 200) kb = 0; }
+  return (size_t)kb * 1024u;
+}
 
 static void ub_timers_collect(lbz_decoder *d);
 

@@ -361,8 +361,10 @@ UB_KERNEL k_ub_tree_l1(const UbBlock *blk, uint32_t nblk, const UbTreeG *tree_al
 //   bit   7      set if the entry needs care: no code, or the end-of-block symbol is among them
 //   bits  8..23  cumulative length after the 1st..4th code (4 bits each)
 //   bits 24..26  1-based index of the end-of-block symbol among them, 0 if absent
+// The low byte of every entry is also kept in a byte table of its own (mq): it is all the common case
+// of the walk reads, and at 4 KB per tree the tables of several blocks stay in one SM's L1.
 UB_KERNEL k_ub_tree_multi(const UbBlock *blk, uint32_t nblk, const UbTreeG *tree_all, const uint16_t *l1_all,
-                          uint32_t *ml_all) {
+                          uint32_t *ml_all, uint8_t *mq_all) {
   uint64_t g = UB_GID;
   uint32_t idx = (uint32_t)(g % UB_WSIZE), t = (uint32_t)((g / UB_WSIZE) % 6u), b = (uint32_t)(g / (UB_WSIZE * 6u));
   if (b >= nblk || blk[b].status != UB_PENDING || t >= blk[b].num_trees) return;
@@ -382,6 +384,7 @@ UB_KERNEL k_ub_tree_multi(const UbBlock *blk, uint32_t nblk, const UbTreeG *tree
   }
   uint32_t care = (cnt == 0 || eobk != 0) ? 0x80u : 0u;
   ml_all[((size_t)b * 6u + t) * UB_WSIZE + idx] = cum | (cnt << 4) | care | (lens << 8) | (eobk << 24);
+  mq_all[((size_t)b * 6u + t) * UB_WSIZE + idx] = (uint8_t)(cum | (cnt << 4) | care);
 }
 
 // One code by its canonical tables, for windows the 12-bit tables do not resolve.  c20 = the next
@@ -399,8 +402,8 @@ UB_DEVICE uint32_t ub_canon_decode(const UbTreeG &T, uint32_t c20, uint32_t *k) 
 // (what stopped the walk: the end-of-block symbol, the end of the input, a bad tree, no end-of-block
 // in the last group); k_ub_tok_scan turns it into retrieve()'s status.
 UB_KERNEL k_ub_chain(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint32_t nblk, const uint8_t *sel_all,
-                     const UbTreeG *tree_all, const uint16_t *l1_all, const uint32_t *ml_all, uint64_t *gpos_all,
-                     uint8_t *gtree_all) {
+                     const UbTreeG *tree_all, const uint16_t *l1_all, const uint32_t *ml_all, const uint8_t *mq_all,
+                     uint64_t *gpos_all, uint8_t *gtree_all) {
   if (UB_TID != 0) return;
   const uint32_t b = UB_BID;
   if (b >= nblk) return;
@@ -428,6 +431,7 @@ UB_KERNEL k_ub_chain(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint3
     gtree[g] = (uint8_t)t;
     const UbTreeG &T = tree_all[(size_t)b * 6u + t];
     const uint32_t *ml = ml_all + ((size_t)b * 6u + t) * UB_WSIZE;
+    const uint8_t *mq = mq_all + ((size_t)b * 6u + t) * UB_WSIZE;
     bool done = false;
 
     // Two code paths, as in the reference (src/decode.c:644-661): while a whole group (50 codes of
@@ -440,12 +444,13 @@ UB_KERNEL k_ub_chain(const uint32_t *words, uint64_t nwords, UbBlock *blk, uint3
       uint32_t rem = 50u;
       while (rem) {
         uint32_t win = ub_funnel_l(lo, hi, bp);        // the 32 bits that start at bit bp of hi
-        uint32_t e = ml[win >> (32u - UB_WBITS)];
+        uint32_t q = mq[win >> (32u - UB_WBITS)];
         uint32_t len;
-        if (rem >= 4u && !(e & 0x80u)) {               // common case: all codes of the entry, no end of block
-          len = e & 15u;
-          rem -= (e >> 4) & 7u;
+        if (rem >= 4u && !(q & 0x80u)) {               // common case: all codes of the entry, no end of block
+          len = q & 15u;
+          rem -= q >> 4;
         } else {
+          uint32_t e = ml[win >> (32u - UB_WBITS)];
           uint32_t cnt = (e >> 4) & 7u;
           if (cnt) {
             uint32_t take = cnt < rem ? cnt : rem;

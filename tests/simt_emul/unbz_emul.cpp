@@ -47,6 +47,9 @@ static int ub_emu_reverse = 0;
     if (nt_) ub_count_launch(d);                                                                    \
   } while (0)
 
+#define UB_LAUNCH_SMEM(d, kern, nthreads, cta, smem, ...) UB_LAUNCH(d, kern, nthreads, cta, __VA_ARGS__)
+static size_t ub_chain_smem() { return 0; }
+
 #include "../../lbzip2_b200/csrc/unbz_engine.inc"
 
 static inline void ub_count_launch(lbz_decoder *d) { d->launches++; }
