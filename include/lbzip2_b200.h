@@ -205,10 +205,11 @@ typedef struct lbz_dstream_info {
 } lbz_dstream_info;
 
 /* A decoder on CUDA device `device` that works on waves of up to `max_blocks`
-   candidate blocks (about 6 MB of device memory each), accepts compressed
+   candidate blocks (about 8 MB of device memory each), accepts compressed
    inputs of up to `in_cap` bytes and stages up to `out_cap` decoded bytes per
    wave (>= 47 MB so that any single block fits).  NULL (and a message) on
    failure; there is no CPU path. */
+/* A decoder is used by one thread at a time; several decoders may run concurrently. */
 lbz_decoder *lbz_decoder_create(int device, int max_blocks, size_t in_cap, size_t out_cap);
 void lbz_decoder_destroy(lbz_decoder *d);
 

@@ -12,7 +12,7 @@
  * (oracle/_ref/lbzip2 -d) on every .bz2 fixture of the reference
  * (tests/ and tests/suite/manual-expand) -- accept/reject, error kind and
  * output bytes -- and on round trips of the compress fixtures; see
- * tools/pin_unoracle.py and tests/test_unoracle.py.
+ * tools/pin_unoracle.py, tests/test_unoracle.py and tests/golden/decode/.
  */
 #include "bz_oracle.h"
 
