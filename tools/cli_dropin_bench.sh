@@ -4,7 +4,8 @@
 #   oracle/_ref/lbzip2_gpu    unmodified reference host code + per-block API of libbz2b200.so
 #   oracle/_ref/lbzip2_b200   reference CLI/scheduler + our batch-aware task graph
 #                             (lbzip2_b200/host/compress_b200.c) + libbz2b200.so
-# and a byte comparison of the three outputs.  Usage: tools/cli_dropin_bench.sh [MB] [GPUS]
+# and a byte comparison of the three outputs; then `-d` of the reference's output through the reference
+# CLI and through our expansion task graph (lbzip2_b200/host/expand_b200.c).  Usage: tools/cli_dropin_bench.sh [MB] [GPUS]
 set -e
 cd "$(dirname "$0")/.."
 MB=${1:-1000}
@@ -43,6 +44,14 @@ t "lbzip2_gpu  -9 -n64 (per-block API)" env LBZIP2_B200_CONTEXTS=64 sh -c "oracl
 t "lbzip2 (CPU reference, all cores) -9" sh -c "oracle/_ref/lbzip2 -9 -c $IN > /dev/shm/lbz_cli_cpu.bz2"
 s=$(date +%s.%N); oracle/_ref/lbzip2 -9 -n1 -c /dev/shm/lbz_cli_20.raw > /dev/null; e=$(date +%s.%N)
 echo "lbzip2 (CPU reference, -n1, 20 MB): $(python -c "print(round(20/($e-$s),1))") MB/s"
+# decompression of the reference's output: reference CLI (all cores) vs our expansion task graph
+for blocks in 320 1200; do
+  t "lbzip2_b200 -d -n8 blocks/wave=$blocks" env LBZIP2_B200_DBLOCKS=$blocks LBZIP2_B200_DWAVE_MB=1024 LBZIP2_B200_STATS=1 \
+     sh -c "oracle/_ref/lbzip2_b200 -d -n8 -c /dev/shm/lbz_cli_cpu.bz2 > /dev/shm/lbz_cli_b200.raw"
+done
+t "lbzip2 -d (CPU reference, all cores)" sh -c "oracle/_ref/lbzip2 -d -c /dev/shm/lbz_cli_cpu.bz2 > /dev/null"
+cmp /dev/shm/lbz_cli_b200.raw $IN && echo "lbzip2_b200 -d output identical to the input"
+rm -f /dev/shm/lbz_cli_b200.raw
 cmp /dev/shm/lbz_cli_b200.bz2 /dev/shm/lbz_cli_cpu.bz2 && echo "lbzip2_b200 output identical to the reference's"
 cmp /dev/shm/lbz_cli_gpu.bz2 /dev/shm/lbz_cli_cpu.bz2 && echo "lbzip2_gpu output identical to the reference's"
 rm -f /dev/shm/lbz_cli_in.raw /dev/shm/lbz_cli_20.raw /dev/shm/lbz_cli_gpu.bz2 /dev/shm/lbz_cli_cpu.bz2 /dev/shm/lbz_cli_b200.bz2
