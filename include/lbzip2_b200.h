@@ -192,6 +192,14 @@ const char *lbz_strerror(int status);
 
 typedef struct lbz_decoder lbz_decoder;
 
+/* One candidate block of a wave (mirror of struct UbBlock, csrc/unbz_kernels.cuh). */
+typedef struct lbz_dblock {
+  uint64_t pos, end_bit, out_len, out_off;
+  uint32_t status, rand, bwt_idx, block_size, alpha_size, num_trees, num_selectors;
+  uint32_t period, rl_state, crc_acc, crc, ntok, nsym, ngrp;
+  uint64_t sym_bit;
+} lbz_dblock;
+
 typedef struct lbz_dstream_info {
   uint32_t status;           /* same as the return value (>= 0)                        */
   uint32_t num_blocks;       /* blocks decoded and verified                            */
@@ -244,6 +252,20 @@ int lbz_decompress_ex(lbz_decoder *d, const uint8_t *in, size_t n, uint8_t *out,
 int lbz_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags);
 int lbz_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info);
 
+/* Building blocks for sharding the blocks of ONE file over several decoders / GPUs (blocks are
+   independent once the scanner has found their start bits; lbzip2_b200/sharding.py
+   sharded_decompress): decode a share of the candidates (count <= max_blocks; table[i]
+   describes candidate i), run the framing walk on the merged table of all shares (pure host
+   code; sorted by pos; returns LBZ_OK, LBZ_MORE if a block is missing from the table, or the
+   error that ends the stream, to be reported after the CRCs of chain[] have been checked), then
+   write the confirmed blocks of the share at out_off[i] (~0 = skip) and collect their CRCs. */
+int lbz_decoder_decode_at(lbz_decoder *d, const uint8_t *in, size_t n, const uint64_t *magic_bits, uint32_t count,
+                          lbz_dblock *table, unsigned flags);
+int lbz_walk_table(const uint8_t *in, size_t n, const lbz_dblock *table, size_t count, uint32_t *chain,
+                   uint32_t *chain_crc, size_t *nchain, lbz_dstream_info *info);
+int lbz_decoder_emit_at(lbz_decoder *d, const uint64_t *out_off, uint32_t count, uint8_t *out, size_t out_cap,
+                        size_t *out_len, uint32_t *crc);
+
 /* Block-boundary scanner alone (row f3): bit positions of every 48-bit block
    magic 0x314159265359 in the input, ascending.  Returns the number found
    (written up to cap), negative on failure. */
@@ -256,12 +278,7 @@ enum lbz_darray {
   LBZ_DA_TEXT = 2,     /* u8  inverse BWT output (still run-length coded)      */
   LBZ_DA_OUT = 3       /* u8  the wave's decoded bytes (slot = byte offset)    */
 };
-typedef struct lbz_dblock {
-  uint64_t pos, end_bit, out_len, out_off;
-  uint32_t status, rand, bwt_idx, block_size, alpha_size, num_trees, num_selectors;
-  uint32_t period, rl_state, crc_acc, crc, ntok, nsym, ngrp;
-  uint64_t sym_bit;
-} lbz_dblock;
+
 int lbz_decoder_read(lbz_decoder *d, int array, uint64_t slot, void *dst, size_t bytes);
 uint32_t lbz_decoder_last_wave_blocks(const lbz_decoder *d);
 uint64_t lbz_decoder_launches(const lbz_decoder *d);

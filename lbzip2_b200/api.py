@@ -80,6 +80,7 @@ EXPORTS = [
     "lbz_decoder_load", "lbz_scan_blocks", "lbz_decoder_read", "lbz_decoder_last_wave_blocks",
     "lbz_decoder_launches", "lbz_decoder_device_bytes", "lbz_decoder_last_ms", "lbz_decoder_stage_ms",
     "lbz_strerror", "lbz_decoder_open", "lbz_decoder_next",
+    "lbz_decoder_decode_at", "lbz_decoder_emit_at", "lbz_walk_table",
 ]
 
 
@@ -177,6 +178,13 @@ def load_library():
     L.lbz_decoder_open.argtypes = [vp, vp, C.c_size_t, C.c_uint]
     L.lbz_decoder_next.restype = C.c_int
     L.lbz_decoder_next.argtypes = [vp, vp, C.c_size_t, szp, C.POINTER(DStreamInfo)]
+    L.lbz_decoder_decode_at.restype = C.c_int
+    L.lbz_decoder_decode_at.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(DBlock), C.c_uint]
+    L.lbz_decoder_emit_at.restype = C.c_int
+    L.lbz_decoder_emit_at.argtypes = [vp, C.POINTER(C.c_uint64), C.c_uint32, vp, C.c_size_t, szp, C.POINTER(C.c_uint32)]
+    L.lbz_walk_table.restype = C.c_int
+    L.lbz_walk_table.argtypes = [vp, C.c_size_t, C.POINTER(DBlock), C.c_size_t, C.POINTER(C.c_uint32),
+                                 C.POINTER(C.c_uint32), szp, C.POINTER(DStreamInfo)]
     L.lbz_strerror.restype = C.c_char_p
     L.lbz_strerror.argtypes = [C.c_int]
     _LIB = L
@@ -315,6 +323,30 @@ class Engine:
         return self.dbg_read_struct(AR_META, slot, BlockMeta)
 
 
+NOEMIT = 0xFFFFFFFFFFFFFFFF
+
+
+def dblock_copy(b):
+    c = DBlock()
+    C.memmove(C.byref(c), C.byref(b), C.sizeof(DBlock))
+    return c
+
+
+def walk_table(fn, z, table):
+    """Framing walk over decoded candidates sorted by position (lbz_walk_table):
+    (status, chain indices, expected CRCs, DStreamInfo)."""
+    a = _as_u8(z)
+    k = len(table)
+    arr = (DBlock * max(k, 1))(*table)
+    chain = (C.c_uint32 * max(k, 1))()
+    ccrc = (C.c_uint32 * max(k, 1))()
+    n = C.c_size_t(0)
+    info = DStreamInfo()
+    src = a if a.size else np.zeros(1, np.uint8)
+    st = fn(src.ctypes.data, a.size, arr, k, chain, ccrc, C.byref(n), C.byref(info))
+    return st, list(chain[: n.value]), list(ccrc[: n.value]), info
+
+
 class Decoder:
     """One GPU context for batch decompression (mirror of lbz_decoder)."""
 
@@ -370,6 +402,32 @@ class Decoder:
             yield st, buf[: n.value].tobytes()
             if st != 1:
                 return
+
+    # ---- sharding building blocks (see lbzip2_b200/sharding.py sharded_decompress) ----
+    def decode_at(self, z, positions):
+        """Decode the candidate blocks whose magics start at the given bit positions; list of DBlock."""
+        a = _as_u8(z)
+        k = len(positions)
+        pos = (C.c_uint64 * max(k, 1))(*positions)
+        table = (DBlock * max(k, 1))()
+        src = a if a.size else np.zeros(1, np.uint8)
+        if self.L.lbz_decoder_decode_at(self.h, src.ctypes.data, a.size, pos, k, table, 0):
+            raise LbzError("lbz_decoder_decode_at failed")
+        return [dblock_copy(table[i]) for i in range(k)]
+
+    def emit_at(self, out_offs, cap):
+        """Write the blocks of the last decode_at at the given offsets (NOEMIT = skip): (bytes, crcs)."""
+        k = len(out_offs)
+        offs = (C.c_uint64 * max(k, 1))(*out_offs)
+        crc = (C.c_uint32 * max(k, 1))()
+        buf = np.empty(max(cap, 1), dtype=np.uint8)
+        n = C.c_size_t(0)
+        if self.L.lbz_decoder_emit_at(self.h, offs, k, buf.ctypes.data, cap, C.byref(n), crc):
+            raise LbzError("lbz_decoder_emit_at failed")
+        return buf[: n.value].tobytes(), list(crc[:k])
+
+    def walk_table(self, z, table):
+        return walk_table(self.L.lbz_walk_table, z, table)
 
     def decompress_ptr(self, in_ptr, n, out_ptr, out_cap, flags=0):
         """Raw-pointer form; returns (status, out_len, info)."""

@@ -177,6 +177,24 @@ extern "C" int lbz_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, si
   return ub_next(d, out, out_cap, out_len ? out_len : &dummy, info);
 }
 
+extern "C" int lbz_decoder_decode_at(lbz_decoder *d, const uint8_t *in, size_t n, const uint64_t *magic_bits, uint32_t count,
+                                     lbz_dblock *table, unsigned flags) {
+  if (cudaSetDevice(d->be.device) != cudaSuccess) return -1;
+  return ub_decode_at(d, in, n, magic_bits, count, table, flags);
+}
+
+extern "C" int lbz_decoder_emit_at(lbz_decoder *d, const uint64_t *out_off, uint32_t count, uint8_t *out, size_t out_cap,
+                                   size_t *out_len, uint32_t *crc) {
+  if (cudaSetDevice(d->be.device) != cudaSuccess) return -1;
+  size_t dummy = 0;
+  return ub_emit_at(d, out_off, count, out, out_cap, out_len ? out_len : &dummy, crc);
+}
+
+extern "C" int lbz_walk_table(const uint8_t *in, size_t n, const lbz_dblock *table, size_t count, uint32_t *chain,
+                              uint32_t *chain_crc, size_t *nchain, lbz_dstream_info *info) {
+  return ub_walk_table(in, n, table, count, chain, chain_crc, nchain, info);
+}
+
 extern "C" long lbz_scan_blocks(lbz_decoder *d, const uint8_t *in, size_t n, uint64_t *bit_positions, size_t cap) {
   if (cudaSetDevice(d->be.device) != cudaSuccess) return -1;
   if (ub_upload(d, in, n) != 0) return -1;

@@ -166,3 +166,86 @@ class BlockGatherer:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         return tables, payloads
+
+
+# ----------------------------------------------------------------------------------------------
+# Decompression: the blocks of ONE .bz2 file over several decoders / GPUs.
+#
+# Once the scanner (lbz_scan_blocks, reference src/parse.c:281-342) has found the block magics,
+# blocks are independent: candidate i goes to rank i mod world.  Every rank decodes its share
+# speculatively (lbz_decoder_decode_at), the small per-block tables are all-gathered, every rank
+# runs the same framing walk on the merged table (lbz_walk_table; src/parse.c:147-263 and the
+# per-block checks of src/expand.c:725-736) and so knows which of its candidates are real blocks
+# and where their bytes go, writes them (lbz_decoder_emit_at) and sends (offset, bytes, CRC) to
+# rank 0, which checks the CRCs in stream order.  No collective on the data path besides that
+# gather.  Works over any torch.distributed backend (gloo in the CPU test).
+
+def _row(b):
+    return (int(b.pos), int(b.end_bit), int(b.out_len), int(b.status), int(b.block_size), int(b.rl_state),
+            int(b.bwt_idx), int(b.rand))
+
+
+def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFFFFFFFFFF):
+    """Decompress the file `z` (bytes, present on every rank) with `world` decoders.
+    `dec` offers scan / decode_at / emit_at / walk_table (lbzip2_b200.Decoder).
+    Returns (status, output bytes, info) on rank 0 and (the same status, None, info) elsewhere.
+    Status and surviving output follow lbz_decompress_stream."""
+    hits = dec.scan(z)
+    mine = hits[rank::world]
+    rows = [_row(b) for b in dec.decode_at(z, mine)]
+    every = [None] * world
+    if world > 1:
+        dist.all_gather_object(every, rows)
+    else:
+        every = [rows]
+    merged = sorted((r + (src,) for src in range(world) for r in every[src]), key=lambda r: r[0])
+    table = []
+    for r in merged:
+        b = dblock_type()
+        b.pos, b.end_bit, b.out_len, b.status, b.block_size, b.rl_state, b.bwt_idx, b.rand = r[:8]
+        table.append(b)
+    status, chain, chain_crc, info = dec.walk_table(z, table)
+    if status == 1:                       # LBZ_MORE cannot happen: every block magic is a scanner hit
+        raise RuntimeError("a block of the stream was not among the scanner's candidates")
+    # global output offsets of the confirmed blocks, and this rank's share of them
+    goff, o = {}, 0
+    for k in chain:
+        goff[merged[k][0]] = o
+        o += merged[k][2]
+    local_off, cursor = [], 0
+    for b in rows:
+        if b[0] in goff:
+            local_off.append(cursor)
+            cursor += b[2]
+        else:
+            local_off.append(noemit)
+    payload, crcs = dec.emit_at(local_off, max(cursor, 1))
+    parts = [(goff[b[0]], b[2], local_off[i], crcs[i]) for i, b in enumerate(rows) if b[0] in goff]
+    gathered = [None] * world
+    if world > 1:
+        dist.gather_object((parts, payload), gathered if rank == 0 else None, dst=0)
+    else:
+        gathered = [(parts, payload)]
+    if rank != 0:
+        final = [None]
+        dist.broadcast_object_list(final, src=0)      # a CRC error found by rank 0 outranks the walk's verdict
+        info.status, info.num_blocks = final[0]
+        return final[0][0], None, info
+    # rank 0: CRCs in stream order; the first bad block ends the output (src/expand.c:731-736)
+    got = {}
+    for prt, pay in gathered:
+        for g, ln, lo, crc in prt:
+            got[g] = (pay[lo:lo + ln], crc)
+    out, nblocks = [], 0
+    for k, want in zip(chain, chain_crc):
+        data, crc = got[goff[merged[k][0]]]
+        if crc != want:
+            status = 15                   # LBZ_ERR_BLKCRC
+            break
+        out.append(data)
+        nblocks += 1
+    info.num_blocks = nblocks
+    info.status = status
+    if world > 1:
+        dist.broadcast_object_list([(status, nblocks)], src=0)
+    return status, b"".join(out), info

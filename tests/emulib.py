@@ -60,6 +60,14 @@ def lib():
         L.emu_gf_shift.restype = C.c_uint32
         L.emu_gf_shift.argtypes = [C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32)]
         L.emu_set_reverse.argtypes = [C.c_int]
+        L.emu_decode_at.restype = C.c_int
+        L.emu_decode_at.argtypes = [C.c_void_p, u8p, C.c_size_t, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(DBlock), C.c_uint]
+        L.emu_emit_at.restype = C.c_int
+        L.emu_emit_at.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p, C.c_size_t,
+                                  C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
+        L.emu_walk_table.restype = C.c_int
+        L.emu_walk_table.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(DBlock), C.c_size_t, C.POINTER(C.c_uint32),
+                                     C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), C.POINTER(DStreamInfo)]
         _lib = L
     return _lib
 
@@ -105,6 +113,40 @@ class EmuDecoder:
         a = np.empty(max(nbytes, 1), np.uint8)
         assert self.L.emu_decoder_read(self.h, which, slot, a.ctypes.data_as(C.c_void_p), nbytes) == 0
         return a[:nbytes]
+
+    # the sharding building blocks, same surface as lbzip2_b200.Decoder
+    def decode_at(self, z, positions):
+        a = np.frombuffer(bytes(z), dtype=np.uint8) if len(z) else np.zeros(1, np.uint8)
+        k = len(positions)
+        pos = (C.c_uint64 * max(k, 1))(*positions)
+        table = (DBlock * max(k, 1))()
+        assert self.L.emu_decode_at(self.h, a.ctypes.data_as(u8p), len(z), pos, k, table, 0) == 0
+        out = []
+        for i in range(k):
+            c = DBlock()
+            C.memmove(C.byref(c), C.byref(table[i]), C.sizeof(DBlock))
+            out.append(c)
+        return out
+
+    def emit_at(self, out_offs, cap):
+        k = len(out_offs)
+        offs = (C.c_uint64 * max(k, 1))(*out_offs)
+        crc = (C.c_uint32 * max(k, 1))()
+        buf = np.empty(max(cap, 1), dtype=np.uint8)
+        n = C.c_size_t(0)
+        assert self.L.emu_emit_at(self.h, offs, k, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), crc) == 0
+        return buf[: n.value].tobytes(), list(crc[:k])
+
+    def walk_table(self, z, table):
+        a = np.frombuffer(bytes(z), dtype=np.uint8) if len(z) else np.zeros(1, np.uint8)
+        k = len(table)
+        arr = (DBlock * max(k, 1))(*table)
+        chain = (C.c_uint32 * max(k, 1))()
+        ccrc = (C.c_uint32 * max(k, 1))()
+        n = C.c_size_t(0)
+        info = DStreamInfo()
+        st = self.L.emu_walk_table(a.ctypes.data_as(C.c_void_p), len(z), arr, k, chain, ccrc, C.byref(n), C.byref(info))
+        return st, list(chain[: n.value]), list(ccrc[: n.value]), info
 
     @property
     def last_wave_blocks(self):

@@ -79,6 +79,16 @@ int emu_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags
 int emu_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info) {
   return ub_next(d, out, out_cap, out_len, info);
 }
+int emu_decode_at(lbz_decoder *d, const uint8_t *in, size_t n, const uint64_t *pos, uint32_t count, lbz_dblock *table, unsigned flags) {
+  return ub_decode_at(d, in, n, pos, count, table, flags);
+}
+int emu_emit_at(lbz_decoder *d, const uint64_t *out_off, uint32_t count, uint8_t *out, size_t out_cap, size_t *out_len, uint32_t *crc) {
+  return ub_emit_at(d, out_off, count, out, out_cap, out_len, crc);
+}
+int emu_walk_table(const uint8_t *in, size_t n, const lbz_dblock *table, size_t count, uint32_t *chain, uint32_t *chain_crc,
+                   size_t *nchain, lbz_dstream_info *info) {
+  return ub_walk_table(in, n, table, count, chain, chain_crc, nchain, info);
+}
 long emu_scan_blocks(lbz_decoder *d, const uint8_t *in, size_t n, uint64_t *pos, size_t cap) {
   if (ub_upload(d, in, n) != 0 || ub_scan(d, (n + 3) / 4) != 0) return -1;
   for (size_t i = 0; i < d->hits.size() && i < cap; i++) pos[i] = d->hits[i];
