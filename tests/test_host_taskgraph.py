@@ -137,3 +137,23 @@ def test_expansion_cli_on_the_gpu_matches_goldens_and_reference_cli():
     z = _reference(9, data)
     r = subprocess.run([GPU_CLI, "-d", "-c", "-n8"], input=z, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
     assert r.returncode == 0 and r.stdout == data, r.stderr[-200:]
+
+
+def test_expansion_task_graph_several_operands_and_thread_counts(tmp_path):
+    """One process, several files (the decoder outlives an operand and is re-sized for a larger
+    one, src/main.c:935), -n from 1 to 64, small and large waves."""
+    if not (os.path.exists(HOSTTEST) and os.path.exists(CPU_CLI)):
+        pytest.skip("oracle/_ref binaries not present")
+    files = {"a": synth.text(200_000, offset=5), "b": synth.text(2_200_000, offset=6), "c": b""}
+    for name, data in files.items():
+        (tmp_path / (name + ".bz2")).write_bytes(_reference(2, data))
+    args = [str(tmp_path / (n + ".bz2")) for n in ("a", "b", "c")]
+    r = subprocess.run([HOSTTEST, "-d", "-k", "-f"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0 and r.stderr == b"", r.stderr[-300:]
+    for name, data in files.items():
+        assert (tmp_path / name).read_bytes() == data
+    z = (tmp_path / "b.bz2").read_bytes()
+    for n, blocks in ((1, "1"), (3, "7"), (64, "320")):
+        r = subprocess.run([HOSTTEST, "-d", "-c", "-n%d" % n], input=z, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           env=dict(os.environ, LBZIP2_B200_DBLOCKS=blocks, LBZIP2_B200_DWAVE_MB="48"), timeout=600)
+        assert r.returncode == 0 and r.stdout == files["b"], (n, blocks, r.stderr[-200:])
