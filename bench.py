@@ -51,13 +51,29 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-decompress", action="store_true", help="skip the decompression leg")
+    ap.add_argument("--batch-chunks", type=int, default=560,
+                    help="engine capacity in chunks; larger inputs run as consecutive batches (560 chunks = 37 GB of HBM at -9)")
+    ap.add_argument("--ref-sample-mb", type=int, default=0,
+                    help="reference arm / cpu_baseline: MB of the workload per step (0 = choose: >= 1000 MB when time allows)")
     return ap.parse_args()
 
 
-def make_input(workload, nbytes, rank):
+def workload_name(a):
+    """One string for both arms (the driver compares config.workload of the two lines)."""
+    shape = {"text": "enwik8-shaped synthetic text", "random": "uniform random bytes (PCG64)",
+             "runs_fib": "single-byte run + Fibonacci word (tests/fib.c)"}[a.workload]
+    return "%d MB %s per GPU at -%d" % (a.size_mb, shape, a.level)
+
+
+def make_input(workload, nbytes, rank, procs=None):
+    """Synthetic input of rank `rank`.  Text up to 100 MB is one stream of the generator (offset =
+    rank); larger text inputs are consecutive 100 MB streams of the same family (offsets
+    1000 * (rank + 1) + j), generated in parallel worker processes -- call before CUDA init."""
     import synth
     if workload == "text":
-        return synth.text(nbytes, offset=rank)
+        if nbytes <= 100 * MB:
+            return synth.text(nbytes, offset=rank)
+        return synth.text_streams(nbytes, first_offset=1000 * (rank + 1), procs=procs)
     if workload == "random":
         return synth.random_bytes(nbytes, seed=1 + rank)
     return synth.runs_and_fib(nbytes)
@@ -70,14 +86,20 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def ncu_traffic(a, nchunks, k0_bytes):
-    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum)
-    from the committed `ncu --set full` capture profiles/r01_ncu_text_pass2_v8.txt.  The capture
-    was taken on the default workload (112 chunks of text at -9: 804.2 MB read + 784.4 MB written
-    for 1602.2 MB algorithmic); for that workload the measured figure is reported, otherwise null."""
-    if a.workload == "text" and a.level == 9 and nchunks == 112 and abs(k0_bytes - 1602183056) < 1e6:
-        return 1588643328
-    return None
+def ncu_traffic(kernel, elements):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` from the
+    newest committed `ncu --set full` capture of a launch over the same number of elements
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py from the .ncu-rep); null when no
+    capture matches -- the figure is never a constant in this file."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p) or not elements:
+        return None
+    best = None
+    for ent in json.load(open(p)):
+        if ent.get("kernel") == kernel and abs(ent.get("elements", 0) - elements) <= 0.005 * elements:
+            if best is None or ent.get("order", 0) > best.get("order", 0):
+                best = ent
+    return int(best["dram_bytes"]) if best else None
 
 
 class ClockSampler:
@@ -161,18 +183,34 @@ def time_reference(data, level, steps, warmup, threads):
     return times, kind, sha
 
 
+def reference_sample(a, own_data=None):
+    """The bytes the reference CLI is timed on: a bounded sample of the workload, at least 1 GB
+    when the CLI is available (a 100 MB batch is only 112 work units: with 16-32 host threads
+    the tail of the run idles and process start-up weighs in), 10 MB for the scalar oracle port."""
+    if not ref_binary():
+        d = own_data if own_data is not None else make_input(a.workload, min(a.size_mb, 10) * MB, 0)
+        return d[: 10 * MB]
+    mb = a.ref_sample_mb or max(a.size_mb, 1000)
+    if own_data is not None and len(own_data) >= mb * MB:
+        return own_data[: mb * MB]
+    return make_input(a.workload, mb * MB, 0)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nbytes = a.size_mb * MB
-    data = make_input(a.workload, nbytes, 0)
     cores = os.cpu_count() or 1
     binp = ref_binary()
     threads = cores if binp else 1
-    # bounded sample: the whole per-GPU batch when the pthread reference is available
-    # (a fraction of a second on a many-core host), 10 MB for the scalar oracle port
-    sample = data if binp else data[: 10 * MB]
+    sample = reference_sample(a)
+    # keep the whole run within a few minutes: one calibration pass, then shrink the sample if needed
+    t_cal, _, _ = time_reference(sample, a.level, 1, 0, threads)
+    budget_s = 170.0
+    est = t_cal[0] / 1e3 * (a.steps + a.warmup)
+    if est > budget_s and len(sample) > 100 * MB:
+        keep = max(100, int(len(sample) / MB * budget_s / est) // 100 * 100)
+        sample = sample[: keep * MB]
     times, kind, _ = time_reference(sample, a.level, a.steps, a.warmup, threads)
     ms = float(np.mean(times))
     val = len(sample) / MB / (ms / 1e3)
@@ -180,8 +218,7 @@ def run_reference(a):
         "impl": "reference", "metric": "input MB/s at -9 (bit-exact .bz2)", "value": round(val, 2), "unit": "MB/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "%d MB enwik8-shaped synthetic text at -%d (bounded sample of the per-GPU batch)" % (len(sample) // MB, a.level)
-                   if a.workload == "text" else "%d MB %s at -%d" % (len(sample) // MB, a.workload, a.level)},
+        "config": {"workload": workload_name(a)},
         "cpu_baseline": {"value": round(val, 2), "unit": "MB/s", "cores": threads, "kind": kind,
                          "sample": "%d MB of the workload per step, lbzip2 -%d -n%d from /dev/shm to /dev/null" % (len(sample) // MB, a.level, threads)
                          if binp else "10 MB of the workload, scalar oracle port"},
@@ -266,7 +303,7 @@ def decompress_leg(a, lbzip2_b200, L, local, stream, data, recs):
                        "achieved": round(walk_gbs, 2), "peak": hbm_peak, "unit": "GB/s",
                        "frac": round(walk_gbs / hbm_peak, 6), "bytes_per_launch": int(walk_bytes),
                        "avg_launch_ms": round(retrieve_ms, 3),
-                       "traffic": 45818368 if (a.workload == "text" and a.level == 9 and a.size_mb == 100) else None,
+                       "traffic": ncu_traffic("k_ub_chain", len(recs)),
                        "note": "latency-bound: 1 warp per block, 1.9 % of warp slots active (profiles/r01_ncu_chain_v11.txt); "
                                "traffic = dram read+write of the k_ub_chain capture"}
     dec.close()
@@ -275,6 +312,8 @@ def decompress_leg(a, lbzip2_b200, L, local, stream, data, recs):
     # the same stream four times over (a concatenated .bz2, 4x the blocks in one wave) shows what
     # the kernels do with more blocks in flight.
     try:
+        if nbytes > 200 * MB:
+            raise RuntimeError("skipped for inputs > 200 MB (the stream already holds > 400 blocks)")
         reps = 4
         z4 = stream * reps
         dec4 = lbzip2_b200.Decoder(device=local, max_blocks=reps * len(recs) + 8, in_cap=len(z4) + 64,
@@ -336,6 +375,21 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no GPU visible; the product has no CPU path (use --impl reference for the CPU arm)")
+    # the input is generated before CUDA is initialised (large text inputs fork worker processes)
+    data = make_input(a.workload, a.size_mb * MB, rank, procs=max(1, (os.cpu_count() or 1) // world))
+    # reference CPU path beside the GPU numbers (rank 0 at N=1 only): timed first, while the GPU is
+    # still idle, on a bounded sample of the workload (>= 1 GB: all host threads stay busy)
+    cpu_base = None
+    if world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        have_cli = ref_binary() is not None
+        sample = reference_sample(a, own_data=data)
+        times, kind, _ = time_reference(sample, a.level, 3, 1, cores if have_cli else 1)
+        cpu_base = {"value": round(len(sample) / MB / (min(times) / 1e3), 2), "unit": "MB/s",
+                    "cores": cores if have_cli else 1, "kind": kind,
+                    "sample": ("%d MB of the workload, lbzip2 -%d -n%d, /dev/shm -> /dev/null, best of 3" % (len(sample) // MB, a.level, cores))
+                    if have_cli else "10 MB of the batch, scalar oracle port"}
+        del sample
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -345,8 +399,8 @@ def run_ours(a):
     level, mbs = a.level, a.level * 100000
     nbytes = a.size_mb * MB
     nchunks = (nbytes + mbs - 1) // mbs
-    data = make_input(a.workload, nbytes, rank)
-    eng = lbzip2_b200.Engine(device=local, level=level, max_chunks=nchunks)
+    eng_chunks = min(nchunks, max(1, a.batch_chunks))      # larger inputs: consecutive batches inside one call
+    eng = lbzip2_b200.Engine(device=local, level=level, max_chunks=eng_chunks)
     L = eng.L
     cap = L.lbz_bound(nbytes) + 64
 
@@ -424,6 +478,8 @@ def run_ours(a):
 
     rd = timed(step_device)
     rh = timed(step_host)
+    sort_rounds = eng.last_rounds
+    dev_bytes = eng.device_bytes
 
     # The dominant kernel is timed ALONE for the roofline: the production engine runs
     # two lanes whose kernels overlap, which stretches every individual launch, so a
@@ -433,48 +489,83 @@ def run_ours(a):
     if world == 1:
         prev = os.environ.get("LBZ_LANES")
         os.environ["LBZ_LANES"] = "1"
-        eng1 = lbzip2_b200.Engine(device=local, level=level, max_chunks=nchunks)
+        eng.close()                                       # one engine's working set at a time (37 GB at 560 chunks)
+        eng1 = lbzip2_b200.Engine(device=local, level=level, max_chunks=eng_chunks)
         if prev is None:
             del os.environ["LBZ_LANES"]
         else:
             os.environ["LBZ_LANES"] = prev
         acc = [0.0, 0, 0]
-        for i in range(a.warmup + a.steps):
+        reps1 = (a.warmup + a.steps) if nbytes <= 200 * MB else 2
+        for i in range(reps1):
             eng1.compress_chunks_ptr(d_in.data_ptr(), nbytes, d_out.data_ptr(), cap, device=True)
-            if i >= a.warmup:
+            if i >= min(a.warmup, reps1 - 1):
                 s1 = eng1.k0_stats()
                 acc[0] += s1[0]; acc[1] += s1[1]; acc[2] = s1[2]
         k0_single = acc
-        single_ms = eng1.last_ms
         eng1.close()
 
     # ---- correctness of what was timed (outside the timed region) -------------------
     n_out, recs = rd["last"][2], rd["last"][3]
     verified = {}
+    ref_sha_own = None
+    stream = None
+    big = nbytes > 200 * MB
+    binp = ref_binary()
+    if not a.no_verify:
+        # every rank: the blocks it produced, framed as a stream of their own, against the reference
+        # CLI on the same bytes (bit-exact), or a bz2 round trip when the CLI is absent
+        import bz2
+        body = d_out[:n_out].cpu().numpy().tobytes()
+        cc = 0
+        for r in recs:
+            cc = (((cc << 1) & 0xFFFFFFFF) ^ (cc >> 31) ^ r.crc ^ 0xFFFFFFFF) & 0xFFFFFFFF
+        stream = b"BZh" + bytes([48 + level]) + body + bytes([0x17, 0x72, 0x45, 0x38, 0x50, 0x90]) + cc.to_bytes(4, "big")
+        own = {"sha256": hashlib.sha256(stream).hexdigest()}
+        host_body = bytes((C.c_uint8 * rh["last"][2]).from_address(h_out))
+        own["host_equals_device_path"] = host_body == body
+        del host_body
+        if binp:
+            tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+            path = os.path.join(tmp, "lbz_bench_own_%d.raw" % os.getpid())
+            with open(path, "wb") as f:
+                f.write(data)
+            try:
+                cores = max(1, (os.cpu_count() or 1) // world)
+                t0 = time.perf_counter()
+                ref_out = subprocess.run([binp, "-%d" % level, "-n%d" % cores, "-c", path], stdout=subprocess.PIPE, check=True).stdout
+                own["ref_cli_s"] = round(time.perf_counter() - t0, 3)
+            finally:
+                os.unlink(path)
+            ref_sha_own = hashlib.sha256(ref_out).hexdigest()
+            own["bit_exact_vs_reference_cli"] = ref_sha_own == own["sha256"]
+            del ref_out
+        if not big or not binp:
+            own["roundtrip"] = bz2.decompress(stream) == data
+        own["periodic_blocks"] = sum(1 for r in recs if r.tie_count > 1)
+        if world == 1:
+            verified = own
+        else:
+            allv = [None] * world
+            dist.all_gather_object(allv, own)
+            if rank == 0:
+                verified["bit_exact_vs_reference_cli_every_rank"] = all(v.get("bit_exact_vs_reference_cli", False) for v in allv) if binp else None
+                verified["host_equals_device_path_every_rank"] = all(v["host_equals_device_path"] for v in allv)
+                verified["periodic_blocks"] = sum(v["periodic_blocks"] for v in allv)
+                verified["rank_sha256"] = [v["sha256"][:16] for v in allv]
     all_sha = [hashlib.sha256(data).hexdigest()]
     if world > 1:
         all_sha = [None] * world
         dist.all_gather_object(all_sha, hashlib.sha256(data).hexdigest())
-    if rank == 0 and not a.no_verify:
+    if rank == 0 and not a.no_verify and world > 1:
         import bz2
-        if world == 1:
-            body = d_out[:n_out].cpu().numpy().tobytes()
-            cc = 0
-            for r in recs:
-                cc = (((cc << 1) & 0xFFFFFFFF) ^ (cc >> 31) ^ r.crc ^ 0xFFFFFFFF) & 0xFFFFFFFF
-            stream = b"BZh" + bytes([48 + level]) + body + bytes([0x17, 0x72, 0x45, 0x38, 0x50, 0x90]) + cc.to_bytes(4, "big")
-            host_body = bytes((C.c_uint8 * rh["last"][2]).from_address(h_out))
-            verified["host_equals_device_path"] = host_body == body
-            verified["roundtrip"] = bz2.decompress(stream) == data
-            verified["sha256"] = hashlib.sha256(stream).hexdigest()
-        else:
-            tables, payloads = sharding.to_host(*rd["last"][4])
-            stream = sharding.assemble_stream(level, tables, payloads, world)
+        tables, payloads = sharding.to_host(*rd["last"][4])
+        gstream = sharding.assemble_stream(level, tables, payloads, world)
+        if not big:
             # chunk i of the job is chunk i // world of rank i % world: de-interleave the
             # decoded stream and compare every rank's part with the sha256 of its input
-            plain = bz2.decompress(stream)
+            plain = bz2.decompress(gstream)
             ok = len(plain) == world * nbytes
-            # stream chunk i is chunk i // world of rank i % world; every rank's last chunk is short
             lens = [min(mbs, nbytes - (i // world) * mbs) for i in range(world * nchunks)]
             offs = [0]
             for ln in lens:
@@ -483,7 +574,26 @@ def run_ours(a):
                 part = b"".join(plain[offs[i]:offs[i + 1]] for i in range(r, world * nchunks, world))
                 ok = ok and hashlib.sha256(part).hexdigest() == all_sha[r]
             verified["gathered_stream_roundtrip"] = ok
-        verified["periodic_blocks"] = sum(1 for r in recs if r.tie_count > 1)
+        elif binp:
+            # large inputs: the gathered stream passes the reference CLI's integrity test (every block
+            # CRC and the combined CRC, which depends on the block order), and its head decodes to
+            # the first chunks in round-robin order (rank 0's first chunk, rank 1's, ...)
+            tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+            path = os.path.join(tmp, "lbz_bench_gathered_%d.bz2" % os.getpid())
+            with open(path, "wb") as f:
+                f.write(gstream)
+            try:
+                verified["gathered_stream_passes_lbzip2_t"] = subprocess.run([binp, "-t", path]).returncode == 0
+                p = subprocess.Popen([binp, "-d", "-c", path], stdout=subprocess.PIPE)
+                head = p.stdout.read(mbs)
+                p.stdout.close()
+                p.kill()
+                p.wait()
+                verified["gathered_stream_head_is_rank0_chunk0"] = head == data[:mbs]
+            finally:
+                os.unlink(path)
+        verified["gathered_stream_bytes"] = len(gstream)
+        del gstream
 
     # ---- decompression leg: the stream just produced, back through the
     # batch decompressor; reported under "decompress", the headline stays the compressor ----
@@ -520,10 +630,10 @@ def run_ours(a):
         "metric": "input MB/s at -9 (bit-exact .bz2)", "value": round(value, 2), "unit": "MB/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": ("%d MB enwik8-shaped synthetic text per GPU at -%d" % (a.size_mb, level)) if a.workload == "text"
-                   else "%d MB %s per GPU at -%d" % (a.size_mb, a.workload, level),
-                   "chunks_per_gpu": nchunks, "blocks": len(recs), "l2": "inputs (100 MB) and working set (>7 GB) larger than L2",
-                   "generator": "tests/synth.py seed 0x5EED, stream offset = rank",
+        "config": {"workload": workload_name(a),
+                   "chunks_per_gpu": nchunks, "blocks": len(recs), "batches_per_step": (nchunks + eng_chunks - 1) // eng_chunks,
+                   "l2": "inputs (%d MB) and working set (%.1f GB) larger than L2" % (a.size_mb, dev_bytes / 1e9),
+                   "generator": "tests/synth.py (text: seed 0x5EED, stream offset = rank; > 100 MB: consecutive 100 MB streams)",
                    "gather": ("device leg: NCCL gather of block bitstreams + block table to rank 0; host leg: block table only, "
                               "payload stays in each rank's pinned host memory") if world > 1 else "none (single GPU)"},
         "e2e": {"value": round(e2e, 2), "unit": "MB/s", "ms_per_step": round(ms_e2e, 3),
@@ -533,28 +643,19 @@ def run_ours(a):
         "clocks": rd["clocks"],
         "roofline": {"bound": "hbm", "kernel": "k_text_pass2 (one LSD pass of the initial rotation sort, 8 per batch)",
                      "achieved": round(k0_gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(k0_gbs / hbm_peak, 4),
-                     "traffic": ncu_traffic(a, nchunks, k0_bytes), "peak_kind": peak_kind,
+                     "traffic": ncu_traffic("k_text_pass2", k0_elems), "peak_kind": peak_kind,
                      "bytes_per_launch": int(k0_bytes), "avg_launch_ms": round(k0_avg_ms, 4),
                      "timed": "single-lane engine, kernel alone on the GPU" if k0_single else "inside the two-lane step"},
         "path_roofline": {"model": "n + 13n' + 20nm + z per block (SURVEY.md 8d)", "bytes_per_step": int(path_bytes),
                           "achieved": round(path_gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(path_gbs / hbm_peak, 5)},
-        "stage_ms_summed_over_lanes": stage, "sort_rounds": eng.last_rounds,
+        "stage_ms_summed_over_lanes": stage, "sort_rounds": sort_rounds,
         "wall_ms_per_step": round(rd["wall_ms"] / a.steps, 3), "verified": verified,
         "compressed_ratio": round(nbytes / max(n_out, 1), 3),
     }
     if decomp is not None:
         line["decompress"] = decomp
-    if world == 1 and not a.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        binp = ref_binary()
-        sample = data if binp else data[: 10 * MB]
-        times, kind, sha = time_reference(sample, level, 3, 1, cores if binp else 1)
-        v = len(sample) / MB / (min(times) / 1e3)
-        line["cpu_baseline"] = {"value": round(v, 2), "unit": "MB/s", "cores": cores if binp else 1, "kind": kind,
-                                "sample": ("%d MB (the whole batch), lbzip2 -%d -n%d, /dev/shm -> /dev/null, best of 3" % (len(sample) // MB, level, cores))
-                                if binp else "10 MB of the batch, scalar oracle port"}
-        if binp and "sha256" in verified:
-            line["verified"]["bit_exact_vs_reference_cli"] = (sha == verified["sha256"])
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
     print(json.dumps(line))
     L.lbz_host_free(h_in)
     L.lbz_host_free(h_out)

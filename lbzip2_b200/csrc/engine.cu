@@ -72,6 +72,7 @@ struct lbz_engine {
   double k0_ms = 0.0;                   // dominant kernel: summed launch time, last call
   uint32_t k0_launches = 0;
   uint64_t k0_elements = 0;             // elements sorted per launch (sum over blocks), last batch
+  double k0_elem_launches = 0.0;        // sum over the call's batches of elements x timed launches
   // device
   uint8_t *d_in = nullptr;     // max_chunks * mbs raw bytes
   uint32_t *d_chunk_len = nullptr;
@@ -285,8 +286,8 @@ extern "C" void lbz_engine_stage_ms(const lbz_engine *e, double *out7) {
 }
 // dominant kernel: summed launch time, launches, average elements per launch
 extern "C" void lbz_engine_k0_stats(const lbz_engine *e, double *sum_ms, uint32_t *launches, uint64_t *elements) {
-  double ms = e->k0_ms; uint64_t nl = e->k0_launches; double el = (double)e->k0_elements * e->k0_launches;
-  if (e->sib) { ms += e->sib->k0_ms; nl += e->sib->k0_launches; el += (double)e->sib->k0_elements * e->sib->k0_launches; }
+  double ms = e->k0_ms; uint64_t nl = e->k0_launches; double el = e->k0_elem_launches;
+  if (e->sib) { ms += e->sib->k0_ms; nl += e->sib->k0_launches; el += e->sib->k0_elem_launches; }
   *sum_ms = ms; *launches = (uint32_t)nl; *elements = nl ? (uint64_t)(el / (double)nl) : 0;
 }
 extern "C" size_t lbz_engine_device_bytes(const lbz_engine *e) { return e->dev_bytes + (e->sib ? e->sib->dev_bytes : 0); }
@@ -373,12 +374,14 @@ static int run_pipeline(lbz_engine *e, const uint8_t *d_in, uint8_t *d_packed, s
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->tm.stage[i], e->tm.stage[i + 1]) == cudaSuccess) e->stage_ms[i] += ms;
   }
-  for (int i = 0; i < (int)e->bwt_k && i < LBZ_NK0; i++) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, e->tm.k0[2 * i], e->tm.k0[2 * i + 1]) == cudaSuccess) { e->k0_ms += ms; e->k0_launches++; }
-  }
   e->k0_elements = 0;
   for (uint32_t b = 0; b < nb; b++) e->k0_elements += e->h_meta[b].n;
+  for (int i = 0; i < (int)e->bwt_k && i < LBZ_NK0; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->tm.k0[2 * i], e->tm.k0[2 * i + 1]) == cudaSuccess) {
+      e->k0_ms += ms; e->k0_launches++; e->k0_elem_launches += (double)e->k0_elements;
+    }
+  }
   size_t sum = 0;
   for (uint32_t b = 0; b < nb; b++) {
     const LbzBlockMeta &m = e->h_meta[b];
@@ -427,7 +430,7 @@ static size_t fill_recs(lbz_engine *e, uint64_t raw_base, lbz_block_rec *recs, s
 
 static void reset_call_stats(lbz_engine *e) {
   for (int i = 0; i < LBZ_NSTAGE; i++) e->stage_ms[i] = 0.0;
-  e->k0_ms = 0.0; e->k0_launches = 0;
+  e->k0_ms = 0.0; e->k0_launches = 0; e->k0_elem_launches = 0.0;
 }
 
 // One lane: chunk table, (H2D,) all stages.  Leaves the packed blocks in
@@ -578,7 +581,8 @@ static int compress_any(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out
   if (!e) return -1;
   ENG_CHECK(cudaSetDevice(e->device));
   const size_t batch_bytes = (size_t)e->total_chunks * e->g.mbs;
-  if (on_device && n > batch_bytes) { fprintf(stderr, "lbzip2_b200: device input exceeds one batch\n"); return -1; }
+  // inputs larger than the engine are cut into consecutive batches of total_chunks chunks
+  // (host and device legs alike: `in + pos` / `out + o` are plain pointer arithmetic)
   size_t o = 0, nrec = 0;
   reset_call_stats(e);
   if (e->sib) reset_call_stats(e->sib);
