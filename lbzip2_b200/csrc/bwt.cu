@@ -48,6 +48,10 @@ struct BwtBuffers {
   uint8_t *bwt;           // output last column
   uint32_t K;             // bytes covered by the initial radix sort (5..8)
   uint32_t *hbits, *cbits; // group-head / size-class bitmaps (1 bit per order position), alias of `head`
+  uint32_t *tickets;       // [1024] work-item counters of the persistent pass kernel, indexed by status epoch (zero before use)
+  uint32_t *wl;            // work lists of the persistent pass kernel: text passes at [0], list passes at [wl_list_off]
+  uint32_t *wl_count;      // [2] number of work items: text passes, list passes
+  uint32_t wl_list_off;
 };
 
 __device__ __forceinline__ uint32_t wrap_add(uint32_t v, uint32_t d, uint32_t n) {
@@ -397,13 +401,16 @@ __global__ void __launch_bounds__(512, MINB)
 k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
              const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
              uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
-             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride) {
+             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride,
+             uint32_t xpose) {
   extern __shared__ __align__(16) unsigned char radix_smem_raw[];
   TextSmem2 &S = *reinterpret_cast<TextSmem2 *>(radix_smem_raw);
   constexpr int THREADS = 512, ITEMS = 8;
   constexpr uint32_t RTILE = THREADS * ITEMS;
   const uint32_t rtiles = g.S1 / RTILE;
-  const uint32_t b = blockIdx.y, tile = blockIdx.x;
+  // xpose: grid = (blocks, tiles) -- CTAs are dispatched x-fastest, so consecutive CTAs then work
+  // on different blocks and a tile's predecessor has usually published its inclusive prefix
+  const uint32_t b = xpose ? blockIdx.x : blockIdx.y, tile = xpose ? blockIdx.y : blockIdx.x;
   const uint32_t n = meta[b].n;
   const uint32_t cnt = LIST ? meta[b].ul : n;
   const uint32_t tbase = tile * RTILE;
@@ -557,27 +564,413 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Third implementation of the pass: a PERSISTENT kernel fed by TMA.
+//
+//   * k_worklist lists the non-empty tiles of the batch in tile-major order (tile 0 of every
+//     block, then tile 1, ...).  The pass kernel runs 2 CTAs per SM; every CTA loops over work
+//     items that it draws from an atomic ticket counter.  Consecutive tickets belong to
+//     different blocks, so the look-back of a tile finds the inclusive prefix of its
+//     predecessor (drawn a whole row of tickets earlier) after one or two steps instead of
+//     walking over hundreds of in-flight aggregates; and a tile only ever waits for tiles with
+//     smaller tickets, each of which is held by a CTA that is working on it or on an even
+//     smaller one -- no reliance on the hardware's CTA dispatch order.
+//   * one elected thread moves the next tile's (key, index) pairs HBM -> shared memory with a
+//     1-D bulk copy (cp.async.bulk ... mbarrier::complete_tx::bytes) into the landing buffer
+//     the CTA is not working on, so the load of item i+1 is in flight while item i is ranked,
+//     staged and written out; it fetches ticket, work-list entry and block record for item
+//     i+2 in the shadow of the other phases.
+//   * warp-private counters and ranks as before, then one column-sum step, after which EVERY
+//     warp scans the 256 digit totals for itself (8 digits per lane) and folds the result
+//     into its own counter row: three barriers per tile instead of six; the landing buffer
+//     doubles as the staging buffer of the digit-ordered tile.
+// Status words, digit bases and the write-out are those of k_text_pass2.
+#define WL_MAXBLOCKS 32768u
+#define WL_INVALID 0xFFFFFFFFu
+template <int LIST>
+__global__ void __launch_bounds__(1024)
+k_worklist(const LbzBlockMeta *__restrict__ meta, uint32_t nb, uint32_t rows, uint32_t *__restrict__ wl,
+           uint32_t *__restrict__ wl_count) {
+  __shared__ uint8_t nt[WL_MAXBLOCKS];
+  __shared__ uint32_t rowstart[256];
+  __shared__ uint32_t ws[40];
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t b = tid; b < nb; b += 1024) {
+    const uint32_t cnt = LIST ? meta[b].ul : meta[b].n;
+    nt[b] = (uint8_t)min((cnt + 4095u) / 4096u, rows);
+  }
+  __syncthreads();
+  uint32_t c = 0;
+  if (tid < rows) for (uint32_t b = 0; b < nb; b++) c += (nt[b] > tid);
+  uint32_t total;
+  const uint32_t start = cta_excl_sum(c, ws, &total);
+  if (tid < 256) rowstart[tid] = start;
+  __syncthreads();
+  if (tid < rows && c) {
+    uint32_t o = rowstart[tid];
+    for (uint32_t b = 0; b < nb; b++) if (nt[b] > tid) wl[o++] = (b << 8) | tid;
+  }
+  if (tid == 0) *wl_count = total;
+}
+
+struct PassDesc { uint32_t b, tile, cnt, off, n, valid, shift1, pad; };
+struct PassSmem {
+  uint2 buf[2][4096 + 2];
+  uint32_t wcnt[16][256];
+  uint32_t hsum[2][256];
+  uint32_t dstart[256];
+  uint32_t delta[256];
+  PassDesc desc[2];
+  unsigned long long full[2];
+  // state of the elected thread (kept out of the register file: the other 511 threads would carry it too)
+  PassDesc nxt;
+  uint32_t qk, qend, total, pad;
+};
+#define P3_THREADS 512
+#define P3_ELECTED 480u          // warp 15, lane 0: idle while the first eight warps look back
+#define P3_GRAB 2u
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// Returns false if the phase did not complete within ~2^24 polls (never expected; the caller
+// raises the error flag and leaves instead of hanging the device).
+__device__ __forceinline__ bool mbar_wait(void *bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok, polls = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok && ++polls < (1u << 24));
+  return ok != 0u;
+}
+__device__ __forceinline__ void mbar_arrive(void *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Elected thread: publish the descriptor of the next item in slot s and start its load.
+template <int MODE>
+__device__ __forceinline__ void pass3_issue(PassSmem &S, uint32_t s, const PassDesc &d0, const uint2 *__restrict__ src) {
+  PassDesc d = d0;
+  d.shift1 = 0u; d.pad = 0u;
+  if (d.valid && MODE == 0) {
+    // 16-byte aligned source: start one pair early when the tile starts at an odd element
+    const uint32_t e0 = d.off + d.tile * 4096u;
+    const uint32_t tile_cnt = min(4096u, d.cnt - d.tile * 4096u);
+    d.shift1 = e0 & 1u;
+    const uint32_t bytes = ((d.shift1 + tile_cnt + 1u) & ~1u) * 8u;
+    S.desc[s] = d;
+    mbar_arrive_expect_tx(&S.full[s], bytes);
+    bulk_g2s(&S.buf[s][0], src + (e0 - d.shift1), bytes, &S.full[s]);
+  } else {
+    S.desc[s] = d;
+    mbar_arrive(&S.full[s]);
+  }
+}
+template <int LIST>
+__device__ __forceinline__ PassDesc pass3_describe(const LbzGeom &g, const LbzBlockMeta *__restrict__ meta, uint32_t we) {
+  PassDesc d;
+  d.valid = 0u; d.b = 0u; d.tile = 0u; d.cnt = 0u; d.off = 0u; d.n = 0u; d.shift1 = 0u; d.pad = 0u;
+  if (we != WL_INVALID) {
+    d.b = we >> 8; d.tile = we & 255u; d.valid = 1u;
+    d.n = meta[d.b].n;
+    d.cnt = LIST ? meta[d.b].ul : d.n;
+    d.off = lbz_slot_off(g, d.b) + (LIST ? meta[d.b].lbase : 0u);
+  }
+  return d;
+}
+
+template <int MODE, int LAST, int LIST>
+__global__ void __launch_bounds__(P3_THREADS, 2)
+k_text_pass3(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+             const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
+             uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
+             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride,
+             uint32_t *__restrict__ ticket, const uint32_t *__restrict__ wl, const uint32_t *__restrict__ wl_count) {
+  extern __shared__ __align__(128) unsigned char pass3_smem_raw[];
+  PassSmem &S = *reinterpret_cast<PassSmem *>(pass3_smem_raw);
+  constexpr int ITEMS = 8;
+  constexpr uint32_t RTILE = 4096u;
+  const uint32_t rtiles = g.S1 / RTILE;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const bool elected = tid == P3_ELECTED;
+
+  if (tid == 0) {
+    mbar_init(&S.full[0], 1u); mbar_init(&S.full[1], 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // elected thread: ticket range [qk, qend), total number of work items, descriptor of the item after the next
+  if (elected) {
+    const uint32_t total = *wl_count;
+    uint32_t qk = atomicAdd(ticket, P3_GRAB);
+    const uint32_t qend = qk + P3_GRAB;
+    uint32_t we = (qk < total) ? wl[qk] : WL_INVALID; qk++;
+    pass3_issue<MODE>(S, 0u, pass3_describe<LIST>(g, meta, we), src);          // item 0 -> buffer 0
+    we = (qk < total) ? wl[qk] : WL_INVALID; qk++;
+    S.nxt = pass3_describe<LIST>(g, meta, we);                                   // item 1, issued after barrier A of item 0
+    S.qk = qk; S.qend = qend; S.total = total;
+  }
+
+  const uint32_t lt = lanemask_lt();
+  uint32_t *wrow = &S.wcnt[warp][0];
+  const uint32_t ep = (epoch << 20) & TS_EPOCH_MASK;
+  for (uint32_t it = 0;; it++) {
+    const uint32_t s = it & 1u;
+    {   // clear this warp's counter row while the tile lands
+      uint4 *z = reinterpret_cast<uint4 *>(wrow);
+      z[lane] = make_uint4(0u, 0u, 0u, 0u);
+      z[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // elected thread: the loads that describe item it+2 are issued early and consumed late (their
+    // results stay in registers in between), so that this warp does not hold up the barriers
+    uint32_t tk = 0, we = WL_INVALID, m_n = 0, m_cnt = 0, m_lbase = 0;
+    const bool grab = elected && S.qk == S.qend;
+    if (grab) tk = atomicAdd(ticket, P3_GRAB);               // consumed after barrier A
+    if (!mbar_wait(&S.full[s], (it >> 1) & 1u)) { *err = 2u; break; }
+    if (!S.desc[s].valid) break;
+    const uint32_t b = S.desc[s].b, tile = S.desc[s].tile, n = S.desc[s].n, off = S.desc[s].off;
+    const uint32_t tbase = tile * RTILE;
+    const uint32_t tile_cnt = min(RTILE, S.desc[s].cnt - tbase);
+    const uint32_t wbase = warp * (32 * ITEMS) + lane;
+    const uint32_t lim = tile_cnt > wbase ? tile_cnt - wbase : 0u;
+    uint2 *stage = &S.buf[s][0];
+
+    uint32_t val[ITEMS], key[ITEMS];
+    if (MODE == 0) {
+      const uint2 *sp = stage + S.desc[s].shift1 + wbase;
+#pragma unroll
+      for (int q = 0; q < ITEMS; q++) {
+        const uint2 pr = (q * 32u < lim) ? sp[q * 32] : make_uint2(0u, 0u);
+        key[q] = pr.x; val[q] = pr.y;
+      }
+    } else if (MODE == 1) {
+      const uint2 *sp = src + off + tbase + wbase;
+#pragma unroll
+      for (int q = 0; q < ITEMS; q++) val[q] = (q * 32u < lim) ? sp[q * 32].y : 0u;
+#pragma unroll
+      for (int q = 0; q < ITEMS; q++) key[q] = (q * 32u < lim) ? text_key4(T + off, val[q], n) : 0u;
+    } else {
+#pragma unroll
+      for (int q = 0; q < ITEMS; q++) {
+        val[q] = tbase + wbase + q * 32;
+        key[q] = (q * 32u < lim) ? text_key4(T + off, wrap_add(val[q], koff, n), n) : 0u;
+      }
+    }
+    __syncwarp();                                            // counter row cleared by all lanes
+
+    uint32_t rkp[ITEMS / 4];
+#pragma unroll
+    for (int q = 0; q < ITEMS / 4; q++) rkp[q] = 0;
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+      const bool valid = q * 32u < lim;
+      const uint32_t digit = valid ? ((key[q] >> shift) & 0xFFu) : 0x100u;
+      const uint32_t mask = __match_any_sync(0xffffffffu, digit);
+      uint32_t base = 0;
+      if (valid) base = wrow[digit];
+      __syncwarp();
+      if (valid && (mask & lt) == 0) wrow[digit] = base + __popc(mask);
+      __syncwarp();
+      rkp[q >> 2] |= (base + __popc(mask & lt)) << (8 * (q & 3));
+    }
+    __syncthreads();                                         // A: all rows counted, all items in registers,
+                                                             //    every thread is done with the other buffer
+    if (elected) {
+      pass3_issue<MODE>(S, s ^ 1u, S.nxt, src);              // item it+1 lands while this one is processed
+      if (grab) { S.qk = tk; S.qend = tk + P3_GRAB; }
+      const uint32_t k = S.qk;
+      if (k < S.total) we = wl[k];                           // item it+2: work-list entry, consumed after barrier B
+      S.qk = k + 1u;
+    }
+    const uint32_t d = tid & 255u, half = tid >> 8;
+    {
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) { const uint32_t c = S.wcnt[half * 8 + w][d]; S.wcnt[half * 8 + w][d] = run; run += c; }
+      S.hsum[half][d] = run;
+    }
+    __syncthreads();                                         // B: column sums ready
+    if (elected && we != WL_INVALID) {                       // block record of item it+2, consumed after the staging step
+      const LbzBlockMeta *mb = meta + (we >> 8);
+      m_n = mb->n;
+      m_cnt = LIST ? mb->ul : m_n;
+      m_lbase = LIST ? mb->lbase : 0u;
+    }
+
+    uint32_t *mine = tstat + ((size_t)b * rtiles + tile) * 256 + d;
+    uint32_t total_d = 0;
+    if (half == 0) {
+      total_d = S.hsum[0][d] + S.hsum[1][d];
+      st_volatile_u32(mine, (tile == 0 ? TS_FLAG_PREFIX : TS_FLAG_AGG) | ep | total_d);
+    }
+    {   // every warp: exclusive scan of the 256 digit totals, 8 digits per lane, folded into its own row
+      uint32_t run;
+      {
+        const uint4 a0 = *reinterpret_cast<const uint4 *>(&S.hsum[0][lane * 8]);
+        const uint4 a1 = *reinterpret_cast<const uint4 *>(&S.hsum[0][lane * 8 + 4]);
+        const uint4 b0 = *reinterpret_cast<const uint4 *>(&S.hsum[1][lane * 8]);
+        const uint4 b1 = *reinterpret_cast<const uint4 *>(&S.hsum[1][lane * 8 + 4]);
+        run = (a0.x + a0.y + a0.z + a0.w) + (a1.x + a1.y + a1.z + a1.w) + (b0.x + b0.y + b0.z + b0.w) + (b1.x + b1.y + b1.z + b1.w);
+      }
+      uint32_t e = warp_incl_sum(run) - run;                             // start of digit lane*8 inside the tile
+      const bool hi = warp >= 8;                                         // second half: after the first half's items
+      const bool pub = (lane >> 2) == warp;                              // warps 0..7: the 32 digits their threads look back for
+#pragma unroll
+      for (int hq = 0; hq < 2; hq++) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(&S.hsum[0][lane * 8 + 4 * hq]);
+        const uint4 c = *reinterpret_cast<const uint4 *>(&S.hsum[1][lane * 8 + 4 * hq]);
+        const uint32_t e0 = e, e1 = e0 + a.x + c.x, e2 = e1 + a.y + c.y, e3 = e2 + a.z + c.z;
+        e = e3 + a.w + c.w;
+        if (pub) *reinterpret_cast<uint4 *>(&S.dstart[lane * 8 + 4 * hq]) = make_uint4(e0, e1, e2, e3);
+        uint4 w = *reinterpret_cast<const uint4 *>(&wrow[lane * 8 + 4 * hq]);
+        w.x += e0 + (hi ? a.x : 0u); w.y += e1 + (hi ? a.y : 0u); w.z += e2 + (hi ? a.z : 0u); w.w += e3 + (hi ? a.w : 0u);
+        *reinterpret_cast<uint4 *>(&wrow[lane * 8 + 4 * hq]) = w;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+      if (q * 32u < lim) {
+        const uint32_t digit = (key[q] >> shift) & 0xFFu;
+        const uint32_t slot = wrow[digit] + ((rkp[q >> 2] >> (8 * (q & 3))) & 0xFFu);
+        stage[slot] = make_uint2(key[q], val[q]);
+      }
+    }
+    if (elected) {
+      PassDesc nd;
+      nd.valid = we != WL_INVALID; nd.b = we >> 8; nd.tile = we & 255u; nd.cnt = m_cnt; nd.n = m_n;
+      nd.off = lbz_slot_off(g, we >> 8) + m_lbase; nd.shift1 = 0u; nd.pad = 0u;
+      S.nxt = nd;
+    }
+    if (half == 0) {
+      uint32_t excl = 0;
+      if (tile != 0) {
+        const uint32_t *row0 = mine - (size_t)tile * 256;
+        int t = (int)tile - 1;
+        uint32_t spins = 0;
+        bool done = false;
+        while (!done) {
+          uint32_t sw[TS_WINDOW];
+#pragma unroll
+          for (int q = 0; q < TS_WINDOW; q++)
+            sw[q] = (t - q >= 0) ? ld_volatile_u32(row0 + (size_t)(t - q) * 256) : (TS_FLAG_PREFIX | ep);
+          int used = 0;
+#pragma unroll
+          for (int q = 0; q < TS_WINDOW; q++) {
+            if (!done && used == q) {
+              const uint32_t w = sw[q];
+              if ((w & TS_EPOCH_MASK) == ep && (w >> 30) != 0u) {
+                excl += w & TS_VALUE_MASK;
+                used = q + 1;
+                if (w & TS_FLAG_PREFIX) done = true;
+              }
+            }
+          }
+          t -= used;
+          if (!done && used < TS_WINDOW) {
+            if (++spins > TS_SPIN_LIMIT) { *err = 1u; break; }
+            __nanosleep(20);
+          }
+        }
+        st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total_d) & TS_VALUE_MASK));
+      }
+      S.delta[d] = gbase[(size_t)b * gstride + d] + excl - S.dstart[d];
+    }
+    __syncthreads();                                         // C: tile staged in digit order, offsets known
+    if (LAST) {
+      uint32_t *o = sa_out + off;
+#pragma unroll
+      for (int q = 0; q < ITEMS; q++) {
+        const uint32_t i = tid + q * P3_THREADS;
+        if (i < tile_cnt) { const uint2 pr = stage[i]; o[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr.y; }
+      }
+    } else {
+      uint2 *o = dst + off;
+#pragma unroll
+      for (int q = 0; q < ITEMS; q++) {
+        const uint32_t i = tid + q * P3_THREADS;
+        if (i < tile_cnt) { const uint2 pr = stage[i]; o[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr; }
+      }
+    }
+    // this thread's generic-proxy accesses to the buffer are ordered before the bulk copy that
+    // refills it (issued by the elected thread after the next barrier A)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+}
+
+// Pass variants (LBZ_TP_VER): 3 = persistent TMA kernel (k_text_pass3), 2 = one CTA per tile
+// (k_text_pass2; LBZ_TP_XPOSE=1 dispatches it block-fastest), 1 = first implementation.
+static int tp_version() {
+  static int v = -1;
+  if (v < 0) { const char *ev = getenv("LBZ_TP_VER"); v = ev ? atoi(ev) : 3; if (v < 1 || v > 3) v = 3; }
+  return v;
+}
+static uint32_t tp_xpose() {
+  static int v = -1;
+  if (v < 0) { const char *ev = getenv("LBZ_TP_XPOSE"); v = ev ? (atoi(ev) != 0) : 1; }
+  return (uint32_t)v;
+}
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int MODE, int LAST, int LIST>
+static int launch_pass3(uint32_t tiles, uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
+                        const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase, uint32_t gstride,
+                        uint32_t shift, uint32_t epoch, uint32_t *err, uint32_t koff, const BwtBuffers &B) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass3<MODE, LAST, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)));
+    attr_set = true;
+  }
+  const uint32_t total = tiles * nb;                       // upper bound of the work list
+  if (total == 0) return 0;
+  const uint32_t grid = min(total, 2u * (uint32_t)sm_count());
+  k_text_pass3<MODE, LAST, LIST><<<grid, P3_THREADS, sizeof(PassSmem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch,
+                                                                            err, koff, gstride, B.tickets + (epoch & 1023u),
+                                                                            B.wl + (LIST ? B.wl_list_off : 0u), B.wl_count + LIST);
+  return 0;
+}
+
 template <int MODE, int LAST, int MINB>
 static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
                             const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
                             uint32_t shift, uint32_t epoch, uint32_t *err, uint32_t koff) {
-  static int v1 = -1;
-  if (v1 < 0) { const char *ev = getenv("LBZ_TP_V1"); v1 = (ev && atoi(ev) != 0) ? 1 : 0; }
-  if (v1) {
+  if (tp_version() == 1) {
     LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem)));
     k_text_pass<MODE, LAST, MINB><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
                                                                                           shift, epoch, err, koff);
     return 0;
   }
   LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
-  k_text_pass2<MODE, LAST, MINB><<<dim3(g.S1 / 4096u, nb), 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
-                                                                                          shift, epoch, err, koff, 256u);
+  const uint32_t xp = tp_xpose();
+  const dim3 grid = xp ? dim3(nb, g.S1 / 4096u) : dim3(g.S1 / 4096u, nb);
+  k_text_pass2<MODE, LAST, MINB><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
+                                                                        shift, epoch, err, koff, 256u, xp);
   return 0;
 }
 template <int MODE, int LAST>
 static int launch_text_pass(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
                             const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
-                            uint32_t shift, uint32_t epoch, uint32_t *err, uint32_t koff) {
+                            uint32_t shift, uint32_t epoch, uint32_t *err, uint32_t koff, const BwtBuffers &B) {
+  if (tp_version() == 3)
+    return launch_pass3<MODE, LAST, 0>(g.S1 / 4096u, nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, 256u, shift, epoch, err, koff, B);
   static int minb = 0;
   if (!minb) { const char *ev = getenv("LBZ_TP_MINB"); minb = (ev && atoi(ev) == 2) ? 2 : 3; }
   if (minb == 3) return launch_text_pass_b<MODE, LAST, 3>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff);
@@ -587,10 +980,15 @@ static int launch_text_pass(uint32_t nb, cudaStream_t st, const LbzGeom &g, cons
 // One pass over the 32-bit-key pairs of every block's list L.
 static int launch_list_pass(uint32_t max_count, uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta,
                             const uint2 *src, uint2 *dst, uint32_t *tstat, const uint32_t *gbase, uint32_t gstride,
-                            uint32_t shift, uint32_t epoch, uint32_t *err) {
+                            uint32_t shift, uint32_t epoch, uint32_t *err, const BwtBuffers &B) {
+  const uint32_t tiles = (max_count + 4095u) / 4096u;
+  if (tp_version() == 3)
+    return launch_pass3<0, 0, 1>(tiles, nb, st, g, meta, nullptr, src, dst, nullptr, tstat, gbase, gstride, shift, epoch, err, 0u, B);
   LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<0, 0, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
-  k_text_pass2<0, 0, 3, 1><<<dim3((max_count + 4095u) / 4096u, nb), 512, sizeof(TextSmem2), st>>>(
-      g, meta, nullptr, src, dst, nullptr, tstat, gbase, shift, epoch, err, 0u, gstride);
+  const uint32_t xp = tp_xpose();
+  const dim3 grid = xp ? dim3(nb, tiles) : dim3(tiles, nb);
+  k_text_pass2<0, 0, 3, 1><<<grid, 512, sizeof(TextSmem2), st>>>(
+      g, meta, nullptr, src, dst, nullptr, tstat, gbase, shift, epoch, err, 0u, gstride, xp);
   return 0;
 }
 
@@ -1614,6 +2012,7 @@ static uint32_t next_epoch(const BwtBuffers &B, uint32_t nb, const LbzGeom &g, c
   uint32_t e = *B.epoch + 1;
   if (e >= 1024) {
     cudaMemsetAsync(B.tstat, 0, (size_t)nb * (g.S1 / 2048u) * 256 * sizeof(uint32_t), st);
+    cudaMemsetAsync(B.tickets, 0, 1024 * sizeof(uint32_t), st);
     e = 1;
   }
   *B.epoch = e;
@@ -1639,6 +2038,7 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
   if (cfg < 0) { const char *ev = getenv("LBZ_RADIX_CFG"); cfg = ev ? (atoi(ev) != 0) : 1; }
 
   k_text_bases<<<nb, 1024, 0, st>>>(g, d_meta, B.T, B.gbase);
+  if (tp_version() == 3) { k_worklist<0><<<1, 1024, 0, st>>>(d_meta, nb, g.tiles1, B.wl, B.wl_count); nl++; }
   // LSD over text bytes 7..0 of every rotation: bytes 4..7 travel as a 32-bit key
   // next to the index for the first four passes, bytes 0..3 are fetched once by
   // the fifth pass; the first pass builds its pairs from the text, the last one
@@ -1652,11 +2052,11 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     const bool last = (p == K - 1u);
     int rc;
     uint32_t *const er = B.counters + 3;
-    if (p == 0) rc = launch_text_pass<2, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
-    else if (p == 4 && last) rc = launch_text_pass<1, 1>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
-    else if (p == 4) rc = launch_text_pass<1, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
-    else if (last) rc = launch_text_pass<0, 1>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
-    else rc = launch_text_pass<0, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff);
+    if (p == 0) rc = launch_text_pass<2, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff, B);
+    else if (p == 4 && last) rc = launch_text_pass<1, 1>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff, B);
+    else if (p == 4) rc = launch_text_pass<1, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff, B);
+    else if (last) rc = launch_text_pass<0, 1>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff, B);
+    else rc = launch_text_pass<0, 0>(nb, st, g, d_meta, B.T, pa, pb, B.sa, B.tstat, B.gbase, shift, ep, er, koff, B);
     if (rc) return -1;
     if (tm && tm->enabled && p < LBZ_NK0) cudaEventRecord(tm->k0[2 * p + 1], st);
     { uint2 *t = pa; pa = pb; pb = t; }
@@ -1692,7 +2092,7 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     LBZ_CUDA_CHECK(cudaMemcpyAsync(h_counters, B.counters, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     LBZ_CUDA_CHECK(cudaStreamSynchronize(st));
     if (h_counters[3]) {
-      fprintf(stderr, "lbzip2_b200: chained scan timed out (tile scheduling assumption violated)\n");
+      fprintf(stderr, "lbzip2_b200: sort pass failed (%s)\n", h_counters[3] == 2u ? "bulk copy never landed" : "chained scan timed out");
       return -1;
     }
     const uint32_t maxU = h_counters[0];
@@ -1713,11 +2113,15 @@ extern "C" int lbz_run_bwt(const LbzGeom *gp, LbzBlockMeta *d_meta, BwtBuffers B
     k_round_keys<<<grid_u, 256, 0, st>>>(g, d_meta, vA, gA, B.rank, kA, B.khist, h, 1u, B.hints, pair ? 1 : 0);
     k_key_bases<<<nb, 256, 0, st>>>(d_meta, B.khist, B.gbase + (size_t)nb * 256);
     k_small_sort<<<grid_u, 256, 0, st>>>(g, d_meta, kA, vA, kB, vB);
+    if (pair && tp_version() == 3) {
+      k_worklist<1><<<1, 1024, 0, st>>>(d_meta, nb, min(grid_u.x, g.tiles1), B.wl + B.wl_list_off, B.wl_count + 1);
+      nl++;
+    }
     if (pair) {
       uint2 *pa2 = reinterpret_cast<uint2 *>(kA), *pb2 = reinterpret_cast<uint2 *>(kB);
       for (uint32_t p = 0; p < 4; p++) {
         if (launch_list_pass(maxU, nb, st, g, d_meta, pa2, pb2, B.tstat, gb1 + p * 256, 5u * 256u, 8u * p,
-                             next_epoch(B, nb, g, st), B.counters + 3)) return -1;
+                             next_epoch(B, nb, g, st), B.counters + 3, B)) return -1;
         uint2 *t = pa2; pa2 = pb2; pb2 = t;
       }
     } else {

@@ -37,6 +37,9 @@ struct BwtBuffers {           // must match bwt.cu
   uint8_t *bwt;
   uint32_t K;
   uint32_t *hbits, *cbits;
+  uint32_t *tickets;
+  uint32_t *wl, *wl_count;
+  uint32_t wl_list_off;
 };
 
 extern "C" {
@@ -82,6 +85,9 @@ struct lbz_engine {
   uint64_t *d_key = nullptr, *d_key2 = nullptr;
   uint32_t *d_val = nullptr, *d_val2 = nullptr, *d_pos = nullptr, *d_pos2 = nullptr, *d_gs = nullptr, *d_gs2 = nullptr;
   uint32_t *d_tstat = nullptr, *d_gbase = nullptr, *d_khist = nullptr, *d_counters = nullptr;
+  uint32_t *d_tickets = nullptr;       // work-item counters of the persistent pass kernel (bwt.cu)
+  uint32_t *d_wl = nullptr;            // its work lists: [0, wl_half) text passes, [wl_half, 2 wl_half) list passes, then 2 counts
+  uint32_t wl_half = 0;
   uint64_t *d_agg = nullptr;
   uint32_t epoch = 0;
   uint16_t *d_mtfv = nullptr;
@@ -211,6 +217,9 @@ static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   rc |= dev_alloc(e, &e->d_khist, NB * 256 * 5);
   rc |= dev_alloc(e, &e->d_agg, 2 * NB * g.tiles1 * 2);   // TileAgg (16 B) for two lists
   rc |= dev_alloc(e, &e->d_counters, 8);
+  rc |= dev_alloc(e, &e->d_tickets, 1024);
+  e->wl_half = (uint32_t)(E / LBZ_TILE) + 64u;
+  rc |= dev_alloc(e, &e->d_wl, 2 * (size_t)e->wl_half + 8);
   rc |= dev_alloc(e, &e->d_mtfv, E);
   rc |= dev_alloc(e, &e->d_freq, NB * 260);
   rc |= dev_alloc(e, &e->d_parttab, NB * lbz_mtf_parts() * 256);
@@ -233,6 +242,7 @@ static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   cudaMemsetAsync(e->d_meta, 0, NB * sizeof(LbzBlockMeta), e->st);
   cudaMemsetAsync(e->d_tstat, 0, NB * (g.S1 / 2048u) * 256 * sizeof(uint32_t), e->st);
   cudaMemsetAsync(e->d_counters, 0, 8 * sizeof(uint32_t), e->st);
+  cudaMemsetAsync(e->d_tickets, 0, 1024 * sizeof(uint32_t), e->st);
   cudaStreamSynchronize(e->st);
   return e;
 }
@@ -307,6 +317,8 @@ static BwtBuffers bwt_buffers(lbz_engine *e) {
   B.counters = e->d_counters; B.epoch = &e->epoch; B.bwt = e->d_bwt;
   B.hbits = reinterpret_cast<uint32_t *>(e->d_head);
   B.cbits = B.hbits + ((size_t)e->max_chunks * e->g.stride) / 32 + 64;   // the byte array holds both bitmaps with room to spare
+  B.tickets = e->d_tickets;
+  B.wl = e->d_wl; B.wl_list_off = e->wl_half; B.wl_count = e->d_wl + 2 * (size_t)e->wl_half;
   B.K = e->bwt_k; B.hints = e->hints; B.on_sorted = e->on_sorted; B.on_sorted_arg = e->on_sorted_arg;
   return B;
 }
