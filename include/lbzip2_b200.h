@@ -60,8 +60,10 @@ int collect(struct encoder_state *e, const uint8_t *buf, size_t *buf_sz);
    and hands back the un-inverted block CRC. */
 size_t encode(struct encoder_state *e, uint32_t *crc);
 /* src/encode.h:33  (src/encode.c:1152-1281).  Writes the block into buf
-   (>= (size+3)/4*4 bytes).  Releases the device context: it is the last call
-   the scheduler makes before free(e) (src/compress.c:220-223). */
+   (>= (size+3)/4*4 bytes) and returns buf; with buf == NULL the block is left in
+   the state's own memory and a pointer to it is returned (src/encode.c:1177-1182).
+   Releases the device context: it is the last call the scheduler makes before
+   free(e) (src/compress.c:220-223). */
 void *transmit(struct encoder_state *e, void *buf);
 /* src/encode.h:34  (src/encode.c:1005-1137).  In the reference this is a step inside
    encode() (its only caller, src/encode.c:469) that builds the prefix codes of the block
@@ -74,6 +76,15 @@ unsigned generate_prefix_code(struct encoder_state *s);
 int32_t divbwt(uint8_t *T, int32_t *SA, int32_t *bucket, int32_t n);
 
 #define combine_crc(cc, c) (((cc) << 1) ^ ((cc) >> 31) ^ (c) ^ -1)   /* src/encode.h:38 */
+
+/* src/decode.h:70  (src/crctab.c:6).  CRC-32/BZIP2 table, poly 0x04C11DB7, MSB first. */
+extern uint32_t crc_table[256];
+
+/* The encode side of the reference API has no error channel; unrecoverable errors end in
+   the host program's failx() (src/main.h:81-88) when the program defines it -- the library
+   holds a weak reference -- so that the CLI's cleanup of partial output (src/main.c:60-74)
+   runs; a handler installed here takes precedence; with neither, abort(). */
+void lbz_set_fatal_handler(void (*fn)(const char *msg));
 
 /* ------------------------------------------------------------------------
  * 2. Batch API.

@@ -67,6 +67,7 @@ AR_TEXT, AR_BWT, AR_MTFV, AR_FREQ, AR_CODING, AR_OUT, AR_META, AR_SA = range(8)
 EXPORTS = [
     # reference-shaped API (src/encode.h:29-36)
     "encoder_alloc_size", "encoder_init", "collect", "encode", "transmit", "generate_prefix_code", "divbwt",
+    "crc_table", "lbz_set_fatal_handler",
     # batch API
     "lbz_engine_create", "lbz_engine_destroy", "lbz_bound", "lbz_compress_chunks",
     "lbz_compress_chunks_device", "lbz_compress_stream", "lbz_host_alloc", "lbz_host_free",

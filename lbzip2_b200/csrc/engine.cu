@@ -20,6 +20,7 @@
 #include <future>
 #include <chrono>
 #include <deque>
+#include <map>
 
 struct BwtBuffers {           // must match bwt.cu
   const uint8_t *T;
@@ -152,9 +153,12 @@ extern "C" size_t lbz_bound(size_t n) {
   return n + n / 32 + 8192 * (n / 100000 + 2) + 64;
 }
 
-static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
-  if (level < 1 || level > 9 || max_chunks < 1 || max_chunks > 16384) {
-    fprintf(stderr, "lbzip2_b200: bad engine parameters (level %d, max_chunks %d)\n", level, max_chunks);
+// `mbs` = maximal block size = raw chunk size: level * 100000 for the batch API, any value in
+// 1..900000 for the reference-shaped API (src/encode.c:121-122).
+static lbz_engine *engine_create_mbs(int device, uint32_t mbs, int max_chunks) {
+  const int level = (int)((mbs + 99999u) / 100000u);
+  if (mbs < 1 || mbs > 900000 || max_chunks < 1 || max_chunks > 16384) {
+    fprintf(stderr, "lbzip2_b200: bad engine parameters (block size %u, max_chunks %d)\n", mbs, max_chunks);
     return nullptr;
   }
   int ndev = 0;
@@ -175,7 +179,7 @@ static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   e->max_chunks = (uint32_t)max_chunks;
   e->total_chunks = (uint32_t)max_chunks;
   LbzGeom &g = e->g;
-  g.mbs = (uint32_t)level * 100000u;
+  g.mbs = mbs;
   g.S1 = round_up(g.mbs + 64, LBZ_TILE);
   g.S2 = round_up(g.mbs / 4 + 64, LBZ_TILE);
   g.stride = g.S1 + g.S2;
@@ -245,6 +249,14 @@ static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
   cudaMemsetAsync(e->d_tickets, 0, 1024 * sizeof(uint32_t), e->st);
   cudaStreamSynchronize(e->st);
   return e;
+}
+
+static lbz_engine *engine_create_one(int device, int level, int max_chunks) {
+  if (level < 1 || level > 9) {
+    fprintf(stderr, "lbzip2_b200: bad engine parameters (level %d)\n", level);
+    return nullptr;
+  }
+  return engine_create_mbs(device, (uint32_t)level * 100000u, max_chunks);
 }
 
 extern "C" lbz_engine *lbz_engine_create(int device, int level, int max_chunks) {
@@ -715,13 +727,28 @@ struct encoder_state {
   uint8_t *staged;           // pinned staging of the raw bytes of this block (lives after the struct)
 };
 
+extern "C" void failx(int x, const char *fmt, ...) __attribute__((weak));
+static void (*g_fatal)(const char *) = nullptr;
+extern "C" void lbz_set_fatal_handler(void (*fn)(const char *msg)) { g_fatal = fn; }
+
+// CRC-32/BZIP2 table (reference src/crctab.c:6, declared in src/decode.h:70), generated at load
+// time from the polynomial (build-aux/make-crctab.pl:29-33): poly 0x04C11DB7, MSB first.
+extern "C" { uint32_t crc_table[256]; }
+__attribute__((constructor)) static void lbz_init_crc_table() {
+  for (uint32_t i = 0; i < 256; i++) {
+    uint32_t r = i << 24;
+    for (int k = 0; k < 8; k++) r = (r & 0x80000000u) ? (r << 1) ^ 0x04C11DB7u : (r << 1);
+    crc_table[i] = r;
+  }
+}
+
 namespace {
 #define POOL_MAX 256
 struct Pool {
   std::mutex mu;
   std::condition_variable cv;
   lbz_engine *engines[POOL_MAX] = {};   // fixed array: slots are read without the lock by their owner
-  int levels[POOL_MAX] = {};
+  uint32_t sizes[POOL_MAX] = {};        // maximal block size of every context
   bool busy[POOL_MAX] = {};
   int count = 0;
   int max_engines = 0;
@@ -729,12 +756,18 @@ struct Pool {
 };
 Pool &g_pool = *new Pool;     // leaked on purpose (see Batcher)
 
+// The reference API has no error channel on the encode side: unrecoverable errors
+// go through the host program's own failx() (src/main.h:81-88, src/main.c:60-74: it removes the
+// partial output file before exiting) when the program linked against this library defines it,
+// or through a handler installed with lbz_set_fatal_handler(); only then abort().
 [[noreturn]] void die(const char *msg) {
+  if (g_fatal) g_fatal(msg);
+  if (failx) failx(0, "lbzip2_b200: %s", msg);
   fprintf(stderr, "lbzip2_b200: fatal: %s\n", msg);
-  abort();      // the reference API has no error channel on the encode side
+  abort();
 }
 
-int pool_acquire(int level) {
+int pool_acquire(uint32_t mbs) {
   std::unique_lock<std::mutex> lk(g_pool.mu);
   if (g_pool.max_engines == 0) {
     const char *s = getenv("LBZIP2_B200_CONTEXTS");
@@ -746,22 +779,22 @@ int pool_acquire(int level) {
   }
   for (;;) {
     for (int i = 0; i < g_pool.count; i++)
-      if (!g_pool.busy[i] && g_pool.engines[i] && g_pool.levels[i] == level) { g_pool.busy[i] = true; return i; }
+      if (!g_pool.busy[i] && g_pool.engines[i] && g_pool.sizes[i] == mbs) { g_pool.busy[i] = true; return i; }
     int slot = -1;
     lbz_engine *old = nullptr;
     if (g_pool.count < g_pool.max_engines) {
       slot = g_pool.count++;
     } else {
-      for (int i = 0; i < g_pool.count; i++)       // recycle an idle context of another level
+      for (int i = 0; i < g_pool.count; i++)       // recycle an idle context of another block size
         if (!g_pool.busy[i] && g_pool.engines[i]) { slot = i; old = g_pool.engines[i]; break; }
     }
     if (slot >= 0) {
       g_pool.busy[slot] = true;
       g_pool.engines[slot] = nullptr;
-      g_pool.levels[slot] = level;
+      g_pool.sizes[slot] = mbs;
       lk.unlock();
       if (old) lbz_engine_destroy(old);
-      lbz_engine *e = lbz_engine_create(g_pool.device, level, 1);
+      lbz_engine *e = engine_create_mbs(g_pool.device, mbs, 1);
       if (!e) die("cannot create a device context (no usable GPU?)");
       lk.lock();
       g_pool.engines[slot] = e;
@@ -781,26 +814,30 @@ namespace { int batch_limit(); }
 
 #define ENC_MAGIC 0xB2005A42u
 
+// Host bytes behind the handle: the raw bytes of the block until encode(), the packed block
+// afterwards (also the internal buffer of transmit(s, NULL), src/encode.c:1177-1182).  A packed
+// block never exceeds 5/2 n' + 8 KiB (lbz_common.cuh out_cap); raw input never exceeds mbs.
+static size_t enc_staged_cap(unsigned long mbs) { return (size_t)mbs * 5 / 2 + 8192 + 64; }
+
 extern "C" size_t encoder_alloc_size(unsigned long max_block_size) {
   // handle + host staging for the raw bytes of one block.  A block of n' <=
   // mbs RLE1 bytes can cover up to mbs*259/5 raw bytes in theory; the
   // scheduler never offers more than in_granul = mbs bytes per state in the
   // default mode (src/process.c:631, src/compress.c:93-110).  collect()
   // handles longer inputs by stopping at the staging capacity when needed.
-  return sizeof(struct encoder_state) + 64 + (size_t)max_block_size * 2 + 64;
+  return sizeof(struct encoder_state) + 64 + enc_staged_cap(max_block_size) + 64;
 }
 
 extern "C" void encoder_init(struct encoder_state *s, unsigned long max_block_size, unsigned cluster_factor) {
   if (!s || max_block_size == 0 || max_block_size > 900000 || cluster_factor == 0 || cluster_factor > 65535)
     die("encoder_init: bad arguments (src/encode.c:121-123)");
-  if (max_block_size % 100000) die("encoder_init: block size must be a multiple of 100000 in this build");
   memset(s, 0, sizeof(*s));
   s->magic = ENC_MAGIC;
   s->max_block_size = (uint32_t)max_block_size;
   s->cluster_factor = cluster_factor;
   s->pool_slot = -1;
   s->staged = reinterpret_cast<uint8_t *>(s) + ((sizeof(struct encoder_state) + 63) / 64) * 64;
-  s->staged_cap = (uint32_t)max_block_size * 2;
+  s->staged_cap = (uint32_t)enc_staged_cap(max_block_size);
 }
 
 // collect(): the raw bytes offered to this state are staged on the host side
@@ -820,7 +857,7 @@ extern "C" int collect(struct encoder_state *s, const uint8_t *buf, size_t *buf_
   if (avail == 0) return 0;
   const uint32_t mbs = s->max_block_size;
   if (s->raw_len >= mbs) die("collect: one block would need more than max_block_size raw bytes (not supported yet)");
-  if (s->pool_slot < 0) s->pool_slot = pool_acquire((int)(mbs / 100000));
+  if (s->pool_slot < 0) s->pool_slot = pool_acquire(mbs);
   lbz_engine *e = g_pool.engines[s->pool_slot];
   const size_t take = (avail < (size_t)(mbs - s->raw_len)) ? avail : (size_t)(mbs - s->raw_len);
   memcpy(s->staged + s->raw_len, buf, take);
@@ -860,17 +897,17 @@ struct Batcher {
   std::deque<BReq *> q;
   bool running = false;
   int max_batch = -1;
-  lbz_engine *eng[10] = {};
+  std::map<uint32_t, lbz_engine *> eng;      // one batch engine per block size in use
 };
 // Deliberately leaked: the dispatcher thread sleeps on these condition variables
 // for the life of the process, and destroying a condition variable that has a
 // waiter (static destruction at exit) blocks forever in glibc.
 Batcher &g_batch = *new Batcher;
 
-int run_batch(int level, std::vector<BReq *> &batch) {
-  lbz_engine *&e = g_batch.eng[level];
+int run_batch(uint32_t mbs_key, std::vector<BReq *> &batch) {
+  lbz_engine *&e = g_batch.eng[mbs_key];
   if (!e) {
-    e = engine_create_one(g_pool.device, level, g_batch.max_batch);
+    e = engine_create_mbs(g_pool.device, mbs_key, g_batch.max_batch);
     if (!e) return -1;
     e->total_chunks = (uint32_t)g_batch.max_batch;
   }
@@ -910,10 +947,10 @@ void batch_worker() {
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(400);
     while ((int)g_batch.q.size() < g_batch.max_batch &&
            g_batch.cv_req.wait_until(lk, deadline) != std::cv_status::timeout) {}
-    const int level = (int)(g_batch.q.front()->s->max_block_size / 100000);
+    const uint32_t level = g_batch.q.front()->s->max_block_size;       // batches are uniform in block size
     std::vector<BReq *> batch;
     for (auto it = g_batch.q.begin(); it != g_batch.q.end() && (int)batch.size() < g_batch.max_batch;) {
-      if ((int)((*it)->s->max_block_size / 100000) == level) { batch.push_back(*it); it = g_batch.q.erase(it); }
+      if ((*it)->s->max_block_size == level) { batch.push_back(*it); it = g_batch.q.erase(it); }
       else ++it;
     }
     lk.unlock();
@@ -954,7 +991,7 @@ extern "C" size_t encode(struct encoder_state *s, uint32_t *crc) {
     if (crc) *crc = s->crc;
     return s->out_len;
   }
-  if (s->pool_slot < 0) s->pool_slot = pool_acquire((int)(s->max_block_size / 100000));
+  if (s->pool_slot < 0) s->pool_slot = pool_acquire(s->max_block_size);
   lbz_engine *e = g_pool.engines[s->pool_slot];
   // exactly the consumed bytes form this block; run every stage on them
   if (lbz_dbg_load(e, s->staged, s->raw_len)) die("encode: H2D failed");
@@ -981,14 +1018,17 @@ extern "C" unsigned generate_prefix_code(struct encoder_state *s) {
 
 extern "C" void *transmit(struct encoder_state *s, void *buf) {
   if (!s || s->magic != ENC_MAGIC || !s->done) die("transmit: encode() has not run");
-  if (!buf) die("transmit: NULL buffer is not supported by this build");
   const size_t bytes = ((size_t)s->out_len + 3) / 4 * 4;
+  if (bytes > s->staged_cap) die("transmit: internal size error");
+  // no external buffer: the block is handed out in the handle's own buffer (src/encode.c:1177-1182)
   if (s->done == 2) {
-    memcpy(buf, s->staged, s->out_len);
-    memset(static_cast<uint8_t *>(buf) + s->out_len, 0, bytes - s->out_len);
+    memset(s->staged + s->out_len, 0, bytes - s->out_len);
+    if (!buf) return s->staged;
+    memcpy(buf, s->staged, bytes);
     return buf;
   }
   lbz_engine *e = g_pool.engines[s->pool_slot];
+  if (!buf) buf = s->staged;
   if (lbz_dbg_read(e, LBZ_AR_OUT, 0, buf, bytes)) die("transmit: D2H failed");
   pool_release(s->pool_slot);
   s->pool_slot = -1;
@@ -998,7 +1038,7 @@ extern "C" void *transmit(struct encoder_state *s, void *buf) {
 extern "C" int32_t divbwt(uint8_t *T, int32_t *SA, int32_t *bucket, int32_t n) {
   (void)bucket;
   if (n <= 0 || n > 900000) die("divbwt: bad length");
-  const int slot = pool_acquire(9);
+  const int slot = pool_acquire(900000u);
   lbz_engine *e = g_pool.engines[slot];
   // one chunk, one block: inject the text and the block record, run the BWT stage
   e->g.nchunks = 1;

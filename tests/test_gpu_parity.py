@@ -379,6 +379,36 @@ def test_reference_shaped_api():
         assert crcs == [i.block_crc for i in infos]
 
 
+def test_reference_shaped_api_any_block_size_and_internal_buffer():
+    """encoder_init accepts every max_block_size in 1..900000 (src/encode.c:121-122) and
+    transmit(s, NULL) hands the block out in the state's own memory (src/encode.c:1177-1182)."""
+    L = lbzip2_b200.load_library()
+    cases = [(1, b"abca"), (7, b"aaaaaaaaaaaaaaaabcdefgh" * 3), (1000, synth.text(3500, offset=31)),
+             (123457, synth.text(300_000, offset=32) + b"\x00" * 70_000), (899_999, synth.random_bytes(1_000_000, seed=33)),
+             (4099, b"r" * 30_000)]
+    for mbs, raw in cases:
+        pos = 0
+        while pos < len(raw):
+            st = C.create_string_buffer(L.encoder_alloc_size(mbs))
+            L.encoder_init(st, mbs, 8)
+            chunk = raw[pos:pos + mbs]
+            cbuf = C.create_string_buffer(chunk, len(chunk))
+            left = C.c_size_t(len(chunk))
+            L.collect(st, cbuf, C.byref(left))
+            consumed = len(chunk) - left.value
+            crc = C.c_uint32(0)
+            size = L.encode(st, C.byref(crc))
+            ptr = L.transmit(st, None)
+            base = C.addressof(st)
+            assert base <= ptr and ptr + (size + 3) // 4 * 4 <= base + len(st), "internal buffer lies inside the state"
+            got = C.string_at(ptr, size)
+            want = orclib.orc_block_stages(chunk, mbs)
+            assert consumed == want["consumed"], (mbs, pos)
+            assert got == want["bits"].tobytes(), (mbs, pos)
+            assert crc.value == want["crc"], (mbs, pos)
+            pos += consumed
+
+
 def test_divbwt_entry_point():
     L = lbzip2_b200.load_library()
     raw = synth.text(50_000, offset=11)

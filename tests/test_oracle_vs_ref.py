@@ -46,3 +46,12 @@ def test_stages_on_synthetic():
     _compare(synth.fib(100000), 100000)
     _compare(b"a" * 900000, 900000)
     _compare(bytes(range(256)) * 100 + b"zz" * 300, 100000)
+
+
+def test_stages_with_arbitrary_block_sizes():
+    """encoder_init takes any max_block_size in 1..900000 (src/encode.c:121-122), not only
+    level * 100000: pins the oracle for the sizes tests/test_gpu_parity.py drives the GPU with."""
+    for cap, raw in [(1, b"a"), (7, b"aaaaaaa"), (7, b"aaaabcd"), (1000, synth.text(1000, offset=31)),
+                     (4099, b"r" * 4099), (123457, synth.text(123457, offset=32)),
+                     (899_999, synth.random_bytes(899_999, seed=33)), (12345, b"\x00" * 9000 + synth.fib(3345))]:
+        _compare(raw, cap)
