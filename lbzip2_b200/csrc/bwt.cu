@@ -909,11 +909,245 @@ k_text_pass3(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   }
 }
 
-// Pass variants (LBZ_TP_VER): 3 = persistent TMA kernel (k_text_pass3), 2 = one CTA per tile
+// ---------------------------------------------------------------------------
+// Fourth implementation of the pass (default): one tile per CTA and three CTAs per SM like
+// k_text_pass2 -- the persistent variant above loses more to its lower occupancy and to the
+// coupling of consecutive tiles than the prefetch gains (measured: 1.31 ms vs 0.59 ms per pass) --
+// with the tile algorithm of k_text_pass3:
+//   * the tile's (key, index) pairs arrive by ONE 1-D bulk copy (cp.async.bulk, completion on an
+//     mbarrier) issued by the first thread while all threads clear the counters; the landing
+//     buffer doubles as the staging buffer of the digit-ordered tile;
+//   * three barriers per tile instead of six: after the column sums every warp scans the 256
+//     digit totals for itself and folds the result into its own counter row;
+//   * full tiles (all but the last of a block) run a specialisation without bounds tests;
+//   * CTAs are dispatched block-fastest (grid = blocks x tiles), so a tile's predecessor has
+//     usually published its inclusive prefix and the look-back ends after one or two steps.
+struct Pass4Smem {
+  uint2 buf[4096 + 2];
+  uint32_t wcnt[16][256];
+  uint32_t hsum[2][256];
+  uint32_t dstart[256];
+  uint32_t delta[256];
+  unsigned long long full;
+};
+
+template <int MODE, int LAST, bool FULL, bool RR>
+__device__ __forceinline__ void pass4_body(Pass4Smem &S, const uint8_t *__restrict__ T, const uint2 *__restrict__ src,
+                                           uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out, uint32_t *__restrict__ tstat,
+                                           const uint32_t *__restrict__ gbase, uint32_t shift, uint32_t ep, uint32_t *__restrict__ err,
+                                           uint32_t koff, uint32_t n, uint32_t tile, uint32_t tile_cnt, uint32_t shift1,
+                                           uint32_t off, uint32_t stat_row, uint32_t gb_row) {
+  constexpr int ITEMS = 8;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint32_t wbase = warp * (32 * ITEMS) + lane;
+  const uint32_t lim = FULL ? 0xFFFFFFFFu : (tile_cnt > wbase ? tile_cnt - wbase : 0u);
+  uint32_t *wrow = &S.wcnt[warp][0];
+  uint2 *stage = &S.buf[0];
+  // RR ("re-read"): only the digits stay in registers through the counting and scanning steps; the
+  // pairs are read again from the landing buffer right before they are staged (one more barrier,
+  // sixteen registers fewer while the scan is live -- the kernel is register-bound at 3 CTAs/SM)
+  uint32_t val[ITEMS], key[ITEMS];
+  uint32_t dgp[ITEMS / 4];
+#pragma unroll
+  for (int q = 0; q < ITEMS / 4; q++) dgp[q] = 0;
+  if (MODE == 0) {
+    const uint2 *sp = stage + shift1 + wbase;
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+      const uint2 pr = (FULL || q * 32u < lim) ? sp[q * 32] : make_uint2(0u, 0u);
+      key[q] = pr.x; val[q] = pr.y;
+    }
+  } else if (MODE == 1) {
+    const uint2 *sp = src + off + tile * 4096u + wbase;
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) val[q] = (FULL || q * 32u < lim) ? sp[q * 32].y : 0u;
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) key[q] = (FULL || q * 32u < lim) ? text_key4(T + off, val[q], n) : 0u;
+  } else {
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+      val[q] = tile * 4096u + wbase + q * 32;
+      key[q] = (FULL || q * 32u < lim) ? text_key4(T + off, wrap_add(val[q], koff, n), n) : 0u;
+    }
+  }
+  if (RR) {
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+      if (MODE != 0 && (FULL || q * 32u < lim)) stage[wbase + q * 32] = make_uint2(key[q], val[q]);
+      dgp[q >> 2] |= ((key[q] >> shift) & 0xFFu) << (8 * (q & 3));
+    }
+  }
+  const uint32_t lt = lanemask_lt();
+  uint32_t rkp[ITEMS / 4];
+#pragma unroll
+  for (int q = 0; q < ITEMS / 4; q++) rkp[q] = 0;
+#pragma unroll
+  for (int q = 0; q < ITEMS; q++) {
+    const bool valid = FULL || q * 32u < lim;
+    const uint32_t dg = RR ? ((dgp[q >> 2] >> (8 * (q & 3))) & 0xFFu) : ((key[q] >> shift) & 0xFFu);
+    const uint32_t digit = valid ? dg : 0x100u;
+    const uint32_t mask = __match_any_sync(0xffffffffu, digit);
+    uint32_t base = 0;
+    if (valid) base = wrow[digit];
+    __syncwarp();
+    if (valid && (mask & lt) == 0) wrow[digit] = base + __popc(mask);
+    __syncwarp();
+    rkp[q >> 2] |= (base + __popc(mask & lt)) << (8 * (q & 3));
+  }
+  __syncthreads();                                           // A: all rows counted, all items in registers
+
+  const uint32_t d = tid & 255u, half = tid >> 8;
+  {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t c = S.wcnt[half * 8 + w][d]; S.wcnt[half * 8 + w][d] = run; run += c; }
+    S.hsum[half][d] = run;
+  }
+  __syncthreads();                                           // B: column sums ready
+
+  uint32_t total_d = 0;
+  uint32_t *mine = tstat + ((size_t)stat_row + tile) * 256 + d;
+  if (half == 0) {
+    total_d = S.hsum[0][d] + S.hsum[1][d];
+    st_volatile_u32(mine, (tile == 0 ? TS_FLAG_PREFIX : TS_FLAG_AGG) | ep | total_d);
+  }
+  {   // every warp: exclusive scan of the 256 digit totals, 8 digits per lane, folded into its own row
+    uint32_t run = 0;
+#pragma unroll
+    for (int hq = 0; hq < 4; hq++) {
+      const uint2 a = *reinterpret_cast<const uint2 *>(&S.hsum[0][lane * 8 + 2 * hq]);
+      const uint2 c = *reinterpret_cast<const uint2 *>(&S.hsum[1][lane * 8 + 2 * hq]);
+      run += a.x + a.y + c.x + c.y;
+    }
+    uint32_t e = warp_incl_sum(run) - run;                               // start of digit lane*8 inside the tile
+    const bool hi = warp >= 8;                                           // second half: after the first half's items
+    const bool pub = (lane >> 2) == warp;                                // warps 0..7: the 32 digits their threads look back for
+#pragma unroll
+    for (int hq = 0; hq < 4; hq++) {
+      const uint2 a = *reinterpret_cast<const uint2 *>(&S.hsum[0][lane * 8 + 2 * hq]);
+      const uint2 c = *reinterpret_cast<const uint2 *>(&S.hsum[1][lane * 8 + 2 * hq]);
+      const uint32_t e0 = e, e1 = e0 + a.x + c.x;
+      e = e1 + a.y + c.y;
+      if (pub) *reinterpret_cast<uint2 *>(&S.dstart[lane * 8 + 2 * hq]) = make_uint2(e0, e1);
+      uint2 w = *reinterpret_cast<const uint2 *>(&wrow[lane * 8 + 2 * hq]);
+      w.x += e0 + (hi ? a.x : 0u); w.y += e1 + (hi ? a.y : 0u);
+      *reinterpret_cast<uint2 *>(&wrow[lane * 8 + 2 * hq]) = w;
+    }
+  }
+  __syncwarp();
+  if (RR) {
+    const uint2 *sp = stage + (MODE == 0 ? shift1 : 0u) + wbase;
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+      const uint2 pr = (FULL || q * 32u < lim) ? sp[q * 32] : make_uint2(0u, 0u);
+      key[q] = pr.x; val[q] = pr.y;
+    }
+    __syncthreads();                                         // every pair is back in registers: the buffer may be overwritten
+  }
+#pragma unroll
+  for (int q = 0; q < ITEMS; q++) {
+    if (FULL || q * 32u < lim) {
+      const uint32_t digit = RR ? ((dgp[q >> 2] >> (8 * (q & 3))) & 0xFFu) : ((key[q] >> shift) & 0xFFu);
+      const uint32_t slot = wrow[digit] + ((rkp[q >> 2] >> (8 * (q & 3))) & 0xFFu);
+      stage[slot] = make_uint2(key[q], val[q]);
+    }
+  }
+  if (half == 0) {
+    uint32_t excl = 0;
+    if (tile != 0) {
+      const uint32_t *row0 = mine - (size_t)tile * 256;
+      int t = (int)tile - 1;
+      uint32_t spins = 0;
+      bool done = false;
+      while (!done) {
+        uint32_t sw[TS_WINDOW];
+#pragma unroll
+        for (int q = 0; q < TS_WINDOW; q++)
+          sw[q] = (t - q >= 0) ? ld_volatile_u32(row0 + (size_t)(t - q) * 256) : (TS_FLAG_PREFIX | ep);
+        int used = 0;
+#pragma unroll
+        for (int q = 0; q < TS_WINDOW; q++) {
+          if (!done && used == q) {
+            const uint32_t w = sw[q];
+            if ((w & TS_EPOCH_MASK) == ep && (w >> 30) != 0u) {
+              excl += w & TS_VALUE_MASK;
+              used = q + 1;
+              if (w & TS_FLAG_PREFIX) done = true;
+            }
+          }
+        }
+        t -= used;
+        if (!done && used < TS_WINDOW) {
+          if (++spins > TS_SPIN_LIMIT) { *err = 1u; break; }
+          __nanosleep(20);
+        }
+      }
+      st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total_d) & TS_VALUE_MASK));
+    }
+    S.delta[d] = gbase[(size_t)gb_row + d] + excl - S.dstart[d];
+  }
+  __syncthreads();                                           // C: tile staged in digit order, offsets known
+#pragma unroll
+  for (int q = 0; q < ITEMS; q++) {
+    const uint32_t i = tid + q * 512u;
+    if (FULL || i < tile_cnt) {
+      const uint2 pr = stage[i];
+      const uint32_t o = S.delta[(pr.x >> shift) & 0xFFu] + i;
+      if (LAST) sa_out[off + o] = pr.y; else dst[off + o] = pr;
+    }
+  }
+}
+
+template <int MODE, int LAST, int LIST, bool RR>
+__global__ void __launch_bounds__(512, 3)
+k_text_pass4(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+             const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
+             uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
+             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride) {
+  extern __shared__ __align__(128) unsigned char pass4_smem_raw[];
+  Pass4Smem &S = *reinterpret_cast<Pass4Smem *>(pass4_smem_raw);
+  const uint32_t b = blockIdx.x, tile = blockIdx.y;           // block-fastest dispatch
+  const uint32_t n = meta[b].n;
+  const uint32_t cnt = LIST ? meta[b].ul : n;
+  const uint32_t tbase = tile * 4096u;
+  if (tbase >= cnt) return;
+  const uint32_t off = lbz_slot_off(g, b) + (LIST ? meta[b].lbase : 0u);
+  const uint32_t tile_cnt = min(4096u, cnt - tbase);
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t shift1 = (MODE == 0) ? ((off + tbase) & 1u) : 0u;
+  if (MODE == 0 && tid == 0) {
+    // 16-byte aligned source: start one pair early when the tile starts at an odd element
+    const uint32_t bytes = ((shift1 + tile_cnt + 1u) & ~1u) * 8u;
+    mbar_init(&S.full, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arrive_expect_tx(&S.full, bytes);
+    bulk_g2s(&S.buf[0], src + (off + tbase - shift1), bytes, &S.full);
+  }
+  {
+    uint4 *z = reinterpret_cast<uint4 *>(&S.wcnt[tid >> 5][0]);
+    z[lane] = make_uint4(0u, 0u, 0u, 0u);
+    z[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (MODE == 0) {
+    __syncthreads();                                          // the mbarrier is initialised
+    if (!mbar_wait(&S.full, 0u)) { *err = 2u; return; }
+  } else {
+    __syncwarp();
+  }
+  const uint32_t ep = (epoch << 20) & TS_EPOCH_MASK;
+  const uint32_t stat_row = b * (g.S1 / 4096u), gb_row = b * gstride;
+  if (tile_cnt == 4096u)
+    pass4_body<MODE, LAST, true, RR>(S, T, src, dst, sa_out, tstat, gbase, shift, ep, err, koff, n, tile, tile_cnt, shift1, off, stat_row, gb_row);
+  else
+    pass4_body<MODE, LAST, false, RR>(S, T, src, dst, sa_out, tstat, gbase, shift, ep, err, koff, n, tile, tile_cnt, shift1, off, stat_row, gb_row);
+}
+
+// Pass variants (LBZ_TP_VER): 4 = one CTA per tile, TMA-fed, three barriers (k_text_pass4, default),
+// 3 = persistent TMA kernel (k_text_pass3), 2 = one CTA per tile
 // (k_text_pass2; LBZ_TP_XPOSE=1 dispatches it block-fastest), 1 = first implementation.
 static int tp_version() {
   static int v = -1;
-  if (v < 0) { const char *ev = getenv("LBZ_TP_VER"); v = ev ? atoi(ev) : 3; if (v < 1 || v > 3) v = 3; }
+  if (v < 0) { const char *ev = getenv("LBZ_TP_VER"); v = ev ? atoi(ev) : 4; if (v < 1 || v > 4) v = 4; }
   return v;
 }
 static uint32_t tp_xpose() {
@@ -948,6 +1182,28 @@ static int launch_pass3(uint32_t tiles, uint32_t nb, cudaStream_t st, const LbzG
   return 0;
 }
 
+template <int MODE, int LAST, int LIST>
+static int launch_pass4(uint32_t tiles, uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
+                        const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase, uint32_t gstride,
+                        uint32_t shift, uint32_t epoch, uint32_t *err, uint32_t koff) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass4<MODE, LAST, LIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pass4Smem)));
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass4<MODE, LAST, LIST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pass4Smem)));
+    attr_set = true;
+  }
+  if (tiles == 0 || nb == 0) return 0;
+  static int rr = -1;
+  if (rr < 0) { const char *ev = getenv("LBZ_TP_RR"); rr = ev ? (atoi(ev) != 0) : 1; }
+  if (rr)
+    k_text_pass4<MODE, LAST, LIST, true><<<dim3(nb, tiles), 512, sizeof(Pass4Smem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase, shift,
+                                                                                       epoch, err, koff, gstride);
+  else
+    k_text_pass4<MODE, LAST, LIST, false><<<dim3(nb, tiles), 512, sizeof(Pass4Smem), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase, shift,
+                                                                                        epoch, err, koff, gstride);
+  return 0;
+}
+
 template <int MODE, int LAST, int MINB>
 static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
                             const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
@@ -969,6 +1225,8 @@ template <int MODE, int LAST>
 static int launch_text_pass(uint32_t nb, cudaStream_t st, const LbzGeom &g, const LbzBlockMeta *meta, const uint8_t *T,
                             const uint2 *src, uint2 *dst, uint32_t *sa_out, uint32_t *tstat, const uint32_t *gbase,
                             uint32_t shift, uint32_t epoch, uint32_t *err, uint32_t koff, const BwtBuffers &B) {
+  if (tp_version() == 4)
+    return launch_pass4<MODE, LAST, 0>(g.S1 / 4096u, nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, 256u, shift, epoch, err, koff);
   if (tp_version() == 3)
     return launch_pass3<MODE, LAST, 0>(g.S1 / 4096u, nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, 256u, shift, epoch, err, koff, B);
   static int minb = 0;
@@ -982,6 +1240,8 @@ static int launch_list_pass(uint32_t max_count, uint32_t nb, cudaStream_t st, co
                             const uint2 *src, uint2 *dst, uint32_t *tstat, const uint32_t *gbase, uint32_t gstride,
                             uint32_t shift, uint32_t epoch, uint32_t *err, const BwtBuffers &B) {
   const uint32_t tiles = (max_count + 4095u) / 4096u;
+  if (tp_version() == 4)
+    return launch_pass4<0, 0, 1>(tiles, nb, st, g, meta, nullptr, src, dst, nullptr, tstat, gbase, gstride, shift, epoch, err, 0u);
   if (tp_version() == 3)
     return launch_pass3<0, 0, 1>(tiles, nb, st, g, meta, nullptr, src, dst, nullptr, tstat, gbase, gstride, shift, epoch, err, 0u, B);
   LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<0, 0, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
