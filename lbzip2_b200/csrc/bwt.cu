@@ -418,6 +418,16 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   const uint32_t off = lbz_slot_off(g, b) + (LIST ? meta[b].lbase : 0u);
   const uint32_t tile_cnt = min(RTILE, cnt - tbase);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  if (MODE == 0 && xpose > 1u && tid == 0) {
+    // TMA bulk prefetch into L2 of the tile that the CTA dispatched `xpose` rows later will load
+    // (block-fastest dispatch: that CTA starts about when the CTAs resident now retire)
+    const uint32_t t2 = tbase + xpose * RTILE;
+    if (t2 < cnt) {
+      const uint32_t e0 = (off + t2) & ~1u;
+      const uint32_t bytes = (min(RTILE, cnt - t2) * 8u) & ~15u;
+      if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + e0), "r"(bytes) : "memory");
+    }
+  }
   const uint32_t wbase = warp * (32 * ITEMS) + lane;              // tile index of this thread's item 0
   const uint32_t lim = tile_cnt > wbase ? tile_cnt - wbase : 0u;  // item `it` exists iff it * 32 < lim
 
@@ -1142,17 +1152,21 @@ k_text_pass4(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
     pass4_body<MODE, LAST, false, RR>(S, T, src, dst, sa_out, tstat, gbase, shift, ep, err, koff, n, tile, tile_cnt, shift1, off, stat_row, gb_row);
 }
 
-// Pass variants (LBZ_TP_VER): 4 = one CTA per tile, TMA-fed, three barriers (k_text_pass4, default),
-// 3 = persistent TMA kernel (k_text_pass3), 2 = one CTA per tile
+// Pass variants (LBZ_TP_VER): 2 = one CTA per tile, dispatched block-fastest, TMA bulk prefetch of the tile
+// two rows ahead into L2 (k_text_pass2, default: the fastest measured, profiles/r02_pass_variants.md),
+// 4 = one CTA per tile, TMA-fed, three barriers (k_text_pass4: bound by the shared-memory pipe),
+// 3 = persistent TMA kernel (k_text_pass3: bound by occupancy), 2 = one CTA per tile
 // (k_text_pass2; LBZ_TP_XPOSE=1 dispatches it block-fastest), 1 = first implementation.
 static int tp_version() {
   static int v = -1;
-  if (v < 0) { const char *ev = getenv("LBZ_TP_VER"); v = ev ? atoi(ev) : 4; if (v < 1 || v > 4) v = 4; }
+  if (v < 0) { const char *ev = getenv("LBZ_TP_VER"); v = ev ? atoi(ev) : 2; if (v < 1 || v > 4) v = 2; }
   return v;
 }
+// 0 = tile-fastest dispatch, 1 = block-fastest, n >= 2 = block-fastest + TMA bulk prefetch into L2 of the
+// tile n rows ahead
 static uint32_t tp_xpose() {
   static int v = -1;
-  if (v < 0) { const char *ev = getenv("LBZ_TP_XPOSE"); v = ev ? (atoi(ev) != 0) : 1; }
+  if (v < 0) { const char *ev = getenv("LBZ_TP_XPOSE"); v = ev ? atoi(ev) : 2; if (v < 0 || v > 8) v = 2; }
   return (uint32_t)v;
 }
 static int sm_count() {

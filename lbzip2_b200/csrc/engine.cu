@@ -115,6 +115,10 @@ struct lbz_engine {
   void (*on_sorted)(void *) = nullptr;  // set per call by the two-lane driver
   void *on_sorted_arg = nullptr;
   lbz_engine *sib = nullptr;
+  // blocks that enter the pipeline after the RLE1 stage (collected on the host, per-block API only):
+  // block bytes + record are copied into their slot once the RLE1 kernels have run
+  struct Inject { uint32_t slot; const uint8_t *bytes; LbzBlockMeta meta; };
+  std::vector<Inject> inject;
   uint32_t total_chunks = 0;           // capacity of the whole engine (both lanes)
   cudaEvent_t ev_done = nullptr;
 };
@@ -389,6 +393,12 @@ static int run_pipeline(lbz_engine *e, const uint8_t *d_in, uint8_t *d_packed, s
   cudaEventRecord(e->tm.stage[0], e->st);
   for (int s = LBZ_ST_RLE1; s <= LBZ_ST_PACK; s++) {
     if (run_stage(e, s, d_in, d_packed)) return -1;
+    if (s == LBZ_ST_RLE1) {
+      for (const lbz_engine::Inject &in : e->inject) {
+        ENG_CHECK(cudaMemcpyAsync(e->d_T + lbz_slot_off(e->g, in.slot), in.bytes, in.meta.n, cudaMemcpyHostToDevice, e->st));
+        ENG_CHECK(cudaMemcpyAsync(e->d_meta + in.slot, &in.meta, sizeof(LbzBlockMeta), cudaMemcpyHostToDevice, e->st));
+      }
+    }
     cudaEventRecord(e->tm.stage[after[s]], e->st);
   }
   ENG_CHECK(cudaMemcpyAsync(e->h_meta, e->d_meta, nb * sizeof(LbzBlockMeta), cudaMemcpyDeviceToHost, e->st));
@@ -724,7 +734,11 @@ struct encoder_state {
   uint32_t rle_char;
   uint32_t staged_cap;
   uint32_t tree_cost;        // bits: prefix-code transmission + payload cost reported by the Huffman kernel
-  uint8_t *staged;           // pinned staging of the raw bytes of this block (lives after the struct)
+  uint32_t nblock;           // RLE1 output bytes so far (host-side count, src/encode.c:333)
+  uint32_t mode;             // 0: raw bytes staged, RLE1 + CRC run on the device; 1: block collected on the host (see collect())
+  uint32_t hcrc;             // mode 1: running CRC of the consumed bytes (un-inverted, src/encode.c:542)
+  uint32_t used[8];          // mode 1: used-byte map
+  uint8_t *staged;           // staging of the raw bytes of this block (lives after the struct)
 };
 
 extern "C" void failx(int x, const char *fmt, ...) __attribute__((weak));
@@ -814,6 +828,68 @@ namespace { int batch_limit(); }
 
 #define ENC_MAGIC 0xB2005A42u
 
+// ---- the block-split automaton of collect() on the host ------------------------------------------
+// collect() must say how many of the offered bytes the block takes and whether it is full
+// (src/encode.c:135-336) when it returns, and the scheduler may offer one block's input in
+// several pieces (the -u mode, src/compress.c:160-187).  Asking the device costs a host<->device
+// round trip per call, so the split is decided here: `rle_feed` walks the input once and tracks
+// only (n' so far, length and byte of the pending run).  Restated from the rules, not the code:
+//   * a run of r equal bytes (r <= 259, longer runs restart) adds min(r, 4) bytes, plus a count
+//     byte r - 4 once it has 4 or more and ends;
+//   * the block is full when n' reaches the capacity after a literal or a count byte, or when the
+//     third literal of a run leaves one slot and the run continues (the fourth literal is only
+//     written together with room for its count byte, src/encode.c:218,233).
+// EMIT = true additionally produces the block bytes, the CRC of the consumed bytes and the
+// used-byte map (for blocks whose raw bytes do not fit the device's chunk buffer: long runs in -u
+// mode) -- exactly what the reference's collect() does on its calling thread.
+struct RleSt { uint32_t nblock; int32_t state; uint32_t ch; };    // state: -1 full, 0 no pending run, else its length (< 259)
+
+template <bool EMIT>
+static size_t rle_feed(RleSt &r, const uint8_t *p, size_t avail, uint32_t cap, uint8_t *out, uint32_t *crcp, uint32_t *used) {
+  const uint8_t *q = p, *const end = p + avail;
+  uint32_t crc = EMIT ? *crcp : 0u;
+  auto lit = [&](uint32_t c) {                       // consume one input byte that becomes a block byte
+    if (EMIT) { out[r.nblock] = (uint8_t)c; used[c >> 5] |= 1u << (c & 31u); crc = (crc << 8) ^ crc_table[(crc >> 24) ^ c]; }
+    r.nblock++;
+  };
+  auto count_byte = [&](uint32_t v) {
+    if (EMIT) { out[r.nblock] = (uint8_t)v; used[v >> 5] |= 1u << (v & 31u); }
+    r.nblock++;
+  };
+  while (q < end && r.state >= 0) {
+    if (r.state == 0) {
+      if (r.nblock == cap) { r.state = -1; break; }
+      r.ch = *q++;
+      lit(r.ch);
+      r.state = 1;
+      if (r.nblock == cap) { r.state = -1; break; }
+    } else if (r.state < 3) {
+      if (*q != r.ch) { r.state = 0; continue; }
+      q++;
+      lit(r.ch);
+      r.state++;
+      if (r.nblock == cap) { r.state = -1; break; }
+    } else if (r.state == 3) {
+      if (*q != r.ch) { r.state = 0; continue; }
+      if (r.nblock + 1u >= cap) { r.state = -1; break; }        // one slot left and the run goes on: cut before the 4th byte
+      q++;
+      lit(r.ch);
+      r.state = 4;
+    } else {
+      while (q < end && *q == r.ch && r.state < 259) {
+        if (EMIT) crc = (crc << 8) ^ crc_table[(crc >> 24) ^ r.ch];
+        q++;
+        r.state++;
+      }
+      if (r.state == 259) { count_byte(255u); r.state = 0; }
+      else if (q < end) { count_byte((uint32_t)r.state - 4u); r.state = 0; }
+    }
+  }
+  if (r.state == 0 && r.nblock == cap) r.state = -1;             // src/encode.c:162: full is noticed before "input exhausted"
+  if (EMIT) *crcp = crc;
+  return (size_t)(q - p);
+}
+
 // Host bytes behind the handle: the raw bytes of the block until encode(), the packed block
 // afterwards (also the internal buffer of transmit(s, NULL), src/encode.c:1177-1182).  A packed
 // block never exceeds 5/2 n' + 8 KiB (lbz_common.cuh out_cap); raw input never exceeds mbs.
@@ -840,15 +916,14 @@ extern "C" void encoder_init(struct encoder_state *s, unsigned long max_block_si
   s->staged_cap = (uint32_t)enc_staged_cap(max_block_size);
 }
 
-// collect(): the raw bytes offered to this state are staged on the host side
-// of the handle, the RLE1 kernel runs over everything staged so far, and the
-// block record tells how many raw bytes the block takes (its cut point is a
-// prefix property, see rle1.cu).  In the scheduler's default mode there is
-// exactly one collect() per state with at most max_block_size bytes
-// (src/compress.c:93-110, src/process.c:631).  Repeated calls (the -u mode,
-// src/compress.c:160-187) are accepted as long as one block does not need more
-// than max_block_size raw bytes; beyond that this build stops loudly (row f4
-// of SURVEY.md 8 is not built yet).
+// collect(): the block split is decided on the host (rle_feed above); the raw bytes the block
+// takes are staged behind the handle and RLE1 + CRC run on the device with the rest of the block
+// (mode 0).  Several calls per state are fine (the -u mode, src/compress.c:160-187).  Only when one
+// block takes more raw bytes than the device's chunk buffer holds (max_block_size; long runs packed
+// across I/O buffers in -u mode) the block is collected on the host like in the reference -- RLE1
+// output, CRC and used-byte map (mode 1) -- and enters the device at the BWT stage.
+static inline uint8_t *enc_block_area(struct encoder_state *s) { return s->staged + ((s->max_block_size + 127u) & ~63u); }
+
 extern "C" int collect(struct encoder_state *s, const uint8_t *buf, size_t *buf_sz) {
   if (!s || s->magic != ENC_MAGIC) die("collect: state not initialised");
   if (s->done) die("collect: called after encode()");
@@ -856,29 +931,33 @@ extern "C" int collect(struct encoder_state *s, const uint8_t *buf, size_t *buf_
   const size_t avail = *buf_sz;
   if (avail == 0) return 0;
   const uint32_t mbs = s->max_block_size;
-  if (s->raw_len >= mbs) die("collect: one block would need more than max_block_size raw bytes (not supported yet)");
-  if (s->pool_slot < 0) s->pool_slot = pool_acquire(mbs);
-  lbz_engine *e = g_pool.engines[s->pool_slot];
-  const size_t take = (avail < (size_t)(mbs - s->raw_len)) ? avail : (size_t)(mbs - s->raw_len);
-  memcpy(s->staged + s->raw_len, buf, take);
-  const uint32_t old_len = s->raw_len;
-  const uint32_t new_len = old_len + (uint32_t)take;
-  if (lbz_dbg_load(e, s->staged, new_len)) die("collect: H2D failed");
-  if (lbz_dbg_run(e, LBZ_ST_RLE1)) die("collect: RLE1 kernel failed");
-  LbzBlockMeta m;
-  if (lbz_dbg_read(e, LBZ_AR_META, 0, &m, sizeof m)) die("collect: meta readback failed");
-  int full = 0;
-  if (m.raw_len < new_len) {            // the block closed before the end of the staged bytes
-    s->raw_len = m.raw_len;             // >= old_len: everything before was consumed without closing
-    s->rle_state = -1;
-    full = 1;
-  } else {
-    s->raw_len = new_len;
-    if (m.n >= mbs) { s->rle_state = -1; full = 1; }   // n' == mbs is only reached by a filling write
+  RleSt r{s->nblock, s->rle_state, s->rle_char};
+  size_t consumed = 0;
+  if (s->mode == 0) {
+    const size_t room = (size_t)mbs - s->raw_len;
+    const size_t offer = avail < room ? avail : room;
+    consumed = rle_feed<false>(r, buf, offer, mbs, nullptr, nullptr, nullptr);
+    memcpy(s->staged + s->raw_len, buf, consumed);
+    s->raw_len += (uint32_t)consumed;
+    if (r.state >= 0 && consumed == offer && offer < avail) {
+      // the chunk buffer is exhausted and the block is not full: collect it on the host from here on
+      RleSt r2{0u, 0, 0u};
+      s->hcrc = 0xFFFFFFFFu;
+      memset(s->used, 0, sizeof s->used);
+      if (rle_feed<true>(r2, s->staged, s->raw_len, mbs, enc_block_area(s), &s->hcrc, s->used) != s->raw_len ||
+          r2.nblock != r.nblock || r2.state != r.state)
+        die("collect: internal error: host block split is not reproducible");
+      s->mode = 1;
+    }
   }
-  *buf_sz = avail - (s->raw_len - old_len);
-  if (batch_limit() > 0) { pool_release(s->pool_slot); s->pool_slot = -1; }   // encode() goes through the batcher
-  return full;
+  if (s->mode == 1 && r.state >= 0 && consumed < avail) {
+    const size_t c2 = rle_feed<true>(r, buf + consumed, avail - consumed, mbs, enc_block_area(s), &s->hcrc, s->used);
+    consumed += c2;
+    s->raw_len += (uint32_t)c2;
+  }
+  s->nblock = r.nblock; s->rle_state = r.state; s->rle_char = r.ch;
+  *buf_sz = avail - consumed;
+  return r.state < 0;
 }
 
 // ---- cross-thread batching of encode() ---------------------------------------
@@ -904,30 +983,52 @@ struct Batcher {
 // waiter (static destruction at exit) blocks forever in glibc.
 Batcher &g_batch = *new Batcher;
 
-int run_batch(uint32_t mbs_key, std::vector<BReq *> &batch) {
-  lbz_engine *&e = g_batch.eng[mbs_key];
-  if (!e) {
-    e = engine_create_mbs(g_pool.device, mbs_key, g_batch.max_batch);
-    if (!e) return -1;
-    e->total_chunks = (uint32_t)g_batch.max_batch;
-  }
+// Push a batch of collected blocks (one per chunk slot) through the kernels on engine `e` and
+// leave every block's bytes in its handle.
+int encode_blocks(lbz_engine *e, std::vector<BReq *> &batch) {
   if (cudaSetDevice(e->device) != cudaSuccess) return -1;
   const uint32_t k = (uint32_t)batch.size();
   const size_t mbs = e->g.mbs;
   e->g.nchunks = k;
+  e->inject.clear();
   for (uint32_t c = 0; c < k; c++) {
     encoder_state *s = batch[c]->s;
-    e->h_chunk_len[c] = s->raw_len;
-    ENG_CHECK(cudaMemcpyAsync(e->d_in + (size_t)c * mbs, s->staged, s->raw_len, cudaMemcpyHostToDevice, e->st));
+    // a pending run of four or more still owes its count byte (src/encode.c:443-447)
+    const bool flush = s->rle_state >= 4;
+    if (s->mode == 0) {
+      e->h_chunk_len[c] = s->raw_len;
+      ENG_CHECK(cudaMemcpyAsync(e->d_in + (size_t)c * mbs, s->staged, s->raw_len, cudaMemcpyHostToDevice, e->st));
+    } else {
+      e->h_chunk_len[c] = 0;                         // nothing for the RLE1 kernels in this slot
+      uint8_t *blk = enc_block_area(s);
+      if (flush) {
+        const uint32_t v = (uint32_t)s->rle_state - 4u;
+        blk[s->nblock++] = (uint8_t)v;
+        s->used[v >> 5] |= 1u << (v & 31u);
+        s->rle_state = 0;
+      }
+      lbz_engine::Inject in;
+      in.slot = 2 * c; in.bytes = blk;
+      memset(&in.meta, 0, sizeof in.meta);
+      in.meta.n = s->nblock; in.meta.raw_len = s->raw_len; in.meta.crc = s->hcrc;
+      memcpy(in.meta.used, s->used, sizeof s->used);
+      e->inject.push_back(in);
+    }
   }
   ENG_CHECK(cudaMemcpyAsync(e->d_chunk_len, e->h_chunk_len, k * sizeof(uint32_t), cudaMemcpyHostToDevice, e->st));
   size_t total = 0;
-  if (run_pipeline(e, e->d_in, e->d_packed, &total)) return -1;
+  const int prc = run_pipeline(e, e->d_in, e->d_packed, &total);
+  e->inject.clear();
+  if (prc) return -1;
   size_t off = 0;
   for (uint32_t c = 0; c < k; c++) {
     encoder_state *s = batch[c]->s;
     const LbzBlockMeta &m0 = e->h_meta[2 * c], &m1 = e->h_meta[2 * c + 1];
-    if (m0.raw_len != s->raw_len || m1.n != 0) { batch[c]->rc = -1; off += m0.out_len + (m1.n ? m1.out_len : 0); continue; }
+    // the device must cut the block exactly where collect() said it would
+    const uint32_t want_n = s->nblock + ((s->mode == 0 && s->rle_state >= 4) ? 1u : 0u);
+    if (m0.raw_len != s->raw_len || m0.n != want_n || m1.n != 0) {
+      batch[c]->rc = -1; off += m0.out_len + (m1.n ? m1.out_len : 0); continue;
+    }
     // the raw bytes are no longer needed: the block's bytes take their place in the handle
     ENG_CHECK(cudaMemcpyAsync(s->staged, e->d_packed + off, m0.out_len, cudaMemcpyDeviceToHost, e->st));
     s->out_len = m0.out_len;
@@ -937,6 +1038,16 @@ int run_batch(uint32_t mbs_key, std::vector<BReq *> &batch) {
   }
   ENG_CHECK(cudaStreamSynchronize(e->st));
   return 0;
+}
+
+int run_batch(uint32_t mbs_key, std::vector<BReq *> &batch) {
+  lbz_engine *&e = g_batch.eng[mbs_key];
+  if (!e) {
+    e = engine_create_mbs(g_pool.device, mbs_key, g_batch.max_batch);
+    if (!e) return -1;
+    e->total_chunks = (uint32_t)g_batch.max_batch;
+  }
+  return encode_blocks(e, batch);
 }
 
 void batch_worker() {
@@ -977,7 +1088,6 @@ extern "C" size_t encode(struct encoder_state *s, uint32_t *crc) {
   if (!s || s->magic != ENC_MAGIC) die("encode: state not initialised");
   if (s->raw_len == 0) die("encode: empty block (src/encode.c:448)");
   if (batch_limit() > 0) {
-    if (s->pool_slot >= 0) { pool_release(s->pool_slot); s->pool_slot = -1; }   // collect()'s context is no longer needed
     BReq r{s, 0, false};
     {
       std::unique_lock<std::mutex> lk(g_batch.mu);
@@ -991,23 +1101,16 @@ extern "C" size_t encode(struct encoder_state *s, uint32_t *crc) {
     if (crc) *crc = s->crc;
     return s->out_len;
   }
-  if (s->pool_slot < 0) s->pool_slot = pool_acquire(s->max_block_size);
-  lbz_engine *e = g_pool.engines[s->pool_slot];
-  // exactly the consumed bytes form this block; run every stage on them
-  if (lbz_dbg_load(e, s->staged, s->raw_len)) die("encode: H2D failed");
-  for (int st = LBZ_ST_RLE1; st <= LBZ_ST_PACK; st++)
-    if (lbz_dbg_run(e, st)) die("encode: kernel failed");
-  LbzBlockMeta m[2];
-  if (lbz_dbg_read(e, LBZ_AR_META, 0, &m[0], sizeof m[0]) || lbz_dbg_read(e, LBZ_AR_META, 1, &m[1], sizeof m[1]))
-    die("encode: meta readback failed");
-  if (m[0].raw_len != s->raw_len || m[1].n != 0) die("encode: internal error: block split changed");
-  if (m[0].pad_[0] != 8u * m[0].out_len) die("encode: internal size mismatch");
-  s->out_len = m[0].out_len;
-  s->crc = m[0].crc;
-  s->tree_cost = m[0].tree_cost;
-  s->done = 1;
-  if (crc) *crc = m[0].crc;
-  return m[0].out_len;
+  // no batching: the block runs alone on a pooled single-chunk context
+  const int slot = pool_acquire(s->max_block_size);
+  BReq r{s, 0, false};
+  std::vector<BReq *> one{&r};
+  const int rc = encode_blocks(g_pool.engines[slot], one);
+  pool_release(slot);
+  if (rc || r.rc) die("encode: kernel pipeline failed");
+  s->done = 2;                               // block bytes live in the handle
+  if (crc) *crc = s->crc;
+  return s->out_len;
 }
 
 extern "C" unsigned generate_prefix_code(struct encoder_state *s) {
@@ -1021,17 +1124,9 @@ extern "C" void *transmit(struct encoder_state *s, void *buf) {
   const size_t bytes = ((size_t)s->out_len + 3) / 4 * 4;
   if (bytes > s->staged_cap) die("transmit: internal size error");
   // no external buffer: the block is handed out in the handle's own buffer (src/encode.c:1177-1182)
-  if (s->done == 2) {
-    memset(s->staged + s->out_len, 0, bytes - s->out_len);
-    if (!buf) return s->staged;
-    memcpy(buf, s->staged, bytes);
-    return buf;
-  }
-  lbz_engine *e = g_pool.engines[s->pool_slot];
-  if (!buf) buf = s->staged;
-  if (lbz_dbg_read(e, LBZ_AR_OUT, 0, buf, bytes)) die("transmit: D2H failed");
-  pool_release(s->pool_slot);
-  s->pool_slot = -1;
+  memset(s->staged + s->out_len, 0, bytes - s->out_len);
+  if (!buf) return s->staged;
+  memcpy(buf, s->staged, bytes);
   return buf;
 }
 

@@ -391,7 +391,10 @@ __device__ __forceinline__ uint32_t rt_seg(int stage, const RtView &v, uint32_t 
 // RLE1 expands by at most 5/4, so the block can only fill -- and a second block can only
 // start -- after 0.8 * cap raw bytes: the cut search and all stage-1 kernels skip the
 // tiles in front of that point (their table entries are preset by k_rt_init).
-__host__ __device__ inline uint32_t rt_tail_tile(uint32_t cap) { return ((cap / 5u) * 4u - 8u) / RT_TILE; }
+__host__ __device__ inline uint32_t rt_tail_tile(uint32_t cap) {
+  const uint32_t t = (cap / 5u) * 4u;                        // capacities below 10 (per-block API, src/encode.c:121) have no skippable head
+  return t > 8u ? (t - 8u) / RT_TILE : 0u;
+}
 
 template <int STAGE>
 __global__ void __launch_bounds__(RT_THREADS)

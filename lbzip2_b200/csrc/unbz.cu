@@ -88,6 +88,166 @@ static size_t ub_chain_smem() {
 
 static void ub_timers_collect(lbz_decoder *d);
 
+// ---------------------------------------------------------------------------------------------
+// k_ub_chain2 -- the walk over the code lengths of a block (src/decode.c:605-791: where code k
+// starts depends on the lengths of codes 0..k-1), device-only rewrite of k_ub_chain for latency:
+//   * one CTA of four warps per block; the CTA copies the block's multi-code byte tables (4 KB
+//     per tree) into shared memory, then ONE warp walks.  Which warp is decided per SM (an atomic
+//     counter per %smid), so that two blocks that share an SM walk on different sub-partitions
+//     -- single-warp CTAs all sit on sub-partition 0 and two of them ran at half speed each.
+//   * the bit window is a 64-bit register refilled one word ahead; a table step is: shift, one
+//     shared-memory byte load, and/shift/add -- about a third of the instructions of k_ub_chain;
+//     the values are kept out of the uniform datapath (every lane computes the same walk).
+//   * the selector list is a register of 4-bit fields (no local-memory array).
+// Results are those of k_ub_chain (same tables, same rules); tests/test_gpu_unbz.py checks both.
+#define CH_THREADS 128u
+__device__ __forceinline__ uint32_t ch_bswap(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+__global__ void __launch_bounds__(CH_THREADS)
+k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, uint32_t nblk,
+            const uint8_t *__restrict__ sel_all, const UbTreeG *__restrict__ tree_all,
+            const uint16_t *__restrict__ l1_all, const uint8_t *__restrict__ mq_all,
+            uint64_t *__restrict__ gpos_all, uint8_t *__restrict__ gtree_all, uint32_t *sm_slots) {
+  __shared__ __align__(16) uint8_t smq[6 * UB_WSIZE];
+  __shared__ uint32_t s_slot;
+  const uint32_t b = blockIdx.x, tid = threadIdx.x;
+  if (b >= nblk) return;
+  UbBlock &B = blk[b];
+  if (B.status != UB_PENDING) return;
+  const uint32_t ntrees = B.num_trees > 6u ? 6u : B.num_trees;
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(mq_all + (size_t)b * 6u * UB_WSIZE);
+    uint4 *dst = reinterpret_cast<uint4 *>(smq);
+    for (uint32_t i = tid; i < ntrees * (UB_WSIZE / 16u); i += CH_THREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_slot = atomicAdd(&sm_slots[smid & 255u], 1u);
+  }
+  __syncthreads();
+  if ((tid >> 5) != (s_slot & 3u)) return;
+  // every lane of the walking warp computes the same walk; `zero` is 0 but opaque to the
+  // compiler, which keeps the chain in vector registers
+  uint32_t zero;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(zero));
+  const bool writer = zero == 0u;
+  zero >>= 5;
+
+  const uint8_t *sel = sel_all + (size_t)b * UB_SELCAP;
+  uint64_t *gpos = gpos_all + (size_t)b * (UB_MAXGRP + 1u);
+  uint8_t *gtree = gtree_all + (size_t)b * (UB_MAXGRP + 1u);
+  const uint32_t eob = B.alpha_size - 1u;
+  const uint32_t nsel = B.num_selectors > UB_MAXGRP ? UB_MAXGRP : B.num_selectors;   // src/decode.c:631-632
+  uint32_t slp = 0;                                  // selector list, 4 bits per entry: tree number or error code
+  for (uint32_t t = 0; t < 6u; t++) slp |= (t < B.num_trees ? ((uint32_t)tree_all[(size_t)b * 6u + t].status & 15u) : 0u) << (4u * t);
+  uint64_t pos = B.sym_bit + zero;
+  uint32_t status = UB_ERR_UNTERM, nsym = 0, g = 0;
+  UbBits br;
+  br.words = words; br.nwords = nwords;
+
+  for (; g < nsel; g++) {
+    const uint32_t r4 = 4u * min((uint32_t)sel[g], 7u);      // the header kernel admits only indices below num_trees
+    const uint32_t t = (slp >> r4) & 15u;
+    if (t >= 6u) { status = t; break; }              // a bad tree is selected (src/decode.c:640-642)
+    {                                                // move entry r to the front
+      const uint32_t below = slp & ((1u << r4) - 1u);
+      const uint32_t above = (r4 >= 28u) ? 0u : (slp >> (r4 + 4u)) << (r4 + 4u);
+      slp = above | (below << 4) | t;
+    }
+    if (writer) { gpos[g] = pos; gtree[g] = (uint8_t)t; }
+    const UbTreeG &T = tree_all[(size_t)b * 6u + t];
+    const uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
+    const uint8_t *mq = smq + t * UB_WSIZE;
+    bool done = false;
+
+    if ((pos >> 5) + 36u <= nwords) {
+      // lean window reader: a whole group (50 codes of at most 20 bits) lies inside the input
+      const uint32_t *wp = words + (pos >> 5);
+      const uint32_t bp = (uint32_t)(pos & 31u);
+      uint64_t buf = (((uint64_t)ch_bswap(wp[0]) << 32) | ch_bswap(wp[1])) << bp;
+      uint32_t avail = 64u - bp;                     // valid bits at the top of buf; the rest is zero
+      wp += 2;
+      uint32_t nxt = *wp;
+      uint32_t rem = 50u;
+      while (rem) {
+        const uint32_t idx = (uint32_t)(buf >> (64u - UB_WBITS));
+        const uint32_t q = mq[idx];
+        uint32_t len;
+        if (rem >= 4u && !(q & 0x80u)) {             // common case: all codes of the entry, no end of block
+          len = q & 15u;
+          rem -= q >> 4;
+        } else {                                     // one code: the last ones of a group, long codes, end of block
+          const uint32_t x = l1[idx];
+          uint32_t s;
+          if (x) { s = x >> 5; len = x & 31u; } else s = ub_canon_decode(T, (uint32_t)(buf >> 44), &len);
+          rem -= 1u;
+          if (s == eob) done = true;
+        }
+        buf <<= len;
+        avail -= len;
+        if (avail <= 32u) {
+          buf |= (uint64_t)ch_bswap(nxt) << (32u - avail);
+          avail += 32u;
+          wp++;
+          nxt = *wp;
+        }
+        if (done) break;
+      }
+      nsym += 50u - rem;
+      pos = ((uint64_t)(wp - words) << 5) - avail;
+    } else {
+      bool eof = !ub_bits_seek(br, pos);
+      for (uint32_t j = 0; j < 50u && !eof && !done; j++) {
+        if (!ub_bits_need(br)) { eof = true; break; }  // NEED(), src/decode.c:387-407
+        uint32_t c20 = ub_bits_peek(br, 20);
+        uint32_t x = l1[c20 >> (20u - UB_WBITS)];
+        uint32_t s, k;
+        if (x) { s = x >> 5; k = x & 31u; } else s = ub_canon_decode(T, c20, &k);
+        ub_bits_dump(br, k);
+        nsym++;
+        if (s == eob) done = true;
+      }
+      if (!eof || done) pos = ub_bits_pos(br);
+      if (eof && !done) { pos = ub_bits_pos(br); status = UB_ERR_EOF; g++; break; }
+    }
+    if (done) { status = UB_OK; g++; break; }
+  }
+  if (writer) {
+    B.nsym = nsym;
+    B.ngrp = g;
+    B.end_bit = pos;
+    B.status = status;
+  }
+}
+
+static uint32_t *ub_sm_slots(int device) {
+  static uint32_t *slots[64] = {};
+  if (device < 0 || device >= 64) return nullptr;
+  if (!slots[device] && cudaMalloc((void **)&slots[device], 256 * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+  return slots[device];
+}
+static int ub_chain_version() {
+  static int v = -1;
+  if (v < 0) { const char *s = getenv("LBZ_CHAIN_VER"); v = s ? atoi(s) : 2; if (v != 1) v = 2; }
+  return v;
+}
+#define UB_CHAIN_LAUNCH(d, nwords, nblk)                                                             \
+  do {                                                                                              \
+    uint32_t *slots_ = ub_chain_version() == 2 ? ub_sm_slots(ub_backend(d)->device) : nullptr;      \
+    if (slots_) {                                                                                   \
+      UB_CUDA(cudaMemsetAsync(slots_, 0, 256 * sizeof(uint32_t), ub_stream(d)));                    \
+      k_ub_chain2<<<(nblk), CH_THREADS, 0, ub_stream(d)>>>((d)->d_words, (nwords), (d)->d_blk, (nblk), (d)->d_sel, (d)->d_tree, \
+                                                            (d)->d_l1, (d)->d_mq, (d)->d_gpos, (d)->d_gtree, slots_);  \
+      cudaError_t le_ = cudaGetLastError();                                                         \
+      if (le_ != cudaSuccess) return ub_cuda_fail(le_, "k_ub_chain2", __LINE__);                    \
+      ub_count_launch(d);                                                                           \
+    } else {                                                                                        \
+      UB_LAUNCH_SMEM(d, k_ub_chain, (uint64_t)(nblk) * 32u, 32u, ub_chain_smem(), (d)->d_words, (nwords), (d)->d_blk, (nblk), \
+                     (d)->d_sel, (d)->d_tree, (d)->d_l1, (d)->d_ml, (d)->d_mq, (d)->d_gpos, (d)->d_gtree);           \
+    }                                                                                               \
+  } while (0)
+
 #include "unbz_engine.inc"
 
 static_assert(sizeof(lbz_dblock) == sizeof(UbBlock), "lbz_dblock mirrors UbBlock");

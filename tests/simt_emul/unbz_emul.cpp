@@ -49,6 +49,9 @@ static int ub_emu_reverse = 0;
 
 #define UB_LAUNCH_SMEM(d, kern, nthreads, cta, smem, ...) UB_LAUNCH(d, kern, nthreads, cta, __VA_ARGS__)
 static size_t ub_chain_smem() { return 0; }
+#define UB_CHAIN_LAUNCH(d, nwords, nblk)                                                             \
+  UB_LAUNCH(d, k_ub_chain, (uint64_t)(nblk) * 32u, 32u, (d)->d_words, (nwords), (d)->d_blk, (nblk), (d)->d_sel, (d)->d_tree, \
+            (d)->d_l1, (d)->d_ml, (d)->d_mq, (d)->d_gpos, (d)->d_gtree)
 
 #include "../../lbzip2_b200/csrc/unbz_engine.inc"
 

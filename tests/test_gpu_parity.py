@@ -444,6 +444,30 @@ def test_reference_cli_drives_the_gpu_engine():
         assert got.stdout == want
 
 
+def test_reference_cli_sequential_mode_on_the_gpu():
+    """Row f4 of SURVEY.md 8: `-u` (src/compress.c:120-198) packs blocks across I/O buffers -- collect()
+    is called again and again on one state until the block is full, so the block split differs
+    from the default mode.  The unmodified scheduler drives the library; the output must be the
+    CPU reference's, including blocks that take far more raw bytes than max_block_size (long runs)."""
+    import os
+    import subprocess
+    gpu_cli = os.path.join(orclib.REF_DIR, "lbzip2_gpu")
+    cpu_cli = os.path.join(orclib.REF_DIR, "lbzip2")
+    if not (os.path.exists(gpu_cli) and os.path.exists(cpu_cli)):
+        pytest.skip("oracle/_ref binaries not present")
+    data = (synth.text(1_700_000, offset=40) + b"\0" * 3_000_000 + synth.random_bytes(250_000, seed=41) +
+            b"ab" * 40_000 + b"z" * 777_777 + synth.text(400_000, offset=42) + b"qqqq" * 100_000)
+    for lv, nthreads in ((9, 4), (1, 8), (3, 2)):
+        env = dict(os.environ, LBZIP2_B200_CONTEXTS="16")
+        got = subprocess.run([gpu_cli, "-u", "-%d" % lv, "-n%d" % nthreads], input=data, stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, env=env, timeout=300)
+        assert got.returncode == 0 and got.stderr == b"", got.stderr[-500:]
+        want = subprocess.run([cpu_cli, "-u", "-%d" % lv], input=data, stdout=subprocess.PIPE, check=True).stdout
+        plain = subprocess.run([cpu_cli, "-%d" % lv], input=data, stdout=subprocess.PIPE, check=True).stdout
+        assert want != plain, "the test input must make -u differ from the default split"
+        assert got.stdout == want
+
+
 def test_reference_shaped_api_from_many_threads():
     """encode() calls from concurrent host threads are pooled into device batches
     (engine.cu batch_worker); every block must still be the oracle's."""
