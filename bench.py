@@ -419,22 +419,25 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     gth = sharding.BlockGatherer(dist, dev, max_blocks=2 * nchunks + 2, max_payload=cap) if world > 1 else None
+    # N > 1, host leg: ONE stream-ordered .bz2 in host memory shared by the ranks (a /dev/shm file
+    # mapped by every rank, registered with CUDA); completed inside the timed region of every step
+    sink = None
+    if world > 1:
+        sink = sharding.SharedStream(dist, dev, "/dev/shm/lbz_bench_stream_%s.bz2" % os.environ.get("MASTER_PORT", "0"),
+                                     world * cap + 64, max_blocks=2 * nchunks + 2)
 
-    def gather(recs, payload_dev, tables_only):
+    def gather(recs, payload_dev):
         """Device leg: NCCL gather of the block bitstreams into rank 0's HBM in one
-        point-to-point transfer per rank (stream order is then a table lookup).
-        Host leg: every rank's blocks are already in its own pinned host memory (the
-        D2H is inside lbz_compress_chunks); only the block table travels to rank 0 --
-        what a multi-process writer needs to pwrite every block at its stream offset."""
+        point-to-point transfer per rank (stream order is then a table lookup)."""
         if world == 1:
             return None
-        return gth.gather(sharding.block_table(recs, mbs), payload_dev, tables_only=tables_only)
+        return gth.gather(sharding.block_table(recs, mbs), payload_dev, tables_only=False)
 
     def step_device():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         n_out, recs = eng.compress_chunks_ptr(d_in.data_ptr(), nbytes, d_out.data_ptr(), cap, device=True)
-        g = gather(recs, d_out[:n_out], False)
+        g = gather(recs, d_out[:n_out])
         ev1.record()
         ev1.synchronize()
         return ev0.elapsed_time(ev1), eng.last_ms, n_out, recs, g
@@ -442,8 +445,19 @@ def run_ours(a):
     def step_host():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        n_out, recs = eng.compress_chunks_ptr(h_in, nbytes, h_out, cap, device=False)
-        g = gather(recs, d_out[:0], True)
+        if world == 1:
+            n_out, recs = eng.compress_chunks_ptr(h_in, nbytes, h_out, cap, device=False)
+            g = None
+        else:
+            # host in -> blocks in HBM; block tables of all ranks; every rank copies its blocks to their
+            # offsets in the shared stream; rank 0 adds header and trailer; closing barrier
+            n_out, recs = eng.compress_chunks_ptr(h_in, nbytes, d_out.data_ptr(), cap, h2d=True)
+            table = sharding.block_table(recs, mbs)
+            every = sink.exchange(table)
+            offs, total, cc = sharding.place_blocks(every, world)
+            src = np.concatenate(([0], np.cumsum(table[:, 1])))[:-1]
+            eng.scatter_to_host(d_out.data_ptr(), src, sink.ptr, offs[rank], table[:, 1])
+            g = sink.finish(level, total, cc)
         ev1.record()
         ev1.synchronize()
         return ev0.elapsed_time(ev1), eng.last_ms, n_out, recs, g
@@ -522,9 +536,12 @@ def run_ours(a):
             cc = (((cc << 1) & 0xFFFFFFFF) ^ (cc >> 31) ^ r.crc ^ 0xFFFFFFFF) & 0xFFFFFFFF
         stream = b"BZh" + bytes([48 + level]) + body + bytes([0x17, 0x72, 0x45, 0x38, 0x50, 0x90]) + cc.to_bytes(4, "big")
         own = {"sha256": hashlib.sha256(stream).hexdigest()}
-        host_body = bytes((C.c_uint8 * rh["last"][2]).from_address(h_out))
-        own["host_equals_device_path"] = host_body == body
-        del host_body
+        if world == 1:
+            host_body = bytes((C.c_uint8 * rh["last"][2]).from_address(h_out))
+            own["host_equals_device_path"] = host_body == body
+            del host_body
+        else:
+            own["host_equals_device_path"] = None       # N > 1: rank 0 compares the shared stream as a whole below
         if binp:
             tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
             path = os.path.join(tmp, "lbz_bench_own_%d.raw" % os.getpid())
@@ -550,7 +567,6 @@ def run_ours(a):
             dist.all_gather_object(allv, own)
             if rank == 0:
                 verified["bit_exact_vs_reference_cli_every_rank"] = all(v.get("bit_exact_vs_reference_cli", False) for v in allv) if binp else None
-                verified["host_equals_device_path_every_rank"] = all(v["host_equals_device_path"] for v in allv)
                 verified["periodic_blocks"] = sum(v["periodic_blocks"] for v in allv)
                 verified["rank_sha256"] = [v["sha256"][:16] for v in allv]
     all_sha = [hashlib.sha256(data).hexdigest()]
@@ -561,6 +577,8 @@ def run_ours(a):
         import bz2
         tables, payloads = sharding.to_host(*rd["last"][4])
         gstream = sharding.assemble_stream(level, tables, payloads, world)
+        # the host leg's product: the shared stream every rank wrote its blocks into during the last step
+        verified["host_stream_equals_gathered_stream"] = bytes(sink.view[: rh["last"][4]]) == gstream
         if not big:
             # chunk i of the job is chunk i // world of rank i % world: de-interleave the
             # decoded stream and compare every rank's part with the sha256 of its input
@@ -606,6 +624,7 @@ def run_ours(a):
 
     if rank != 0:
         if world > 1:
+            sink.close()
             dist.destroy_process_group()
         return
 
@@ -634,10 +653,13 @@ def run_ours(a):
                    "chunks_per_gpu": nchunks, "blocks": len(recs), "batches_per_step": (nchunks + eng_chunks - 1) // eng_chunks,
                    "l2": "inputs (%d MB) and working set (%.1f GB) larger than L2" % (a.size_mb, dev_bytes / 1e9),
                    "generator": "tests/synth.py (text: seed 0x5EED, stream offset = rank; > 100 MB: consecutive 100 MB streams)",
-                   "gather": ("device leg: NCCL gather of block bitstreams + block table to rank 0; host leg: block table only, "
-                              "payload stays in each rank's pinned host memory") if world > 1 else "none (single GPU)"},
+                   "gather": ("device leg: NCCL gather of block bitstreams + block table into rank 0's HBM; host leg (e2e): "
+                              "one stream-ordered .bz2 assembled inside every timed step in a host buffer shared by the "
+                              "ranks (/dev/shm mapping%s): tables all-gathered, every rank's blocks copied D2H to their "
+                              "stream offsets, header + trailer by rank 0, closing barrier"
+                              % (", CUDA-registered" if sink.registered else ", not registered: staged copies")) if world > 1 else "none (single GPU)"},
         "e2e": {"value": round(e2e, 2), "unit": "MB/s", "ms_per_step": round(ms_e2e, 3),
-                "h2d_bytes_per_step": world * nbytes, "d2h_bytes_per_step": int(world * rh["last"][2]),
+                "h2d_bytes_per_step": world * nbytes, "d2h_bytes_per_step": int(rh["last"][4] - 14) if world > 1 else int(rh["last"][2]),
                 "api": "lbz_compress_chunks (pinned host in/out)"},
         "gpu_launches": int(rd["launches"]),
         "clocks": rd["clocks"],
@@ -660,6 +682,7 @@ def run_ours(a):
     L.lbz_host_free(h_in)
     L.lbz_host_free(h_out)
     if world > 1:
+        sink.close()
         dist.destroy_process_group()
 
 

@@ -129,6 +129,18 @@ int lbz_compress_chunks(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out
 int lbz_compress_chunks_device(lbz_engine *e, const void *d_in, size_t n, void *d_out, size_t out_cap,
                                size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs);
 
+/* Same with HOST input and DEVICE output: the multi-process host sink.  Every rank of a sharded
+   job (chunk i -> rank i mod N) keeps its blocks in HBM until the block tables of
+   all ranks are known, then copies each block to its offset in the ONE stream-ordered output
+   (a host buffer shared between the ranks) with lbz_scatter_to_host: the order key is the
+   reference's (major = chunk, minor = block in chunk), src/compress.c:85-86,238-252. */
+int lbz_compress_chunks_h2d(lbz_engine *e, const uint8_t *in, size_t n, void *d_out, size_t out_cap,
+                            size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs);
+/* count device->host copies: len[i] bytes from d_src + src_off[i] to h_dst + dst_off[i]; returns
+   when all have landed. */
+int lbz_scatter_to_host(lbz_engine *e, const void *d_src, const uint64_t *src_off, void *h_dst,
+                        const uint64_t *dst_off, const uint64_t *len, size_t count);
+
 /* A complete .bz2 stream, bit-identical to `lbzip2 -<level>` of the same
    input: "BZh"+level, blocks, 0x177245385090, combined CRC
    (src/compress.c:290-321, src/encode.h:38).  Returns 0 on success. */

@@ -70,7 +70,7 @@ EXPORTS = [
     "crc_table", "lbz_set_fatal_handler",
     # batch API
     "lbz_engine_create", "lbz_engine_destroy", "lbz_bound", "lbz_compress_chunks",
-    "lbz_compress_chunks_device", "lbz_compress_stream", "lbz_host_alloc", "lbz_host_free",
+    "lbz_compress_chunks_device", "lbz_compress_chunks_h2d", "lbz_scatter_to_host", "lbz_compress_stream", "lbz_host_alloc", "lbz_host_free",
     "lbz_engine_launches", "lbz_engine_last_rounds", "lbz_engine_device_bytes", "lbz_version",
     "lbz_engine_last_ms", "lbz_engine_stage_ms", "lbz_engine_k0_stats",
     # stage hooks
@@ -106,6 +106,10 @@ def load_library():
     L.lbz_compress_chunks.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp, C.POINTER(BlockRec), C.c_size_t, szp]
     L.lbz_compress_chunks_device.restype = C.c_int
     L.lbz_compress_chunks_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp, C.POINTER(BlockRec), C.c_size_t, szp]
+    L.lbz_compress_chunks_h2d.restype = C.c_int
+    L.lbz_compress_chunks_h2d.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp, C.POINTER(BlockRec), C.c_size_t, szp]
+    L.lbz_scatter_to_host.restype = C.c_int
+    L.lbz_scatter_to_host.argtypes = [vp, vp, C.POINTER(C.c_uint64), vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_size_t]
     L.lbz_compress_stream.restype = C.c_int
     L.lbz_compress_stream.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, szp]
     L.lbz_host_alloc.restype = vp
@@ -247,12 +251,24 @@ class Engine:
             raise LbzError("lbz_compress_chunks failed (%d)" % rc)
         return out[: ln.value].tobytes(), [recs[i] for i in range(nr.value)]
 
-    def compress_chunks_ptr(self, in_ptr, n, out_ptr, out_cap, device=False, max_recs=0):
-        """Raw-pointer form (host or device memory); returns (out_len, recs)."""
+    def scatter_to_host(self, d_src, src_off, h_dst, dst_off, lens):
+        """Blocks from device memory to their places in a host buffer (see lbz_scatter_to_host)."""
+        n = len(lens)
+        a = np.ascontiguousarray(src_off, dtype=np.uint64)
+        b = np.ascontiguousarray(dst_off, dtype=np.uint64)
+        c = np.ascontiguousarray(lens, dtype=np.uint64)
+        u64p = C.POINTER(C.c_uint64)
+        rc = self.L.lbz_scatter_to_host(self.h, d_src, a.ctypes.data_as(u64p), h_dst, b.ctypes.data_as(u64p),
+                                        c.ctypes.data_as(u64p), n)
+        if rc:
+            raise LbzError("lbz_scatter_to_host failed (%d)" % rc)
+
+    def compress_chunks_ptr(self, in_ptr, n, out_ptr, out_cap, device=False, max_recs=0, h2d=False):
+        """Raw-pointer form (host or device memory; h2d: host in, device out); returns (out_len, recs)."""
         maxrec = max_recs or 2 * (n // self.mbs + 2)
         recs = (BlockRec * maxrec)()
         ln, nr = C.c_size_t(0), C.c_size_t(0)
-        fn = self.L.lbz_compress_chunks_device if device else self.L.lbz_compress_chunks
+        fn = self.L.lbz_compress_chunks_h2d if h2d else (self.L.lbz_compress_chunks_device if device else self.L.lbz_compress_chunks)
         rc = fn(self.h, in_ptr, n, out_ptr, out_cap, C.byref(ln), recs, maxrec, C.byref(nr))
         if rc:
             raise LbzError("compress failed (%d)" % rc)
@@ -353,6 +369,7 @@ class Decoder:
 
     def __init__(self, device=0, max_blocks=64, in_cap=1 << 24, out_cap=0):
         self.L = load_library()
+        self.max_blocks = max_blocks
         self.h = self.L.lbz_decoder_create(device, max_blocks, in_cap, out_cap)
         if not self.h:
             raise LbzError("lbz_decoder_create failed (no usable GPU? this package has no CPU path)")

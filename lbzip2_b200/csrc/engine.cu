@@ -521,10 +521,11 @@ struct SubBatch {
 };
 
 static int super_batch(lbz_engine *e, const uint8_t *src, size_t len, uint8_t *dst, size_t dst_cap, bool on_device,
-                       uint64_t raw_base, size_t *written, lbz_block_rec *recs, size_t max_recs, size_t *nrec) {
+                       bool dst_on_device, uint64_t raw_base, size_t *written, lbz_block_rec *recs, size_t max_recs,
+                       size_t *nrec) {
   const size_t mbs = e->g.mbs;
   const size_t nc = (len + mbs - 1) / mbs;
-  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (!e->sib || nc < 2) {
     size_t total;
     if (lane_run(e, src, on_device, len, nullptr, &total)) return -1;
@@ -611,7 +612,7 @@ static int super_batch(lbz_engine *e, const uint8_t *src, size_t len, uint8_t *d
 }
 
 static int compress_any(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, bool on_device,
-                        size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
+                        bool dst_on_device, size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
   if (!e) return -1;
   ENG_CHECK(cudaSetDevice(e->device));
   const size_t batch_bytes = (size_t)e->total_chunks * e->g.mbs;
@@ -624,7 +625,7 @@ static int compress_any(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out
   for (size_t pos = 0; pos < n; pos += batch_bytes) {
     const size_t len = (n - pos < batch_bytes) ? n - pos : batch_bytes;
     size_t written = 0;
-    const int rc = super_batch(e, in + pos, len, out + o, out_cap - o, on_device, pos, &written, recs, max_recs, &nrec);
+    const int rc = super_batch(e, in + pos, len, out + o, out_cap - o, on_device, dst_on_device, pos, &written, recs, max_recs, &nrec);
     if (rc) return rc;
     o += written;
   }
@@ -636,13 +637,35 @@ static int compress_any(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out
 
 extern "C" int lbz_compress_chunks(lbz_engine *e, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
                                    size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
-  return compress_any(e, in, n, out, out_cap, false, out_len, recs, max_recs, num_recs);
+  return compress_any(e, in, n, out, out_cap, false, false, out_len, recs, max_recs, num_recs);
+}
+
+// Host input (pinned memory gives the full link rate), DEVICE output: what a multi-process writer
+// uses -- the blocks stay in HBM until the stream offsets of all ranks' blocks are known, then
+// lbz_scatter_to_host puts every block at its place in the one output stream.
+extern "C" int lbz_compress_chunks_h2d(lbz_engine *e, const uint8_t *in, size_t n, void *d_out, size_t out_cap,
+                                       size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
+  if (e && out_cap < lbz_bound(n)) { fprintf(stderr, "lbzip2_b200: device output buffer too small\n"); return -2; }
+  return compress_any(e, in, n, reinterpret_cast<uint8_t *>(d_out), out_cap, false, true, out_len, recs, max_recs, num_recs);
+}
+
+extern "C" int lbz_scatter_to_host(lbz_engine *e, const void *d_src, const uint64_t *src_off, void *h_dst,
+                                   const uint64_t *dst_off, const uint64_t *len, size_t count) {
+  if (!e) return -1;
+  ENG_CHECK(cudaSetDevice(e->device));
+  const uint8_t *s = reinterpret_cast<const uint8_t *>(d_src);
+  uint8_t *d = reinterpret_cast<uint8_t *>(h_dst);
+  for (size_t i = 0; i < count; i++)
+    if (len[i]) ENG_CHECK(cudaMemcpyAsync(d + dst_off[i], s + src_off[i], len[i], cudaMemcpyDeviceToHost, (i & 1) ? e->st_copy : e->st));
+  ENG_CHECK(cudaStreamSynchronize(e->st));
+  ENG_CHECK(cudaStreamSynchronize(e->st_copy));
+  return 0;
 }
 
 extern "C" int lbz_compress_chunks_device(lbz_engine *e, const void *d_in, size_t n, void *d_out, size_t out_cap,
                                           size_t *out_len, lbz_block_rec *recs, size_t max_recs, size_t *num_recs) {
   if (e && out_cap < lbz_bound(n)) { fprintf(stderr, "lbzip2_b200: device output buffer too small\n"); return -2; }
-  return compress_any(e, reinterpret_cast<const uint8_t *>(d_in), n, reinterpret_cast<uint8_t *>(d_out), out_cap, true,
+  return compress_any(e, reinterpret_cast<const uint8_t *>(d_in), n, reinterpret_cast<uint8_t *>(d_out), out_cap, true, true,
                       out_len, recs, max_recs, num_recs);
 }
 

@@ -102,11 +102,16 @@ static void ub_timers_collect(lbz_decoder *d);
 // Results are those of k_ub_chain (same tables, same rules); tests/test_gpu_unbz.py checks both.
 #define CH_THREADS 128u
 __device__ __forceinline__ uint32_t ch_bswap(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+__device__ __forceinline__ uint32_t ch_lds_u8(uint32_t addr) {       // addr: 32-bit shared-window address
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 
 __global__ void __launch_bounds__(CH_THREADS)
 k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, uint32_t nblk,
             const uint8_t *__restrict__ sel_all, const UbTreeG *__restrict__ tree_all,
-            const uint16_t *__restrict__ l1_all, const uint8_t *__restrict__ mq_all,
+            const uint16_t *__restrict__ l1_all, const uint32_t *__restrict__ ml_all, const uint8_t *__restrict__ mq_all,
             uint64_t *__restrict__ gpos_all, uint8_t *__restrict__ gtree_all, uint32_t *sm_slots) {
   __shared__ __align__(16) uint8_t smq[6 * UB_WSIZE];
   __shared__ uint32_t s_slot;
@@ -138,6 +143,7 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
   uint64_t *gpos = gpos_all + (size_t)b * (UB_MAXGRP + 1u);
   uint8_t *gtree = gtree_all + (size_t)b * (UB_MAXGRP + 1u);
   const uint32_t eob = B.alpha_size - 1u;
+  const uint32_t smq_base = (uint32_t)__cvta_generic_to_shared(smq);
   const uint32_t nsel = B.num_selectors > UB_MAXGRP ? UB_MAXGRP : B.num_selectors;   // src/decode.c:631-632
   uint32_t slp = 0;                                  // selector list, 4 bits per entry: tree number or error code
   for (uint32_t t = 0; t < 6u; t++) slp |= (t < B.num_trees ? ((uint32_t)tree_all[(size_t)b * 6u + t].status & 15u) : 0u) << (4u * t);
@@ -158,44 +164,63 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
     if (writer) { gpos[g] = pos; gtree[g] = (uint8_t)t; }
     const UbTreeG &T = tree_all[(size_t)b * 6u + t];
     const uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
-    const uint8_t *mq = smq + t * UB_WSIZE;
+    const uint32_t *ml = ml_all + ((size_t)b * 6u + t) * UB_WSIZE;
     bool done = false;
 
     if ((pos >> 5) + 36u <= nwords) {
-      // lean window reader: a whole group (50 codes of at most 20 bits) lies inside the input
+      // lean window reader: a whole group (50 codes of at most 20 bits) lies inside the input.
+      // hi:lo = the 64 bits at the word of `pos`, bp = bit offset inside hi, nxt = the following word (raw)
       const uint32_t *wp = words + (pos >> 5);
-      const uint32_t bp = (uint32_t)(pos & 31u);
-      uint64_t buf = (((uint64_t)ch_bswap(wp[0]) << 32) | ch_bswap(wp[1])) << bp;
-      uint32_t avail = 64u - bp;                     // valid bits at the top of buf; the rest is zero
+      uint32_t bp = (uint32_t)(pos & 31u);
+      uint32_t hi = ch_bswap(wp[0]), lo = ch_bswap(wp[1]);
       wp += 2;
       uint32_t nxt = *wp;
-      uint32_t rem = 50u;
+      const uint32_t tb = smq_base + t * UB_WSIZE;
+      // Phase 1, "blind": table steps while even a four-code entry cannot overshoot the group.  Only
+      // the bit position is carried from step to step (funnel shift, one shared-memory byte, add);
+      // the code count and the OR of the entries' flag bits ride along and are looked at afterwards.
+      const uint32_t hi0 = hi, lo0 = lo, bp0 = bp, nxt0 = nxt;
+      const uint32_t *const wp0 = wp;
+      uint32_t cnt = 0, orq = 0;
+      do {
+        const uint32_t win = __funnelshift_l(lo, hi, bp);
+        const uint32_t q = ch_lds_u8(tb + (win >> (32u - UB_WBITS)));
+        orq |= q;
+        cnt += q >> 4;
+        bp += q & 15u;
+        if (bp >= 32u) { bp -= 32u; hi = lo; lo = ch_bswap(nxt); wp++; nxt = *wp; }
+      } while (cnt <= 46u);
+      uint32_t rem;
+      if (orq & 0x80u) {                               // an entry needs care (end of block, or a code longer than the window):
+        hi = hi0; lo = lo0; bp = bp0; nxt = nxt0; wp = wp0;   // walk this group again, one careful step at a time
+        rem = 50u;
+      } else {
+        rem = 50u - cnt;                               // 0..3 codes left
+      }
       while (rem) {
-        const uint32_t idx = (uint32_t)(buf >> (64u - UB_WBITS));
-        const uint32_t q = mq[idx];
+        // careful steps (the last codes of a group; a whole group when an entry was flagged): the full
+        // table entry tells how far each of its codes reaches (k_ub_tree_multi)
+        const uint32_t win = __funnelshift_l(lo, hi, bp);
+        const uint32_t e = ml[win >> (32u - UB_WBITS)];
+        const uint32_t cnt1 = (e >> 4) & 7u;
         uint32_t len;
-        if (rem >= 4u && !(q & 0x80u)) {             // common case: all codes of the entry, no end of block
-          len = q & 15u;
-          rem -= q >> 4;
-        } else {                                     // one code: the last ones of a group, long codes, end of block
-          const uint32_t x = l1[idx];
-          uint32_t s;
-          if (x) { s = x >> 5; len = x & 31u; } else s = ub_canon_decode(T, (uint32_t)(buf >> 44), &len);
+        if (cnt1) {
+          uint32_t take = cnt1 < rem ? cnt1 : rem;
+          const uint32_t eobk = e >> 24;
+          if (eobk && eobk <= take) { take = eobk; done = true; }
+          len = (e >> (4u + 4u * take)) & 15u;
+          rem -= take;
+        } else {                                       // a code longer than the window
+          const uint32_t s1 = ub_canon_decode(T, win >> 12, &len);
           rem -= 1u;
-          if (s == eob) done = true;
+          if (s1 == eob) done = true;
         }
-        buf <<= len;
-        avail -= len;
-        if (avail <= 32u) {
-          buf |= (uint64_t)ch_bswap(nxt) << (32u - avail);
-          avail += 32u;
-          wp++;
-          nxt = *wp;
-        }
+        bp += len;
+        if (bp >= 32u) { bp -= 32u; hi = lo; lo = ch_bswap(nxt); wp++; nxt = *wp; }
         if (done) break;
       }
       nsym += 50u - rem;
-      pos = ((uint64_t)(wp - words) << 5) - avail;
+      pos = ((uint64_t)(wp - words - 2) << 5) + bp;
     } else {
       bool eof = !ub_bits_seek(br, pos);
       for (uint32_t j = 0; j < 50u && !eof && !done; j++) {
@@ -238,7 +263,7 @@ static int ub_chain_version() {
     if (slots_) {                                                                                   \
       UB_CUDA(cudaMemsetAsync(slots_, 0, 256 * sizeof(uint32_t), ub_stream(d)));                    \
       k_ub_chain2<<<(nblk), CH_THREADS, 0, ub_stream(d)>>>((d)->d_words, (nwords), (d)->d_blk, (nblk), (d)->d_sel, (d)->d_tree, \
-                                                            (d)->d_l1, (d)->d_mq, (d)->d_gpos, (d)->d_gtree, slots_);  \
+                                                            (d)->d_l1, (d)->d_ml, (d)->d_mq, (d)->d_gpos, (d)->d_gtree, slots_);  \
       cudaError_t le_ = cudaGetLastError();                                                         \
       if (le_ != cudaSuccess) return ub_cuda_fail(le_, "k_ub_chain2", __LINE__);                    \
       ub_count_launch(d);                                                                           \

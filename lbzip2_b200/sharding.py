@@ -168,6 +168,129 @@ class BlockGatherer:
         return tables, payloads
 
 
+def place_blocks(tables, world, header=4):
+    """Stream offsets of every rank's blocks in the one output stream.
+
+    tables[r]: int64 [nblocks_r, 3] rows (local chunk, out_len, crc) in rank r's local order.
+    Stream order is the reference's (src/compress.c:85-86,238-252): major = chunk of the job
+    (local chunk * world + rank), minor = block within the chunk.  Returns (offs, total, cc):
+    offs[r] = int64 array of byte offsets of rank r's blocks (the 4-byte stream header comes
+    first), total = stream length without the 10-byte trailer, cc = combined CRC (src/encode.h:38)."""
+    keys, lens, crcs, owner = [], [], [], []
+    for r in range(world):
+        t = np.asarray(tables[r], dtype=np.int64).reshape(-1, 3)
+        if not len(t):
+            continue
+        chunk = t[:, 0] * world + r
+        # minor: index of the block inside its chunk (blocks of a chunk are consecutive rows)
+        first = np.concatenate(([True], chunk[1:] != chunk[:-1]))
+        start = np.maximum.accumulate(np.where(first, np.arange(len(t)), 0))
+        minor = np.arange(len(t)) - start
+        keys.append(chunk * 4 + minor)
+        lens.append(t[:, 1])
+        crcs.append(t[:, 2])
+        owner.append(np.full(len(t), r, dtype=np.int64))
+    if not keys:
+        return [np.zeros(0, np.int64) for _ in range(world)], header, 0
+    keys, lens, crcs, owner = (np.concatenate(x) for x in (keys, lens, crcs, owner))
+    order = np.argsort(keys, kind="stable")
+    off_sorted = header + np.concatenate(([0], np.cumsum(lens[order])[:-1]))
+    off = np.empty_like(off_sorted)
+    off[order] = off_sorted
+    offs = [off[owner == r] for r in range(world)]
+    cc = 0
+    for c in crcs[order].tolist():
+        cc = (((cc << 1) & 0xFFFFFFFF) ^ (cc >> 31) ^ (c & 0xFFFFFFFF) ^ 0xFFFFFFFF) & 0xFFFFFFFF
+    return offs, int(header + lens.sum()), cc
+
+
+class SharedStream:
+    """The ONE stream-ordered .bz2 of a sharded job in host memory: a /dev/shm file that every rank
+    of the node maps, registered with CUDA where possible so that device->host copies land in it
+    directly.  Per step: exchange() the block tables (one small all_gather), place_blocks(), every
+    rank scatters its blocks to their offsets (lbz_scatter_to_host), rank 0 adds header and trailer
+    (src/compress.c:290-321); after the closing barrier the file holds the complete stream."""
+
+    def __init__(self, dist, device, path, capacity, max_blocks, register=True):
+        import mmap
+        import os
+        import torch
+        self.dist, self.device = dist, device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.path, self.capacity, self.max_blocks = path, int(capacity), int(max_blocks)
+        if self.rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(self.capacity)
+        dist.barrier()
+        self.fd = os.open(path, os.O_RDWR)
+        self.mm = mmap.mmap(self.fd, self.capacity)
+        import ctypes as C
+        self.ptr = C.addressof(C.c_char.from_buffer(self.mm))
+        self.view = np.frombuffer(self.mm, dtype=np.uint8)
+        self.registered = False
+        if register and str(device) != "cpu":
+            try:
+                rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.capacity, 0)
+                self.registered = int(rc) == 0
+            except Exception:
+                self.registered = False
+        on_gpu = str(device) != "cpu"
+        self.tbuf = torch.zeros((1 + self.max_blocks, 3), dtype=torch.int64, device=device)
+        self.tstage = torch.zeros((1 + self.max_blocks, 3), dtype=torch.int64)
+        self.tall_host = torch.zeros((self.world, 1 + self.max_blocks, 3), dtype=torch.int64)
+        if on_gpu:
+            self.tstage = self.tstage.pin_memory()
+            self.tall_host = self.tall_host.pin_memory()
+        self.tall = torch.zeros((self.world, 1 + self.max_blocks, 3), dtype=torch.int64, device=device)
+
+    def exchange(self, table):
+        """All ranks learn all block tables (fixed-shape all_gather; row 0 = number of blocks)."""
+        import torch
+        nb = int(table.shape[0])
+        if nb > self.max_blocks:
+            raise ValueError("SharedStream capacity exceeded")
+        self.tstage[0, 0] = nb
+        if nb:
+            self.tstage[1:1 + nb] = torch.from_numpy(np.ascontiguousarray(table, dtype=np.int64))
+        self.tbuf.copy_(self.tstage, non_blocking=True)
+        self.dist.all_gather_into_tensor(self.tall, self.tbuf) if hasattr(self.dist, "all_gather_into_tensor") and str(self.device) != "cpu" \
+            else self.dist.all_gather(list(self.tall.unbind(0)), self.tbuf)
+        self.tall_host.copy_(self.tall)
+        a = self.tall_host.numpy()
+        return [a[r, 1:1 + int(a[r, 0, 0])] for r in range(self.world)]
+
+    def finish(self, level, total, cc):
+        """Rank 0: stream header and trailer around the blocks; everyone: closing barrier."""
+        if self.rank == 0:
+            if total + 10 > self.capacity:
+                raise ValueError("SharedStream too small")
+            self.view[0:4] = np.frombuffer(b"BZh" + bytes([ord("0") + level]), dtype=np.uint8)
+            self.view[total:total + 10] = np.frombuffer(bytes([0x17, 0x72, 0x45, 0x38, 0x50, 0x90]) + cc.to_bytes(4, "big"), dtype=np.uint8)
+        self.dist.barrier()
+        return total + 10
+
+    def close(self):
+        import os
+        import torch
+        if self.registered:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self.ptr)
+            except Exception:
+                pass
+        self.view = None
+        try:
+            self.mm.close()
+        except BufferError:
+            pass
+        os.close(self.fd)
+        self.dist.barrier()
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 # ----------------------------------------------------------------------------------------------
 # Decompression: the blocks of ONE .bz2 file over several decoders / GPUs.
 #
@@ -192,6 +315,12 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
     Status and surviving output follow lbz_decompress_stream."""
     hits = dec.scan(z)
     mine = hits[rank::world]
+    cap_blocks = getattr(dec, "max_blocks", None)
+    if cap_blocks is not None and len(mine) > cap_blocks:
+        # every candidate of the share stays resident between decode_at and emit_at (the framing walk
+        # over ALL ranks' tables decides which candidates are blocks): size the decoder for the share
+        raise ValueError("decoder holds %d blocks, this rank's share of the file has %d candidates: create the "
+                         "Decoder with max_blocks >= ceil(candidates / world)" % (cap_blocks, len(mine)))
     rows = [_row(b) for b in dec.decode_at(z, mine)]
     every = [None] * world
     if world > 1:

@@ -42,8 +42,23 @@ def _worker(rank, world, path, level, data, q):
     for _ in range(2):
         t2, p2 = gth.gather(table, torch.from_numpy(payload.copy()))
     t3, p3 = gth.gather(table, torch.from_numpy(payload.copy()), tables_only=True)
+    # the host sink of the N>1 end-to-end leg: every rank puts its own blocks at their stream
+    # offsets in one shared mapping (on GPUs the copies are lbz_scatter_to_host from HBM)
+    sink = sharding.SharedStream(dist, "cpu", path + ".stream", 2_000_000, max_blocks=64, register=False)
+    shared = None
+    for _ in range(2):
+        every = sink.exchange(table)
+        offs, total, cc = sharding.place_blocks(every, world)
+        src = np.concatenate(([0], np.cumsum(table[:, 1])))
+        for k in range(len(table)):
+            sink.view[offs[rank][k]:offs[rank][k] + table[k, 1]] = payload[src[k]:src[k + 1]]
+        end = sink.finish(level, total, cc)
+        if rank == 0:
+            shared = bytes(sink.view[:end])
+    sink.close()
     if rank == 0:
         stream = sharding.assemble_stream(level, tables, payloads, world)
+        assert shared == stream
         assert sharding.assemble_stream(level, *sharding.to_host(t2, p2), world) == stream
         assert all(np.array_equal(a.numpy(), b.numpy()) for a, b in zip(t2, t3)) and p3 == [None] * world
         q.put(stream)
