@@ -402,15 +402,19 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
              const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
              uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
              uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride,
-             uint32_t xpose) {
+             uint32_t xpose, uint32_t nb) {
   extern __shared__ __align__(16) unsigned char radix_smem_raw[];
   TextSmem2 &S = *reinterpret_cast<TextSmem2 *>(radix_smem_raw);
   constexpr int THREADS = 512, ITEMS = 8;
   constexpr uint32_t RTILE = THREADS * ITEMS;
   const uint32_t rtiles = g.S1 / RTILE;
-  // xpose: grid = (blocks, tiles) -- CTAs are dispatched x-fastest, so consecutive CTAs then work
-  // on different blocks and a tile's predecessor has usually published its inclusive prefix
-  const uint32_t b = xpose ? blockIdx.x : blockIdx.y, tile = xpose ? blockIdx.y : blockIdx.x;
+  // xpose: grid = (blocks of a group, tiles, groups) -- CTAs are dispatched x-fastest, so consecutive
+  // CTAs then work on different blocks and a tile's predecessor has usually published its inclusive
+  // prefix.  The group is the whole batch except for the pass that gathers from the text (MODE 1):
+  // there 32 blocks share the resident CTAs, so that their text (29 MB) stays in L2 -- spread over
+  // all blocks of the batch every gathered sector came from DRAM (5.2 GB per launch instead of 0.8).
+  const uint32_t b = xpose ? blockIdx.z * gridDim.x + blockIdx.x : blockIdx.y, tile = xpose ? blockIdx.y : blockIdx.x;
+  if (b >= nb) return;
   const uint32_t n = meta[b].n;
   const uint32_t cnt = LIST ? meta[b].ul : n;
   const uint32_t tbase = tile * RTILE;
@@ -932,10 +936,17 @@ k_text_pass3(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
 //   * full tiles (all but the last of a block) run a specialisation without bounds tests;
 //   * CTAs are dispatched block-fastest (grid = blocks x tiles), so a tile's predecessor has
 //     usually published its inclusive prefix and the look-back ends after one or two steps.
+// Counter rows are skewed by two words per 32 digits (P4_IDX): the scan step reads eight consecutive
+// digits per lane, which in a flat row is a stride of 32 B (4-way bank conflicts on 64-bit accesses;
+// the first build of this kernel was bound by the shared-memory pipe, profiles/r02_ncu_text_pass4.txt);
+// with the skew the 16 lanes of a half-warp cover all 32 banks, and single digits keep their low
+// five bits as the bank, which is what spreads the letters of a text over the banks when ranking.
+#define P4_ROW 272u
+#define P4_IDX(d) ((d) + (((d) >> 5) << 1))
 struct Pass4Smem {
   uint2 buf[4096 + 2];
-  uint32_t wcnt[16][256];
-  uint32_t hsum[2][256];
+  uint32_t wcnt[16][P4_ROW];
+  uint32_t hsum[2][P4_ROW];
   uint32_t dstart[256];
   uint32_t delta[256];
   unsigned long long full;
@@ -997,36 +1008,39 @@ __device__ __forceinline__ void pass4_body(Pass4Smem &S, const uint8_t *__restri
     const uint32_t dg = RR ? ((dgp[q >> 2] >> (8 * (q & 3))) & 0xFFu) : ((key[q] >> shift) & 0xFFu);
     const uint32_t digit = valid ? dg : 0x100u;
     const uint32_t mask = __match_any_sync(0xffffffffu, digit);
+    const uint32_t pd = P4_IDX(dg);
     uint32_t base = 0;
-    if (valid) base = wrow[digit];
+    if (valid) base = wrow[pd];
     __syncwarp();
-    if (valid && (mask & lt) == 0) wrow[digit] = base + __popc(mask);
+    if (valid && (mask & lt) == 0) wrow[pd] = base + __popc(mask);
     __syncwarp();
     rkp[q >> 2] |= (base + __popc(mask & lt)) << (8 * (q & 3));
   }
   __syncthreads();                                           // A: all rows counted, all items in registers
 
   const uint32_t d = tid & 255u, half = tid >> 8;
+  const uint32_t pdd = P4_IDX(d);
   {
     uint32_t run = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) { const uint32_t c = S.wcnt[half * 8 + w][d]; S.wcnt[half * 8 + w][d] = run; run += c; }
-    S.hsum[half][d] = run;
+    for (int w = 0; w < 8; w++) { const uint32_t c = S.wcnt[half * 8 + w][pdd]; S.wcnt[half * 8 + w][pdd] = run; run += c; }
+    S.hsum[half][pdd] = run;
   }
   __syncthreads();                                           // B: column sums ready
 
   uint32_t total_d = 0;
   uint32_t *mine = tstat + ((size_t)stat_row + tile) * 256 + d;
   if (half == 0) {
-    total_d = S.hsum[0][d] + S.hsum[1][d];
+    total_d = S.hsum[0][pdd] + S.hsum[1][pdd];
     st_volatile_u32(mine, (tile == 0 ? TS_FLAG_PREFIX : TS_FLAG_AGG) | ep | total_d);
   }
   {   // every warp: exclusive scan of the 256 digit totals, 8 digits per lane, folded into its own row
+    const uint32_t pl = P4_IDX(lane * 8u);                             // this lane's eight digits: one skewed, contiguous run
     uint32_t run = 0;
 #pragma unroll
     for (int hq = 0; hq < 4; hq++) {
-      const uint2 a = *reinterpret_cast<const uint2 *>(&S.hsum[0][lane * 8 + 2 * hq]);
-      const uint2 c = *reinterpret_cast<const uint2 *>(&S.hsum[1][lane * 8 + 2 * hq]);
+      const uint2 a = *reinterpret_cast<const uint2 *>(&S.hsum[0][pl + 2 * hq]);
+      const uint2 c = *reinterpret_cast<const uint2 *>(&S.hsum[1][pl + 2 * hq]);
       run += a.x + a.y + c.x + c.y;
     }
     uint32_t e = warp_incl_sum(run) - run;                               // start of digit lane*8 inside the tile
@@ -1034,14 +1048,14 @@ __device__ __forceinline__ void pass4_body(Pass4Smem &S, const uint8_t *__restri
     const bool pub = (lane >> 2) == warp;                                // warps 0..7: the 32 digits their threads look back for
 #pragma unroll
     for (int hq = 0; hq < 4; hq++) {
-      const uint2 a = *reinterpret_cast<const uint2 *>(&S.hsum[0][lane * 8 + 2 * hq]);
-      const uint2 c = *reinterpret_cast<const uint2 *>(&S.hsum[1][lane * 8 + 2 * hq]);
+      const uint2 a = *reinterpret_cast<const uint2 *>(&S.hsum[0][pl + 2 * hq]);
+      const uint2 c = *reinterpret_cast<const uint2 *>(&S.hsum[1][pl + 2 * hq]);
       const uint32_t e0 = e, e1 = e0 + a.x + c.x;
       e = e1 + a.y + c.y;
       if (pub) *reinterpret_cast<uint2 *>(&S.dstart[lane * 8 + 2 * hq]) = make_uint2(e0, e1);
-      uint2 w = *reinterpret_cast<const uint2 *>(&wrow[lane * 8 + 2 * hq]);
+      uint2 w = *reinterpret_cast<const uint2 *>(&wrow[pl + 2 * hq]);
       w.x += e0 + (hi ? a.x : 0u); w.y += e1 + (hi ? a.y : 0u);
-      *reinterpret_cast<uint2 *>(&wrow[lane * 8 + 2 * hq]) = w;
+      *reinterpret_cast<uint2 *>(&wrow[pl + 2 * hq]) = w;
     }
   }
   __syncwarp();
@@ -1058,7 +1072,7 @@ __device__ __forceinline__ void pass4_body(Pass4Smem &S, const uint8_t *__restri
   for (int q = 0; q < ITEMS; q++) {
     if (FULL || q * 32u < lim) {
       const uint32_t digit = RR ? ((dgp[q >> 2] >> (8 * (q & 3))) & 0xFFu) : ((key[q] >> shift) & 0xFFu);
-      const uint32_t slot = wrow[digit] + ((rkp[q >> 2] >> (8 * (q & 3))) & 0xFFu);
+      const uint32_t slot = wrow[P4_IDX(digit)] + ((rkp[q >> 2] >> (8 * (q & 3))) & 0xFFu);
       stage[slot] = make_uint2(key[q], val[q]);
     }
   }
@@ -1134,9 +1148,10 @@ k_text_pass4(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
     bulk_g2s(&S.buf[0], src + (off + tbase - shift1), bytes, &S.full);
   }
   {
-    uint4 *z = reinterpret_cast<uint4 *>(&S.wcnt[tid >> 5][0]);
+    uint4 *z = reinterpret_cast<uint4 *>(&S.wcnt[tid >> 5][0]);             // P4_ROW = 272 words = 68 uint4
     z[lane] = make_uint4(0u, 0u, 0u, 0u);
     z[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < 4) z[lane + 64] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (MODE == 0) {
     __syncthreads();                                          // the mbarrier is initialised
@@ -1230,9 +1245,12 @@ static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, co
   }
   LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
   const uint32_t xp = tp_xpose();
-  const dim3 grid = xp ? dim3(nb, g.S1 / 4096u) : dim3(g.S1 / 4096u, nb);
+  static int ggrp = -1;
+  if (ggrp < 0) { const char *ev = getenv("LBZ_TP_GATHER_GROUP"); ggrp = ev ? atoi(ev) : 32; if (ggrp < 1) ggrp = 1; }
+  const uint32_t gsz = (MODE == 1) ? min(nb, (uint32_t)ggrp) : nb;
+  const dim3 grid = xp ? dim3(gsz, g.S1 / 4096u, (nb + gsz - 1) / gsz) : dim3(g.S1 / 4096u, nb);
   k_text_pass2<MODE, LAST, MINB><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
-                                                                        shift, epoch, err, koff, 256u, xp);
+                                                                        shift, epoch, err, koff, 256u, xp, nb);
   return 0;
 }
 template <int MODE, int LAST>
@@ -1262,7 +1280,7 @@ static int launch_list_pass(uint32_t max_count, uint32_t nb, cudaStream_t st, co
   const uint32_t xp = tp_xpose();
   const dim3 grid = xp ? dim3(nb, tiles) : dim3(tiles, nb);
   k_text_pass2<0, 0, 3, 1><<<grid, 512, sizeof(TextSmem2), st>>>(
-      g, meta, nullptr, src, dst, nullptr, tstat, gbase, shift, epoch, err, 0u, gstride, xp);
+      g, meta, nullptr, src, dst, nullptr, tstat, gbase, shift, epoch, err, 0u, gstride, xp, nb);
   return 0;
 }
 

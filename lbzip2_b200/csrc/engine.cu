@@ -105,6 +105,8 @@ struct lbz_engine {
   LbzBlockMeta *h_meta = nullptr;
   uint32_t *h_counters = nullptr;   // [0..1] sort counters, [2] packed total
   std::vector<void *> allocs;
+  struct PendingAlloc { void **pp; size_t bytes; };
+  std::vector<PendingAlloc> pending;
   // Two-lane mode: large engines are split into two half-capacity lanes (this
   // object + `sib`) that work on disjoint chunk ranges of a batch on their own
   // streams, driven by two host threads, so that the latency-bound kernels of one
@@ -133,18 +135,29 @@ struct lbz_engine {
     }                                                                             \
   } while (0)
 
+// Device arrays are carved out of ONE allocation per engine (one cudaMalloc instead of forty: engine
+// set-up is what a short CLI run pays first): dev_alloc() only records the request, dev_commit()
+// allocates the slab and hands out 256-byte aligned pieces with 256 bytes of slack behind each.
 template <class T>
 static int dev_alloc(lbz_engine *e, T **p, size_t count) {
+  const size_t bytes = (count * sizeof(T) + 256 + 255) & ~(size_t)255;
+  e->pending.push_back({reinterpret_cast<void **>(p), bytes});
+  return 0;
+}
+static int dev_commit(lbz_engine *e) {
+  size_t total = 0;
+  for (const auto &r : e->pending) total += r.bytes;
   void *q = nullptr;
-  const size_t bytes = count * sizeof(T) + 256;
-  cudaError_t err = cudaMalloc(&q, bytes);
+  cudaError_t err = cudaMalloc(&q, total ? total : 256);
   if (err != cudaSuccess) {
-    fprintf(stderr, "lbzip2_b200: cudaMalloc(%zu) failed: %s\n", bytes, cudaGetErrorString(err));
+    fprintf(stderr, "lbzip2_b200: cudaMalloc(%zu) failed: %s\n", total, cudaGetErrorString(err));
     return -1;
   }
   e->allocs.push_back(q);
-  e->dev_bytes += bytes;
-  *p = reinterpret_cast<T *>(q);
+  e->dev_bytes += total;
+  uint8_t *base = reinterpret_cast<uint8_t *>(q);
+  for (const auto &r : e->pending) { *r.pp = base; base += r.bytes; }
+  e->pending.clear();
   return 0;
 }
 
@@ -239,6 +252,7 @@ static lbz_engine *engine_create_mbs(int device, uint32_t mbs, int max_chunks) {
   rc |= dev_alloc(e, &e->d_packed2, lbz_bound((size_t)e->max_chunks * g.mbs));
   rc |= cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess;
   rc |= dev_alloc(e, &e->d_out_off, NB);
+  rc |= dev_commit(e);
   rc |= cudaHostAlloc((void **)&e->h_chunk_len, e->max_chunks * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess;
   rc |= cudaHostAlloc((void **)&e->h_meta, NB * sizeof(LbzBlockMeta), cudaHostAllocDefault) != cudaSuccess;
   rc |= cudaHostAlloc((void **)&e->h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess;
@@ -989,17 +1003,20 @@ extern "C" int collect(struct encoder_state *s, const uint8_t *buf, size_t *buf_
 // every encode() queues its staged raw bytes and sleeps; a dispatcher thread
 // collects what arrives within a short window (or until the batch engine is
 // full), pushes the whole batch through the kernels at once and wakes the
-// callers.  `LBZIP2_B200_BATCH` = chunks per batch (default 64, 0 = no batching:
+// callers.  `LBZIP2_B200_BATCH` = chunks per batch (default 32, 0 = no batching:
 // every block runs alone on its pooled context).
 namespace {
 struct BReq { encoder_state *s; int rc; bool done; };
+#define BATCH_DISPATCHERS_MAX 4
 struct Batcher {
   std::mutex mu;
   std::condition_variable cv_req, cv_done;
   std::deque<BReq *> q;
   bool running = false;
+  bool forming = false;                      // one dispatcher at a time gathers a batch; the others run theirs
   int max_batch = -1;
-  std::map<uint32_t, lbz_engine *> eng;      // one batch engine per block size in use
+  int dispatchers = 2;
+  std::map<uint32_t, lbz_engine *> eng[BATCH_DISPATCHERS_MAX];   // per dispatcher: one batch engine per block size in use
 };
 // Deliberately leaked: the dispatcher thread sleeps on these condition variables
 // for the life of the process, and destroying a condition variable that has a
@@ -1063,8 +1080,8 @@ int encode_blocks(lbz_engine *e, std::vector<BReq *> &batch) {
   return 0;
 }
 
-int run_batch(uint32_t mbs_key, std::vector<BReq *> &batch) {
-  lbz_engine *&e = g_batch.eng[mbs_key];
+int run_batch(int who, uint32_t mbs_key, std::vector<BReq *> &batch) {
+  lbz_engine *&e = g_batch.eng[who][mbs_key];
   if (!e) {
     e = engine_create_mbs(g_pool.device, mbs_key, g_batch.max_batch);
     if (!e) return -1;
@@ -1073,10 +1090,15 @@ int run_batch(uint32_t mbs_key, std::vector<BReq *> &batch) {
   return encode_blocks(e, batch);
 }
 
-void batch_worker() {
+// Dispatcher `who` (LBZIP2_B200_DISPATCHERS of them, default 2, each with its own engines): while one
+// batch runs on the device the other dispatcher gathers the next one, so the host work of the
+// scheduler's threads (reading, collect(), transmit(), writing) overlaps the kernels.  For that the
+// scheduler needs more worker threads than one batch holds: -n 64 with the default batch of 32.
+void batch_worker(int who) {
   std::unique_lock<std::mutex> lk(g_batch.mu);
   for (;;) {
-    g_batch.cv_req.wait(lk, [] { return !g_batch.q.empty(); });
+    g_batch.cv_req.wait(lk, [] { return !g_batch.q.empty() && !g_batch.forming; });
+    g_batch.forming = true;
     // gathering window: wait a little for more blocks unless the batch is already full
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(400);
     while ((int)g_batch.q.size() < g_batch.max_batch &&
@@ -1087,8 +1109,10 @@ void batch_worker() {
       if ((*it)->s->max_block_size == level) { batch.push_back(*it); it = g_batch.q.erase(it); }
       else ++it;
     }
+    g_batch.forming = false;
+    g_batch.cv_req.notify_all();                     // another dispatcher may start gathering
     lk.unlock();
-    const int rc = run_batch(level, batch);
+    const int rc = run_batch(who, level, batch);
     lk.lock();
     for (BReq *r : batch) { if (rc) r->rc = rc; r->done = true; }
     g_batch.cv_done.notify_all();
@@ -1099,9 +1123,13 @@ int batch_limit() {
   std::lock_guard<std::mutex> lk(g_batch.mu);
   if (g_batch.max_batch < 0) {
     const char *ev = getenv("LBZIP2_B200_BATCH");
-    g_batch.max_batch = ev ? atoi(ev) : 64;
+    g_batch.max_batch = ev ? atoi(ev) : 32;
     if (g_batch.max_batch < 0) g_batch.max_batch = 0;
     if (g_batch.max_batch > 1024) g_batch.max_batch = 1024;
+    const char *dv = getenv("LBZIP2_B200_DISPATCHERS");
+    g_batch.dispatchers = dv ? atoi(dv) : 2;
+    if (g_batch.dispatchers < 1) g_batch.dispatchers = 1;
+    if (g_batch.dispatchers > BATCH_DISPATCHERS_MAX) g_batch.dispatchers = BATCH_DISPATCHERS_MAX;
   }
   return g_batch.max_batch;
 }
@@ -1114,9 +1142,12 @@ extern "C" size_t encode(struct encoder_state *s, uint32_t *crc) {
     BReq r{s, 0, false};
     {
       std::unique_lock<std::mutex> lk(g_batch.mu);
-      if (!g_batch.running) { g_batch.running = true; std::thread(batch_worker).detach(); }
+      if (!g_batch.running) {
+        g_batch.running = true;
+        for (int w = 0; w < g_batch.dispatchers; w++) std::thread(batch_worker, w).detach();
+      }
       g_batch.q.push_back(&r);
-      g_batch.cv_req.notify_one();
+      g_batch.cv_req.notify_all();
       g_batch.cv_done.wait(lk, [&] { return r.done; });
     }
     if (r.rc) die("encode: batched kernel pipeline failed");

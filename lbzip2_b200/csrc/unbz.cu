@@ -101,6 +101,7 @@ static void ub_timers_collect(lbz_decoder *d);
 //   * the selector list is a register of 4-bit fields (no local-memory array).
 // Results are those of k_ub_chain (same tables, same rules); tests/test_gpu_unbz.py checks both.
 #define CH_THREADS 128u
+#define CH_DBG_BLOCKS 1024u
 __device__ __forceinline__ uint32_t ch_bswap(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 __device__ __forceinline__ uint32_t ch_lds_u8(uint32_t addr) {       // addr: 32-bit shared-window address
   uint32_t v;
@@ -125,13 +126,12 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
     uint4 *dst = reinterpret_cast<uint4 *>(smq);
     for (uint32_t i = tid; i < ntrees * (UB_WSIZE / 16u); i += CH_THREADS) dst[i] = src[i];
   }
-  if (tid == 0) {
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    s_slot = atomicAdd(&sm_slots[smid & 255u], 1u);
-  }
+  uint32_t smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (tid == 0) s_slot = atomicAdd(&sm_slots[smid & 255u], 1u);
   __syncthreads();
   if ((tid >> 5) != (s_slot & 3u)) return;
+  const long long t_start = clock64();
   // every lane of the walking warp computes the same walk; `zero` is 0 but opaque to the
   // compiler, which keeps the chain in vector registers
   uint32_t zero;
@@ -243,14 +243,38 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
     B.ngrp = g;
     B.end_bit = pos;
     B.status = status;
+    if (b < CH_DBG_BLOCKS) {                         // per-block walk statistics (LBZ_CHAIN_DEBUG=1 prints them)
+      uint32_t *dbg = sm_slots + 256u + 4u * b;
+      dbg[0] = smid; dbg[1] = s_slot; dbg[2] = (uint32_t)((clock64() - t_start) >> 10); dbg[3] = g;
+    }
   }
 }
 
 static uint32_t *ub_sm_slots(int device) {
   static uint32_t *slots[64] = {};
   if (device < 0 || device >= 64) return nullptr;
-  if (!slots[device] && cudaMalloc((void **)&slots[device], 256 * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+  if (!slots[device] && cudaMalloc((void **)&slots[device], (256 + 4 * CH_DBG_BLOCKS) * sizeof(uint32_t)) != cudaSuccess) return nullptr;
   return slots[device];
+}
+static void ub_chain_debug_print(uint32_t *d_slots, uint32_t nblk, cudaStream_t st) {
+  static int on = -1;
+  if (on < 0) on = getenv("LBZ_CHAIN_DEBUG") != nullptr;
+  if (!on) return;
+  const uint32_t n = nblk < CH_DBG_BLOCKS ? nblk : CH_DBG_BLOCKS;
+  static uint32_t h[256 + 4 * CH_DBG_BLOCKS];
+  cudaStreamSynchronize(st);
+  if (cudaMemcpy(h, d_slots, (256 + 4 * n) * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  // blocks alone on their SM vs blocks that shared it: kilo-cycles per group of 50 codes
+  double alone = 0, shared = 0; uint32_t na = 0, ns = 0, mx = 0;
+  for (uint32_t b = 0; b < n; b++) {
+    const uint32_t *e = h + 256 + 4 * b;
+    if (!e[3]) continue;
+    const double per = (double)e[2] * 1024.0 / (double)e[3];
+    if (h[e[0] & 255u] > 1) { shared += per; ns++; } else { alone += per; na++; }
+    if (e[2] > mx) mx = e[2];
+  }
+  fprintf(stderr, "lbzip2_b200: k_ub_chain2: %u blocks alone on an SM: %.0f cycles per group; %u blocks sharing an SM: %.0f cycles per group; "
+          "longest walk %.2f M cycles\n", na, na ? alone / na : 0.0, ns, ns ? shared / ns : 0.0, mx * 1024.0 / 1e6);
 }
 static int ub_chain_version() {
   static int v = -1;
@@ -267,6 +291,7 @@ static int ub_chain_version() {
       cudaError_t le_ = cudaGetLastError();                                                         \
       if (le_ != cudaSuccess) return ub_cuda_fail(le_, "k_ub_chain2", __LINE__);                    \
       ub_count_launch(d);                                                                           \
+      ub_chain_debug_print(slots_, (nblk), ub_stream(d));                                           \
     } else {                                                                                        \
       UB_LAUNCH_SMEM(d, k_ub_chain, (uint64_t)(nblk) * 32u, 32u, ub_chain_smem(), (d)->d_words, (nwords), (d)->d_blk, (nblk), \
                      (d)->d_sel, (d)->d_tree, (d)->d_l1, (d)->d_ml, (d)->d_mq, (d)->d_gpos, (d)->d_gtree);           \
