@@ -430,7 +430,7 @@ extern "C" int lbz_decoder_read(lbz_decoder *d, int array, uint64_t slot, void *
       src = d->d_txt + slot * UB_STRIDE;
       break;
     case LBZ_DA_OUT:
-      if (slot + bytes > d->out_cap) return -1;
+      if (bytes > d->out_cap || slot > d->out_cap - bytes) return -1;
       src = d->d_out + slot;
       break;
     default:

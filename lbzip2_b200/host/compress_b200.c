@@ -44,6 +44,7 @@
 */
 #include "common.h"
 
+#include <assert.h>
 #include <string.h>             /* memcpy() */
 #include <stdio.h>              /* fprintf() */
 #include <time.h>               /* clock_gettime() */
@@ -191,9 +192,32 @@ creatable(void)
 }
 
 
+/* ---- -u (src/compress.c:120-198: blocks packed across I/O buffers) --------------------------------
+   The sequential collector is the reference's own: its task graph (src/compress.c, compiled into this
+   binary as `compression_ref`) drives collect()/encode()/transmit() of libbz2b200.so -- collect()
+   decides the block split on the calling thread, encode() calls of the worker threads are pooled
+   into device batches.  With -u every entry of this process forwards to
+   it; the batch tasks below stay idle. */
+#ifdef LBZ_WITH_REF_SEQUENTIAL
+extern const struct process compression_ref;
+#define SEQ (ultra)
+#define REF_TASK(i)                                                                      \
+  static bool can_ref##i(void) { return ultra && compression_ref.tasks[i].ready(); }      \
+  static void do_ref##i(void) { compression_ref.tasks[i].run(); }
+REF_TASK(0)
+REF_TASK(1)
+REF_TASK(2)
+REF_TASK(3)
+#else
+#define SEQ (false)
+#endif
+
+
 static bool
 can_create(void)
 {
+  if (SEQ)
+    return false;
   /* input is waiting, no batch is open and no engine is free: set up another one */
   return !empty(stage_q) && open_slot < 0 && find_slot(B_FREE) < 0 &&
     creatable() >= 0;
@@ -234,6 +258,8 @@ do_create(void)
 static bool
 can_stage(void)
 {
+  if (SEQ)
+    return false;
   if (empty(stage_q) || peek(stage_q)->pos.major != next_stage)
     return false;
   if (open_slot >= 0)
@@ -290,6 +316,8 @@ do_stage(void)
 static bool
 can_launch(void)
 {
+  if (SEQ)
+    return false;
   return launchable() >= 0;
 }
 
@@ -352,6 +380,8 @@ do_launch(void)
 static bool
 can_reorder(void)
 {
+  if (SEQ)
+    return false;
   return !empty(reord_q) && peek(reord_q)->pos.major == order && out_slots > 0;
 }
 
@@ -379,6 +409,10 @@ do_reorder(void)
 static bool
 can_terminate(void)
 {
+#ifdef LBZ_WITH_REF_SEQUENTIAL
+  if (ultra)
+    return compression_ref.finished();
+#endif
   return eof && empty(stage_q) && empty(reord_q) && unsunk == 0 &&
     creating == 0 && out_slots == total_out_slots;
 }
@@ -387,7 +421,15 @@ can_terminate(void)
 static void
 on_input_avail(void *buffer, size_t size)
 {
-  struct in_blk *iblk = XMALLOC(struct in_blk);
+  struct in_blk *iblk;
+
+#ifdef LBZ_WITH_REF_SEQUENTIAL
+  if (ultra) {
+    compression_ref.on_block(buffer, size);
+    return;
+  }
+#endif
+  iblk = XMALLOC(struct in_blk);
 
   iblk->pos.major = next_id++;
   iblk->pos.minor = 0u;
@@ -403,6 +445,12 @@ on_input_avail(void *buffer, size_t size)
 static void
 on_write_complete(void *buffer)
 {
+#ifdef LBZ_WITH_REF_SEQUENTIAL
+  if (ultra) {
+    compression_ref.on_written(buffer);
+    return;
+  }
+#endif
   free(buffer);
 
   sched_lock();
@@ -420,8 +468,16 @@ init(void)
   stat_t0 = now();
   stat_batches = stat_chunks = stat_blocks = 0;
   stat_gpu = stat_stage = stat_copy = 0.0;
+#ifdef LBZ_WITH_REF_SEQUENTIAL
+  if (ultra) {
+    assert(compression_ref.tasks[4].name == NULL);
+    compression_ref.init();
+    return;
+  }
+#else
   if (ultra)
     failx(0, "-u is not supported by the GPU task graph");
+#endif
   assert(1 <= bs100k && bs100k <= 9);
 
   batch_cap = env_uint("LBZIP2_B200_BATCH", 32u, 1u, 1024u);
@@ -480,6 +536,12 @@ init(void)
 static void
 uninit(void)
 {
+#ifdef LBZ_WITH_REF_SEQUENTIAL
+  if (ultra) {
+    compression_ref.uninit();
+    return;
+  }
+#endif
   uint8_t trailer[TRAILER_SIZE];
 
   trailer[0] = 0x17;            /* end-of-stream magic + stream CRC, */
@@ -511,6 +573,12 @@ uninit(void)
 
 
 static const struct task task_list[] = {
+#ifdef LBZ_WITH_REF_SEQUENTIAL
+  { "seq0",    can_ref0,    do_ref0    },
+  { "seq1",    can_ref1,    do_ref1    },
+  { "seq2",    can_ref2,    do_ref2    },
+  { "seq3",    can_ref3,    do_ref3    },
+#endif
   { "reorder", can_reorder, do_reorder },
   { "launch",  can_launch,  do_launch  },
   { "stage",   can_stage,   do_stage   },

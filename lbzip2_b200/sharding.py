@@ -308,11 +308,15 @@ def _row(b):
             int(b.bwt_idx), int(b.rand))
 
 
-def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFFFFFFFFFF):
+def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFFFFFFFFFF, gather_payload=True, keep=None):
     """Decompress the file `z` (bytes, present on every rank) with `world` decoders.
     `dec` offers scan / decode_at / emit_at / walk_table (lbzip2_b200.Decoder).
     Returns (status, output bytes, info) on rank 0 and (the same status, None, info) elsewhere.
-    Status and surviving output follow lbz_decompress_stream."""
+    Status and surviving output follow lbz_decompress_stream.
+    gather_payload=False: the decoded bytes stay in every rank's host memory (a multi-process writer
+    would pwrite them at their offsets); only (offset, length, CRC) per block travel to rank 0, which
+    still checks the CRCs in stream order; rank 0 then returns None for the output.  `keep` (a dict)
+    receives this rank's (parts, payload) for checks by the caller."""
     hits = dec.scan(z)
     mine = hits[rank::world]
     cap_blocks = getattr(dec, "max_blocks", None)
@@ -350,11 +354,13 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
             local_off.append(noemit)
     payload, crcs = dec.emit_at(local_off, max(cursor, 1))
     parts = [(goff[b[0]], b[2], local_off[i], crcs[i]) for i, b in enumerate(rows) if b[0] in goff]
+    if keep is not None:
+        keep["parts"], keep["payload"] = parts, payload
     gathered = [None] * world
     if world > 1:
-        dist.gather_object((parts, payload), gathered if rank == 0 else None, dst=0)
+        dist.gather_object((parts, payload if gather_payload else None), gathered if rank == 0 else None, dst=0)
     else:
-        gathered = [(parts, payload)]
+        gathered = [(parts, payload if gather_payload else None)]
     if rank != 0:
         final = [None]
         dist.broadcast_object_list(final, src=0)      # a CRC error found by rank 0 outranks the walk's verdict
@@ -364,7 +370,7 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
     got = {}
     for prt, pay in gathered:
         for g, ln, lo, crc in prt:
-            got[g] = (pay[lo:lo + ln], crc)
+            got[g] = (pay[lo:lo + ln] if pay is not None else None, crc)
     out, nblocks = [], 0
     for k, want in zip(chain, chain_crc):
         data, crc = got[goff[merged[k][0]]]
@@ -377,4 +383,4 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
     info.status = status
     if world > 1:
         dist.broadcast_object_list([(status, nblocks)], src=0)
-    return status, b"".join(out), info
+    return status, (b"".join(out) if gather_payload else None), info

@@ -68,13 +68,29 @@ def test_batch_cli_on_the_gpu_matches_reference_cli(batch, engines, nthreads, gp
     import torch
     if not (os.path.exists(CPU_CLI) and os.path.exists(GPU_CLI)):
         pytest.skip("oracle/_ref binaries not present")
-    gpus = min(gpus, torch.cuda.device_count())
+    if gpus > torch.cuda.device_count():
+        pytest.skip("needs %d GPUs (run under gpurun --gpus %d)" % (gpus, gpus))
     env = {"LBZIP2_B200_BATCH": str(batch), "LBZIP2_B200_ENGINES": str(engines), "LBZIP2_B200_GPUS": str(gpus)}
     ins = _inputs()
     ins["text_9"] = synth.text(5_000_000, offset=34)
     for name, data in ins.items():
         level = 9 if name == "text_9" else (1 if len(data) < 1_000_000 else 3)
         assert _run(GPU_CLI, level, nthreads, data, env) == _reference(level, data), name
+
+
+@pytest.mark.gpu
+def test_batch_cli_sequential_mode_forwards_to_the_reference_collector():
+    """`lbzip2_b200 -u`: the reference's own sequential collector (src/compress.c:120-198, linked in as
+    compression_ref) drives the library's per-block API; output = the CPU reference's with -u."""
+    if not (os.path.exists(CPU_CLI) and os.path.exists(GPU_CLI)):
+        pytest.skip("oracle/_ref binaries not present")
+    data = synth.text(1_300_000, offset=51) + b"\0" * 2_500_000 + synth.random_bytes(200_000, seed=52) + b"k" * 600_000
+    for level, nthreads in ((9, 4), (2, 8)):
+        got = subprocess.run([GPU_CLI, "-u", "-%d" % level, "-n%d" % nthreads], input=data, stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, timeout=300)
+        assert got.returncode == 0, got.stderr[-400:]
+        want = subprocess.run([CPU_CLI, "-u", "-%d" % level], input=data, stdout=subprocess.PIPE, check=True).stdout
+        assert got.stdout == want
 
 
 # ---- expansion task graph (lbzip2_b200/host/expand_b200.c, SURVEY 8 f1/f3) ---------------------
