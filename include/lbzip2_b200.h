@@ -87,6 +87,36 @@ extern uint32_t crc_table[256];
 void lbz_set_fatal_handler(void (*fn)(const char *msg));
 
 /* ------------------------------------------------------------------------
+ * 1b. Reference-compatible per-block DECODER API.
+ *    Replaces: reference src/decode.h:72-81 as implemented in src/decode.c
+ *    (decoder_init :1148, decoder_free :1159, retrieve :519, decode :852,
+ *    emit :944).  `struct decoder_state` and `struct bitstream` are the
+ *    reference's own public layouts (src/decode.h:39-66): callers compile
+ *    against the reference's decode.h and link this library instead of
+ *    src/decode.c (oracle/Makefile: _ref/lbzip2_gpu).  The
+ *    stream parser and the block scanner (parser_init/parse/scan,
+ *    src/parse.c) are host-side framing logic and stay the reference's.
+ *    Return values are the reference's `enum error` (src/common.h:54-76).
+ * ---------------------------------------------------------------------- */
+struct decoder_state;
+struct bitstream;
+/* src/decode.h:77.  Allocates the per-block state behind ds->internal_state. */
+void decoder_init(struct decoder_state *ds);
+/* src/decode.h:78. */
+void decoder_free(struct decoder_state *ds);
+/* src/decode.h:79  (src/decode.c:519-850).  Consumes the bits offered by `bs`
+   (one I/O buffer at a time); MORE = the block continues in the next buffer,
+   OK = block complete with the cursor on its last bit, else the error. */
+int retrieve(struct decoder_state *ds, struct bitstream *bs);
+/* src/decode.h:80  (src/decode.c:852-931).  Inverse BWT; here it already ran
+   with the rest of the block when retrieve() returned OK. */
+void decode(struct decoder_state *ds);
+/* src/decode.h:81  (src/decode.c:944-1143).  Writes decoded bytes into buf;
+   *buf_sz: in = capacity, out = space left; MORE, OK (ds->crc = block CRC)
+   or ERR_RUNLEN. */
+int emit(struct decoder_state *ds, void *buf, size_t *buf_sz);
+
+/* ------------------------------------------------------------------------
  * 2. Batch API.
  * ---------------------------------------------------------------------- */
 typedef struct lbz_engine lbz_engine;

@@ -68,6 +68,8 @@ EXPORTS = [
     # reference-shaped API (src/encode.h:29-36)
     "encoder_alloc_size", "encoder_init", "collect", "encode", "transmit", "generate_prefix_code", "divbwt",
     "crc_table", "lbz_set_fatal_handler",
+    # reference-shaped decoder API (src/decode.h:72-81)
+    "decoder_init", "decoder_free", "retrieve", "decode", "emit",
     # batch API
     "lbz_engine_create", "lbz_engine_destroy", "lbz_bound", "lbz_compress_chunks",
     "lbz_compress_chunks_device", "lbz_compress_chunks_h2d", "lbz_scatter_to_host", "lbz_compress_stream", "lbz_host_alloc", "lbz_host_free",

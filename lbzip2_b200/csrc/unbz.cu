@@ -5,6 +5,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
 
 #include "../../include/lbzip2_b200.h"
 #include "unbz_kernels.cuh"
@@ -108,13 +111,21 @@ __device__ __forceinline__ uint32_t ch_lds_u8(uint32_t addr) {       // addr: 32
   asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t ch_lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 
+#define CH_SMEM_BYTES (6u * UB_WSIZE + 6u * UB_WSIZE * 2u)      // byte tables + one-code tables of up to six trees: 72 KB
 __global__ void __launch_bounds__(CH_THREADS)
 k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, uint32_t nblk,
             const uint8_t *__restrict__ sel_all, const UbTreeG *__restrict__ tree_all,
             const uint16_t *__restrict__ l1_all, const uint32_t *__restrict__ ml_all, const uint8_t *__restrict__ mq_all,
             uint64_t *__restrict__ gpos_all, uint8_t *__restrict__ gtree_all, uint32_t *sm_slots) {
-  __shared__ __align__(16) uint8_t smq[6 * UB_WSIZE];
+  extern __shared__ __align__(16) uint8_t ch_smem[];
+  uint8_t *smq = ch_smem;                                          // [6][4096] multi-code byte entries
+  uint16_t *sl1 = reinterpret_cast<uint16_t *>(ch_smem + 6u * UB_WSIZE);   // [6][4096] (symbol << 5 | length) of the first code
   __shared__ uint32_t s_slot;
   const uint32_t b = blockIdx.x, tid = threadIdx.x;
   if (b >= nblk) return;
@@ -125,6 +136,9 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
     const uint4 *src = reinterpret_cast<const uint4 *>(mq_all + (size_t)b * 6u * UB_WSIZE);
     uint4 *dst = reinterpret_cast<uint4 *>(smq);
     for (uint32_t i = tid; i < ntrees * (UB_WSIZE / 16u); i += CH_THREADS) dst[i] = src[i];
+    const uint4 *src1 = reinterpret_cast<const uint4 *>(l1_all + (size_t)b * 6u * UB_WSIZE);
+    uint4 *dst1 = reinterpret_cast<uint4 *>(sl1);
+    for (uint32_t i = tid; i < ntrees * (UB_WSIZE / 8u); i += CH_THREADS) dst1[i] = src1[i];
   }
   uint32_t smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -144,6 +158,7 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
   uint8_t *gtree = gtree_all + (size_t)b * (UB_MAXGRP + 1u);
   const uint32_t eob = B.alpha_size - 1u;
   const uint32_t smq_base = (uint32_t)__cvta_generic_to_shared(smq);
+  const uint32_t sl1_base = (uint32_t)__cvta_generic_to_shared(sl1);
   const uint32_t nsel = B.num_selectors > UB_MAXGRP ? UB_MAXGRP : B.num_selectors;   // src/decode.c:631-632
   uint32_t slp = 0;                                  // selector list, 4 bits per entry: tree number or error code
   for (uint32_t t = 0; t < 6u; t++) slp |= (t < B.num_trees ? ((uint32_t)tree_all[(size_t)b * 6u + t].status & 15u) : 0u) << (4u * t);
@@ -151,6 +166,12 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
   uint32_t status = UB_ERR_UNTERM, nsym = 0, g = 0;
   UbBits br;
   br.words = words; br.nwords = nwords;
+  // window of the lean reader, carried from group to group: hi:lo = the 64 bits at the word of the
+  // current position, bp = bit offset inside hi, nxt = the word after lo (raw), wp = its address
+  const uint32_t *wp = words;
+  const uint32_t *const wend = words + nwords;
+  uint32_t bp = 0, hi = 0, lo = 0, nxt = 0;
+  bool window = false;                               // the registers above describe `pos`
 
   for (; g < nsel; g++) {
     const uint32_t r4 = 4u * min((uint32_t)sel[g], 7u);      // the header kernel admits only indices below num_trees
@@ -161,21 +182,23 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
       const uint32_t above = (r4 >= 28u) ? 0u : (slp >> (r4 + 4u)) << (r4 + 4u);
       slp = above | (below << 4) | t;
     }
+    if (window) pos = ((uint64_t)(wp - words - 2) << 5) + bp;
     if (writer) { gpos[g] = pos; gtree[g] = (uint8_t)t; }
     const UbTreeG &T = tree_all[(size_t)b * 6u + t];
-    const uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
-    const uint32_t *ml = ml_all + ((size_t)b * 6u + t) * UB_WSIZE;
     bool done = false;
 
     if ((pos >> 5) + 36u <= nwords) {
-      // lean window reader: a whole group (50 codes of at most 20 bits) lies inside the input.
-      // hi:lo = the 64 bits at the word of `pos`, bp = bit offset inside hi, nxt = the following word (raw)
-      const uint32_t *wp = words + (pos >> 5);
-      uint32_t bp = (uint32_t)(pos & 31u);
-      uint32_t hi = ch_bswap(wp[0]), lo = ch_bswap(wp[1]);
-      wp += 2;
-      uint32_t nxt = *wp;
+      // lean window reader: a whole group (50 codes of at most 20 bits) lies inside the input
+      if (!window) {
+        wp = words + (pos >> 5);
+        bp = (uint32_t)(pos & 31u);
+        hi = ch_bswap(wp[0]); lo = ch_bswap(wp[1]);
+        wp += 2;
+        nxt = *wp;
+        window = true;
+      }
       const uint32_t tb = smq_base + t * UB_WSIZE;
+      const uint32_t tl = sl1_base + t * (UB_WSIZE * 2u);
       // Phase 1, "blind": table steps while even a four-code entry cannot overshoot the group.  Only
       // the bit position is carried from step to step (funnel shift, one shared-memory byte, add);
       // the code count and the OR of the entries' flag bits ride along and are looked at afterwards.
@@ -188,40 +211,36 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
         orq |= q;
         cnt += q >> 4;
         bp += q & 15u;
-        if (bp >= 32u) { bp -= 32u; hi = lo; lo = ch_bswap(nxt); wp++; nxt = *wp; }
+        if (bp >= 32u) {
+          bp -= 32u; hi = lo; lo = ch_bswap(nxt); wp++; nxt = *wp;
+          if (wp + 64 < wend) asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));   // the stream two cache lines ahead
+        }
       } while (cnt <= 46u);
       uint32_t rem;
       if (orq & 0x80u) {                               // an entry needs care (end of block, or a code longer than the window):
-        hi = hi0; lo = lo0; bp = bp0; nxt = nxt0; wp = wp0;   // walk this group again, one careful step at a time
+        hi = hi0; lo = lo0; bp = bp0; nxt = nxt0; wp = wp0;   // walk this group again, one code at a time
         rem = 50u;
       } else {
         rem = 50u - cnt;                               // 0..3 codes left
       }
       while (rem) {
-        // careful steps (the last codes of a group; a whole group when an entry was flagged): the full
-        // table entry tells how far each of its codes reaches (k_ub_tree_multi)
+        // one code at a time (the last codes of a group; a whole group when an entry was flagged)
         const uint32_t win = __funnelshift_l(lo, hi, bp);
-        const uint32_t e = ml[win >> (32u - UB_WBITS)];
-        const uint32_t cnt1 = (e >> 4) & 7u;
-        uint32_t len;
-        if (cnt1) {
-          uint32_t take = cnt1 < rem ? cnt1 : rem;
-          const uint32_t eobk = e >> 24;
-          if (eobk && eobk <= take) { take = eobk; done = true; }
-          len = (e >> (4u + 4u * take)) & 15u;
-          rem -= take;
-        } else {                                       // a code longer than the window
-          const uint32_t s1 = ub_canon_decode(T, win >> 12, &len);
-          rem -= 1u;
-          if (s1 == eob) done = true;
-        }
+        const uint32_t x = ch_lds_u16(tl + 2u * (win >> (32u - UB_WBITS)));
+        uint32_t len, s1;
+        if (x) { s1 = x >> 5; len = x & 31u; }
+        else s1 = ub_canon_decode(T, win >> 12, &len);        // a code longer than the window
+        rem -= 1u;
+        if (s1 == eob) done = true;
         bp += len;
         if (bp >= 32u) { bp -= 32u; hi = lo; lo = ch_bswap(nxt); wp++; nxt = *wp; }
         if (done) break;
       }
       nsym += 50u - rem;
-      pos = ((uint64_t)(wp - words - 2) << 5) + bp;
+      if (done) pos = ((uint64_t)(wp - words - 2) << 5) + bp;
     } else {
+      window = false;
+      const uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
       bool eof = !ub_bits_seek(br, pos);
       for (uint32_t j = 0; j < 50u && !eof && !done; j++) {
         if (!ub_bits_need(br)) { eof = true; break; }  // NEED(), src/decode.c:387-407
@@ -238,6 +257,7 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
     }
     if (done) { status = UB_OK; g++; break; }
   }
+  if (window && status != UB_OK) pos = ((uint64_t)(wp - words - 2) << 5) + bp;   // ran out of selectors inside the window reader
   if (writer) {
     B.nsym = nsym;
     B.ngrp = g;
@@ -286,7 +306,9 @@ static int ub_chain_version() {
     uint32_t *slots_ = ub_chain_version() == 2 ? ub_sm_slots(ub_backend(d)->device) : nullptr;      \
     if (slots_) {                                                                                   \
       UB_CUDA(cudaMemsetAsync(slots_, 0, 256 * sizeof(uint32_t), ub_stream(d)));                    \
-      k_ub_chain2<<<(nblk), CH_THREADS, 0, ub_stream(d)>>>((d)->d_words, (nwords), (d)->d_blk, (nblk), (d)->d_sel, (d)->d_tree, \
+      static bool ch_attr_ = false;                                                                 \
+      if (!ch_attr_) { cudaFuncSetAttribute(k_ub_chain2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM_BYTES); ch_attr_ = true; } \
+      k_ub_chain2<<<(nblk), CH_THREADS, CH_SMEM_BYTES, ub_stream(d)>>>((d)->d_words, (nwords), (d)->d_blk, (nblk), (d)->d_sel, (d)->d_tree, \
                                                             (d)->d_l1, (d)->d_ml, (d)->d_mq, (d)->d_gpos, (d)->d_gtree, slots_);  \
       cudaError_t le_ = cudaGetLastError();                                                         \
       if (le_ != cudaSuccess) return ub_cuda_fail(le_, "k_ub_chain2", __LINE__);                    \
@@ -460,4 +482,179 @@ extern "C" const char *lbz_strerror(int status) {
   if (status >= LBZ_ERR_MAGIC && status <= LBZ_ERR_EOF) return text[status - LBZ_ERR_MAGIC];
   if (status == LBZ_ERR_OUTCAP) return "output buffer too small";
   return "internal error";
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5. The reference's per-block decoder API (src/decode.h:72-81): decoder_init / decoder_free /
+//    retrieve / decode / emit, so that the UNMODIFIED src/expand.c (reference scheduler, parser
+//    and scanner) drives the GPU decoder.  oracle/Makefile links _ref/lbzip2_gpu without
+//    src/decode.c for exactly this.
+//
+// The impedance: retrieve() is fed one 256 KiB I/O buffer at a time
+// (src/expand.c:553-565), must return MORE at the end of a buffer and OK with the bit cursor ON
+// the block's last bit -- the caller turns the cursor into the stream position the parser
+// resumes at and releases the buffers behind it (src/expand.c:305-343, :585-596).  Where a block
+// ends is only known after its codes have been decoded, so every call decodes what it has: the
+// bits offered so far are kept behind the state, the block is pushed through the kernels on a
+// pooled single-block decoder, and
+//   * "input exhausted" (and more to come)  -> MORE, everything offered is consumed;
+//   * block complete                        -> its bytes and CRC are fetched at once, the cursor is
+//     put on the end bit -- which lies in the CURRENT buffer, because a call that had seen the end
+//     would have returned OK itself -- and decode() has nothing left to do; emit() hands the
+//     bytes out in the caller's 900 000-byte pieces.
+// A block that spans k buffers is decoded k times (k <= 2 for text at -9, <= 5 for incompressible
+// data); the scheduler's worker threads (-n) keep that many single-block decodes in flight.  The
+// throughput path is the batch decompressor (section 4); this is the drop-in boundary.
+struct in_blk;
+struct bitstream {              // src/decode.h:39-46
+  unsigned live;
+  uint64_t buff;
+  struct in_blk *block;
+  const uint32_t *data;
+  const uint32_t *limit;
+  bool eof;
+};
+struct retriever_internal_state {
+  std::vector<uint8_t> acc;     // [24-byte lead-in with a stand-in block header][the block's bits, byte-aligned to the input words]
+  uint64_t start_bit;           // the stand-in header's first bit in acc
+  bool started;
+  std::vector<uint8_t> out;     // decoded bytes of the block
+  size_t out_pos;
+  uint32_t crc, rl_state;
+};
+struct decoder_state {          // src/decode.h:49-66 (public: the caller reads block_size and crc, src/expand.c:666,682)
+  struct retriever_internal_state *internal_state;
+  bool rand;
+  unsigned bwt_idx;
+  unsigned block_size;
+  uint32_t crc;
+  uint32_t ftab[256];
+  uint32_t *tt;
+  int rle_state;
+  uint32_t rle_crc, rle_index, rle_avail;
+  uint8_t rle_char, rle_prev;
+};
+
+namespace {
+struct DecPool {
+  std::mutex mu;
+  std::vector<lbz_decoder *> idle;
+};
+DecPool &g_decpool = *new DecPool;     // leaked on purpose: worker threads may outlive static destruction
+const size_t kShimInCap = 4u << 20;    // > the longest block: 900 000 symbols of 20 bits + tables
+
+lbz_decoder *decpool_acquire() {
+  {
+    std::lock_guard<std::mutex> lk(g_decpool.mu);
+    if (!g_decpool.idle.empty()) { lbz_decoder *d = g_decpool.idle.back(); g_decpool.idle.pop_back(); return d; }
+  }
+  const char *dv = getenv("LBZIP2_B200_DEVICE");
+  return lbz_decoder_create(dv ? atoi(dv) : 0, 1, kShimInCap, 0);
+}
+void decpool_release(lbz_decoder *d) {
+  std::lock_guard<std::mutex> lk(g_decpool.mu);
+  g_decpool.idle.push_back(d);
+}
+[[noreturn]] void shim_die(const char *msg) {
+  fprintf(stderr, "lbzip2_b200: fatal: %s\n", msg);
+  abort();
+}
+}  // namespace
+
+extern "C" void decoder_init(struct decoder_state *ds) {
+  ds->internal_state = new retriever_internal_state();
+  ds->internal_state->started = false;
+  ds->internal_state->out_pos = 0;
+  ds->tt = nullptr;
+  ds->block_size = 0;
+}
+
+extern "C" void decoder_free(struct decoder_state *ds) {
+  delete ds->internal_state;
+  ds->internal_state = nullptr;
+}
+
+extern "C" int retrieve(struct decoder_state *ds, struct bitstream *bs) {
+  retriever_internal_state *rs = ds->internal_state;
+  if (!rs) shim_die("retrieve: state not initialised");
+  if (!rs->started) {
+    // the cursor's pending bits (left-justified in buff, src/decode.c:367-372) come right before the
+    // first word; an 80-bit stand-in for the block header the parser has consumed (magic + CRC,
+    // src/parse.c:213-243) comes right before them, because the decoder addresses blocks by their magic
+    const unsigned w = bs->live;
+    if (w > 63u) shim_die("retrieve: bad bit cursor");
+    rs->acc.assign(24, 0);
+    const uint64_t x = w ? (bs->buff >> (64u - w)) : 0ull;
+    for (int k = 0; k < 8; k++) rs->acc[16 + k] = (uint8_t)(x >> (56 - 8 * k));
+    const uint64_t body = 192u - w;
+    rs->start_bit = body - 80u;
+    const uint64_t magic = 0x314159265359ull;
+    for (unsigned k = 0; k < 48u; k++)
+      if ((magic >> (47u - k)) & 1u) { const uint64_t p = rs->start_bit + k; rs->acc[p >> 3] |= (uint8_t)(0x80u >> (p & 7u)); }
+    rs->started = true;
+  }
+  const uint32_t *const data0 = bs->data;
+  const size_t call_base_bits = rs->acc.size() * 8;
+  if (bs->limit > bs->data && rs->acc.size() < kShimInCap - (1u << 19))
+    rs->acc.insert(rs->acc.end(), reinterpret_cast<const uint8_t *>(bs->data), reinterpret_cast<const uint8_t *>(bs->limit));
+  lbz_decoder *dec = decpool_acquire();
+  if (!dec) shim_die("retrieve: cannot create a device context (no usable GPU?)");
+  lbz_dblock tb;
+  uint64_t pos = rs->start_bit;
+  if (ub_decode_at(dec, rs->acc.data(), rs->acc.size(), &pos, 1, &tb, 0) != 0) shim_die("retrieve: device error");
+  int status = (int)tb.status;
+  if (status == UB_OK && tb.rl_state == 4u) { /* reported by emit(), like the reference */ }
+  if (status != UB_OK) {
+    decpool_release(dec);
+    bs->data = bs->limit; bs->live = 0; bs->buff = 0;                  // everything offered is consumed
+    if (status == UB_ERR_EOF && !bs->eof) return UB_MORE;              // src/decode.c:387-396
+    return status;
+  }
+  ds->rand = tb.rand != 0;
+  ds->bwt_idx = tb.bwt_idx;
+  ds->block_size = tb.block_size;
+  rs->out.resize((size_t)tb.out_len);
+  rs->out_pos = 0;
+  const uint64_t off0 = 0;
+  size_t olen = 0;
+  uint32_t crc = 0;
+  if (tb.out_len > dec->out_cap ||
+      ub_emit_at(dec, &off0, 1, rs->out.empty() ? nullptr : rs->out.data(), rs->out.size(), &olen, &crc) != 0)
+    shim_die("retrieve: device error while writing the block");
+  rs->crc = crc;
+  rs->rl_state = dec->h_blk[0].rl_state;
+  decpool_release(dec);
+  // the bit cursor goes on the first bit after the block
+  const uint64_t E = tb.end_bit;
+  if (E >= call_base_bits) {
+    const uint64_t rel = E - call_base_bits;                           // bits of this call's words that belong to the block
+    const uint64_t nw = (rel + 31u) / 32u;
+    const unsigned live = (unsigned)(nw * 32u - rel);
+    bs->data = data0 + nw;
+    bs->live = live;
+    bs->buff = live ? ((uint64_t)(__builtin_bswap32(data0[nw - 1]) & ((1u << live) - 1u)) << (64u - live)) : 0ull;
+  } else {
+    // the block ended inside the bits the cursor held when the first call came in
+    const uint64_t left = call_base_bits - E;                          // pending bits that stay pending
+    if (left > 63u || call_base_bits != 192u) shim_die("retrieve: internal cursor error");
+    const uint64_t x = bs->live ? (bs->buff >> (64u - bs->live)) : 0ull;
+    bs->live = (unsigned)left;
+    bs->buff = left ? (x << (64u - left)) : 0ull;
+  }
+  return UB_OK;
+}
+
+extern "C" void decode(struct decoder_state *ds) { (void)ds; }       // the inverse BWT ran with the rest of the block
+
+extern "C" int emit(struct decoder_state *ds, void *buf, size_t *buf_sz) {
+  retriever_internal_state *rs = ds->internal_state;
+  const size_t cap = *buf_sz, left = rs->out.size() - rs->out_pos;
+  const size_t n = cap < left ? cap : left;
+  if (n) memcpy(buf, rs->out.data() + rs->out_pos, n);
+  rs->out_pos += n;
+  *buf_sz = cap - n;
+  if (rs->out_pos < rs->out.size()) return UB_MORE;
+  if (rs->rl_state == 4u) return UB_ERR_RUNLEN;                        // src/decode.c:936-942
+  ds->crc = rs->crc;
+  return UB_OK;
 }

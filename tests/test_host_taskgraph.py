@@ -155,6 +155,25 @@ def test_expansion_cli_on_the_gpu_matches_goldens_and_reference_cli():
     assert r.returncode == 0 and r.stdout == data, r.stderr[-200:]
 
 
+@pytest.mark.gpu
+def test_unmodified_expand_c_drives_the_gpu_decoder():
+    """oracle/_ref/lbzip2_gpu links the reference's main.c/process.c/expand.c/parse.c WITHOUT src/decode.c:
+    decoder_init/retrieve/decode/emit/decoder_free (src/decode.h:72-81) come from libbz2b200.so.  The
+    reference's scheduler feeds retrieve() one 256 KiB buffer at a time and takes the block end from the
+    bit cursor; verdicts, messages and bytes must be the reference CLI's (the committed goldens)."""
+    shim_cli = os.path.join(orclib.REF_DIR, "lbzip2_gpu")
+    if not (os.path.exists(shim_cli) and os.path.exists(CPU_CLI)):
+        pytest.skip("oracle/_ref binaries not present")
+    cases = _decode_cases()
+    pick = cases[:: 9] + [c for c in cases if c["status"] == "OK" and c["num_blocks"] >= 2][:6]
+    _check_expand(shim_cli, pick, {}, 4)
+    data = synth.text(6_000_000, offset=43) + synth.random_bytes(2_500_000, seed=43) + b"\0" * 4_000_000
+    for level, nthreads in ((9, 8), (1, 16)):
+        z = _reference(level, data)
+        r = subprocess.run([shim_cli, "-d", "-c", "-n%d" % nthreads], input=z, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+        assert r.returncode == 0 and r.stdout == data, r.stderr[-200:]
+
+
 def test_expansion_task_graph_several_operands_and_thread_counts(tmp_path):
     """One process, several files (the decoder outlives an operand and is re-sized for a larger
     one, src/main.c:935), -n from 1 to 64, small and large waves."""
