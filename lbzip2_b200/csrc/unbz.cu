@@ -166,12 +166,21 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
   uint32_t status = UB_ERR_UNTERM, nsym = 0, g = 0;
   UbBits br;
   br.words = words; br.nwords = nwords;
-  // window of the lean reader, carried from group to group: hi:lo = the 64 bits at the word of the
-  // current position, bp = bit offset inside hi, nxt = the word after lo (raw), wp = its address
-  const uint32_t *wp = words;
-  const uint32_t *const wend = words + nwords;
-  uint32_t bp = 0, hi = 0, lo = 0, nxt = 0;
+  // window of the lean reader, carried from group to group: v = the next `avail` bits of the block,
+  // left-justified (at least 32 of them whenever a table is consulted), wi = index of the word that
+  // is appended next, nxt = that word (raw).  Position = 32 wi - avail.
+  uint64_t v = 0;
+  uint32_t avail = 0, wi = 0, nxt = 0;
+  const uint32_t pf_lim = nwords > 64u ? (uint32_t)(nwords - 64u < 0xFFFFFFFFull ? nwords - 64u : 0xFFFFFFFFull) : 0u;   // prefetch stays inside the input
   bool window = false;                               // the registers above describe `pos`
+#define CH_REFILL()                                                                              \
+  do {                                                                                           \
+    v |= (uint64_t)ch_bswap(nxt) << (32u - avail);                                               \
+    avail += 32u;                                                                                \
+    wi++;                                                                                        \
+    nxt = words[wi];                                                                             \
+    if (!(wi & 31u) && wi < pf_lim) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + wi + 64));              \
+  } while (0)
 
   for (; g < nsel; g++) {
     const uint32_t r4 = 4u * min((uint32_t)sel[g], 7u);      // the header kernel admits only indices below num_trees
@@ -182,7 +191,7 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
       const uint32_t above = (r4 >= 28u) ? 0u : (slp >> (r4 + 4u)) << (r4 + 4u);
       slp = above | (below << 4) | t;
     }
-    if (window) pos = ((uint64_t)(wp - words - 2) << 5) + bp;
+    if (window) pos = ((uint64_t)wi << 5) - avail;
     if (writer) { gpos[g] = pos; gtree[g] = (uint8_t)t; }
     const UbTreeG &T = tree_all[(size_t)b * 6u + t];
     bool done = false;
@@ -190,54 +199,62 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
     if ((pos >> 5) + 36u <= nwords) {
       // lean window reader: a whole group (50 codes of at most 20 bits) lies inside the input
       if (!window) {
-        wp = words + (pos >> 5);
-        bp = (uint32_t)(pos & 31u);
-        hi = ch_bswap(wp[0]); lo = ch_bswap(wp[1]);
-        wp += 2;
-        nxt = *wp;
+        const uint32_t w0 = (uint32_t)(pos >> 5), bp = (uint32_t)(pos & 31u);
+        v = (((uint64_t)ch_bswap(words[w0]) << 32) | ch_bswap(words[w0 + 1])) << bp;
+        avail = 64u - bp;
+        wi = w0 + 2u;
+        nxt = words[wi];
         window = true;
       }
       const uint32_t tb = smq_base + t * UB_WSIZE;
       const uint32_t tl = sl1_base + t * (UB_WSIZE * 2u);
-      // Phase 1, "blind": table steps while even a four-code entry cannot overshoot the group.  Only
-      // the bit position is carried from step to step (funnel shift, one shared-memory byte, add);
-      // the code count and the OR of the entries' flag bits ride along and are looked at afterwards.
-      const uint32_t hi0 = hi, lo0 = lo, bp0 = bp, nxt0 = nxt;
-      const uint32_t *const wp0 = wp;
+      // Phase 1, "blind": table steps while even four-code entries cannot overshoot the group.  Only
+      // the bit window is carried from step to step (shift, one shared-memory byte, shift); the code
+      // count and the OR of the entries' flag bits ride along and are looked at afterwards.  Two steps
+      // per refill test: a step consumes at most 12 bits and 32 are guaranteed.
+      const uint64_t v0 = v;
+      const uint32_t avail0 = avail, wi0 = wi, nxt0 = nxt;
       uint32_t cnt = 0, orq = 0;
-      do {
-        const uint32_t win = __funnelshift_l(lo, hi, bp);
-        const uint32_t q = ch_lds_u8(tb + (win >> (32u - UB_WBITS)));
-        orq |= q;
+      while (cnt <= 42u) {
+        if (avail < 32u) CH_REFILL();
+        const uint32_t q1 = ch_lds_u8(tb + (uint32_t)(v >> (64u - UB_WBITS)));
+        v <<= (q1 & 15u);
+        const uint32_t q2 = ch_lds_u8(tb + (uint32_t)(v >> (64u - UB_WBITS)));
+        v <<= (q2 & 15u);
+        avail -= (q1 & 15u) + (q2 & 15u);
+        cnt += (q1 >> 4) + (q2 >> 4);
+        orq |= q1 | q2;
+      }
+      while (cnt <= 46u) {
+        if (avail < 32u) CH_REFILL();
+        const uint32_t q = ch_lds_u8(tb + (uint32_t)(v >> (64u - UB_WBITS)));
+        v <<= (q & 15u);
+        avail -= q & 15u;
         cnt += q >> 4;
-        bp += q & 15u;
-        if (bp >= 32u) {
-          bp -= 32u; hi = lo; lo = ch_bswap(nxt); wp++; nxt = *wp;
-          if (wp + 64 < wend) asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));   // the stream two cache lines ahead
-        }
-      } while (cnt <= 46u);
+        orq |= q;
+      }
       uint32_t rem;
       if (orq & 0x80u) {                               // an entry needs care (end of block, or a code longer than the window):
-        hi = hi0; lo = lo0; bp = bp0; nxt = nxt0; wp = wp0;   // walk this group again, one code at a time
+        v = v0; avail = avail0; wi = wi0; nxt = nxt0;  // walk this group again, one code at a time
         rem = 50u;
       } else {
         rem = 50u - cnt;                               // 0..3 codes left
       }
       while (rem) {
         // one code at a time (the last codes of a group; a whole group when an entry was flagged)
-        const uint32_t win = __funnelshift_l(lo, hi, bp);
-        const uint32_t x = ch_lds_u16(tl + 2u * (win >> (32u - UB_WBITS)));
+        if (avail < 32u) CH_REFILL();
+        const uint32_t x = ch_lds_u16(tl + 2u * (uint32_t)(v >> (64u - UB_WBITS)));
         uint32_t len, s1;
         if (x) { s1 = x >> 5; len = x & 31u; }
-        else s1 = ub_canon_decode(T, win >> 12, &len);        // a code longer than the window
+        else s1 = ub_canon_decode(T, (uint32_t)(v >> 44), &len);        // a code longer than the window
         rem -= 1u;
         if (s1 == eob) done = true;
-        bp += len;
-        if (bp >= 32u) { bp -= 32u; hi = lo; lo = ch_bswap(nxt); wp++; nxt = *wp; }
+        v <<= len;
+        avail -= len;
         if (done) break;
       }
       nsym += 50u - rem;
-      if (done) pos = ((uint64_t)(wp - words - 2) << 5) + bp;
+      if (done) pos = ((uint64_t)wi << 5) - avail;
     } else {
       window = false;
       const uint16_t *l1 = l1_all + ((size_t)b * 6u + t) * UB_WSIZE;
@@ -257,7 +274,8 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
     }
     if (done) { status = UB_OK; g++; break; }
   }
-  if (window && status != UB_OK) pos = ((uint64_t)(wp - words - 2) << 5) + bp;   // ran out of selectors inside the window reader
+  if (window && status != UB_OK) pos = ((uint64_t)wi << 5) - avail;              // ran out of selectors inside the window reader
+#undef CH_REFILL
   if (writer) {
     B.nsym = nsym;
     B.ngrp = g;

@@ -166,7 +166,11 @@ def test_unmodified_expand_c_drives_the_gpu_decoder():
         pytest.skip("oracle/_ref binaries not present")
     cases = _decode_cases()
     pick = cases[:: 9] + [c for c in cases if c["status"] == "OK" and c["num_blocks"] >= 2][:6]
-    _check_expand(shim_cli, pick, {}, 4)
+    # which error of a damaged file is reported first depends on the scheduling of the reference's own
+    # scanner / parser / retriever tasks (its CLI says "bad number of trees" with -n1 and "bad block header
+    # magic" with -n2 for golden 03c2e5d6...): the goldens were made with one worker, so are these runs
+    _check_expand(shim_cli, [c for c in pick if c["status"] != "OK"], {}, 1)
+    _check_expand(shim_cli, [c for c in pick if c["status"] == "OK"], {}, 4)
     data = synth.text(6_000_000, offset=43) + synth.random_bytes(2_500_000, seed=43) + b"\0" * 4_000_000
     for level, nthreads in ((9, 8), (1, 16)):
         z = _reference(level, data)
