@@ -208,52 +208,50 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
       }
       const uint32_t tb = smq_base + t * UB_WSIZE;
       const uint32_t tl = sl1_base + t * (UB_WSIZE * 2u);
-      // Phase 1, "blind": table steps while even four-code entries cannot overshoot the group.  Only
-      // the bit window is carried from step to step (shift, one shared-memory byte, shift); the code
-      // count and the OR of the entries' flag bits ride along and are looked at afterwards.  Two steps
-      // per refill test: a step consumes at most 12 bits and 32 are guaranteed.
-      const uint64_t v0 = v;
-      const uint32_t avail0 = avail, wi0 = wi, nxt0 = nxt;
-      uint32_t cnt = 0, orq = 0;
-      while (cnt <= 42u) {
+      // Table steps while even four-code entries cannot overshoot the group.  Only the bit window is
+      // carried from step to step (shift, one shared-memory byte, shift); the code count rides along.
+      // Two steps per refill test: a step consumes at most 12 bits and 32 are guaranteed.  A flagged
+      // entry (a code longer than the window -- every other group of a text block has one -- or the
+      // end-of-block symbol) is rare per step: it is decoded as ONE code from the one-code table (or
+      // the canonical tables) and the walk goes on.
+      uint32_t cnt = 0;                                // codes of this group walked so far
+#define CH_ONE_CODE()                                                                            \
+      do {                                                                                       \
+        if (avail < 32u) CH_REFILL();                                                            \
+        const uint32_t x_ = ch_lds_u16(tl + 2u * (uint32_t)(v >> (64u - UB_WBITS)));             \
+        uint32_t len_, s_;                                                                       \
+        if (x_) { s_ = x_ >> 5; len_ = x_ & 31u; }                                               \
+        else s_ = ub_canon_decode(T, (uint32_t)(v >> 44), &len_);                                \
+        v <<= len_;                                                                              \
+        avail -= len_;                                                                           \
+        cnt += 1u;                                                                               \
+        if (s_ == eob) done = true;                                                              \
+      } while (0)
+      while (cnt <= 42u && !done) {
         if (avail < 32u) CH_REFILL();
+        const uint64_t vb = v;
         const uint32_t q1 = ch_lds_u8(tb + (uint32_t)(v >> (64u - UB_WBITS)));
         v <<= (q1 & 15u);
         const uint32_t q2 = ch_lds_u8(tb + (uint32_t)(v >> (64u - UB_WBITS)));
         v <<= (q2 & 15u);
-        avail -= (q1 & 15u) + (q2 & 15u);
-        cnt += (q1 >> 4) + (q2 >> 4);
-        orq |= q1 | q2;
+        if (!((q1 | q2) & 0x80u)) {
+          avail -= (q1 & 15u) + (q2 & 15u);
+          cnt += (q1 >> 4) + (q2 >> 4);
+        } else {
+          v = vb;                                      // take the first entry if it is plain, then one code
+          if (!(q1 & 0x80u)) { v <<= (q1 & 15u); avail -= q1 & 15u; cnt += q1 >> 4; }
+          CH_ONE_CODE();
+        }
       }
-      while (cnt <= 46u) {
+      while (cnt <= 46u && !done) {
         if (avail < 32u) CH_REFILL();
         const uint32_t q = ch_lds_u8(tb + (uint32_t)(v >> (64u - UB_WBITS)));
-        v <<= (q & 15u);
-        avail -= q & 15u;
-        cnt += q >> 4;
-        orq |= q;
+        if (!(q & 0x80u)) { v <<= (q & 15u); avail -= q & 15u; cnt += q >> 4; }
+        else CH_ONE_CODE();
       }
-      uint32_t rem;
-      if (orq & 0x80u) {                               // an entry needs care (end of block, or a code longer than the window):
-        v = v0; avail = avail0; wi = wi0; nxt = nxt0;  // walk this group again, one code at a time
-        rem = 50u;
-      } else {
-        rem = 50u - cnt;                               // 0..3 codes left
-      }
-      while (rem) {
-        // one code at a time (the last codes of a group; a whole group when an entry was flagged)
-        if (avail < 32u) CH_REFILL();
-        const uint32_t x = ch_lds_u16(tl + 2u * (uint32_t)(v >> (64u - UB_WBITS)));
-        uint32_t len, s1;
-        if (x) { s1 = x >> 5; len = x & 31u; }
-        else s1 = ub_canon_decode(T, (uint32_t)(v >> 44), &len);        // a code longer than the window
-        rem -= 1u;
-        if (s1 == eob) done = true;
-        v <<= len;
-        avail -= len;
-        if (done) break;
-      }
-      nsym += 50u - rem;
+      while (cnt < 50u && !done) CH_ONE_CODE();        // the last codes of the group, one at a time
+#undef CH_ONE_CODE
+      nsym += cnt;
       if (done) pos = ((uint64_t)wi << 5) - avail;
     } else {
       window = false;
