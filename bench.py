@@ -292,20 +292,20 @@ def decompress_leg(a, lbzip2_b200, L, local, stream, data, recs):
                      "host_output_equals_input": host_out == data},
         "device_bytes": int(dec.device_bytes),
     }
-    # dominant kernel of this leg: the per-block walk over the code lengths (k_ub_chain, timed with
+    # dominant kernel of this leg: the per-block walk over the code lengths (k_ub_chain2, timed with
     # the header and table kernels as stage "retrieve", CUDA events on the decoder's stream).  It reads
     # the compressed bits once and writes 9 bytes per 50-code group; it is latency-bound by
-    # construction (one warp per block), the fraction is reported for completeness.
+    # construction (one walking warp per block), the fraction is reported for completeness.
     retrieve_ms = float(stage.get("retrieve", 0.0))
     walk_bytes = nz + 9 * ((sum(r.nmtf for r in recs) + 49 * len(recs)) // 50)
     walk_gbs = walk_bytes / (retrieve_ms / 1e3) / 1e9 if retrieve_ms > 0 else 0.0
-    res["roofline"] = {"bound": "hbm", "kernel": "k_ub_chain (+ k_ub_header, k_ub_tree_*): stage 'retrieve'",
+    res["roofline"] = {"bound": "hbm", "kernel": "k_ub_chain2 (+ k_ub_header, k_ub_tree_*): stage 'retrieve'",
                        "achieved": round(walk_gbs, 2), "peak": hbm_peak, "unit": "GB/s",
                        "frac": round(walk_gbs / hbm_peak, 6), "bytes_per_launch": int(walk_bytes),
                        "avg_launch_ms": round(retrieve_ms, 3),
-                       "traffic": ncu_traffic("k_ub_chain", len(recs)),
-                       "note": "latency-bound: 1 warp per block, 1.9 % of warp slots active (profiles/r01_ncu_chain_v11.txt); "
-                               "traffic = dram read+write of the k_ub_chain capture"}
+                       "traffic": ncu_traffic("k_ub_chain2", len(recs)),
+                       "note": "latency-bound: one walking warp per block, a dependent chain of shift -> shared-memory byte -> "
+                               "shift per table step (profiles/r02_ncu_chain2.txt); traffic = dram read+write of that capture"}
     dec.close()
     dec = None
     # The walk over the code lengths is serial per block, so decode time at 223 blocks is latency;
