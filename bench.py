@@ -373,9 +373,9 @@ def decompress_leg_multi(a, lbzip2_b200, dist, dev, local, rank, world, sink, en
     import torch
     from lbzip2_b200 import api, sharding
     z = bytes(sink.view[:end])
-    share = (nblocks_total + world - 1) // world + 16
+    share = min(nblocks_total + 16, 2 * ((nblocks_total + world - 1) // world) + 64)
     dec = lbzip2_b200.Decoder(device=local, max_blocks=share, in_cap=len(z) + 64,
-                              out_cap=total_plain // world + 4 * 900000 + (1 << 20))
+                              out_cap=2 * (total_plain // world) + 8 * 900000 + (1 << 20))
     times, keep, st = [], {}, None
     for i in range(1 + 3):
         dist.barrier(); torch.cuda.synchronize()

@@ -172,6 +172,8 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
   uint64_t v = 0;
   uint32_t avail = 0, wi = 0, nxt = 0;
   const uint32_t pf_lim = nwords > 64u ? (uint32_t)(nwords - 64u < 0xFFFFFFFFull ? nwords - 64u : 0xFFFFFFFFull) : 0u;   // prefetch stays inside the input
+  // wi = (pos >> 5) + 2 or + 1 (+2 right after a refill, the window then holds 33..64 bits): wi + 34 <= nwords implies the lean test
+  const uint32_t lean_lim = nwords > 34u ? (uint32_t)(nwords - 34u < 0xFFFFFFFFull ? nwords - 34u : 0xFFFFFFFFull) : 0u;
   bool window = false;                               // the registers above describe `pos`
 #define CH_REFILL()                                                                              \
   do {                                                                                           \
@@ -179,7 +181,6 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
     avail += 32u;                                                                                \
     wi++;                                                                                        \
     nxt = words[wi];                                                                             \
-    if (!(wi & 31u) && wi < pf_lim) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + wi + 64));              \
   } while (0)
 
   for (; g < nsel; g++) {
@@ -196,8 +197,8 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
     const UbTreeG &T = tree_all[(size_t)b * 6u + t];
     bool done = false;
 
-    if ((pos >> 5) + 36u <= nwords) {
-      // lean window reader: a whole group (50 codes of at most 20 bits) lies inside the input
+    // lean window reader while a whole group (50 codes of at most 20 bits = 32 words) lies inside the input
+    if (window ? (wi < lean_lim) : ((pos >> 5) + 36u <= nwords)) {
       if (!window) {
         const uint32_t w0 = (uint32_t)(pos >> 5), bp = (uint32_t)(pos & 31u);
         v = (((uint64_t)ch_bswap(words[w0]) << 32) | ch_bswap(words[w0 + 1])) << bp;
@@ -206,6 +207,7 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
         nxt = words[wi];
         window = true;
       }
+      if (wi < pf_lim) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + wi + 64));   // the stream two cache lines ahead
       const uint32_t tb = smq_base + t * UB_WSIZE;
       const uint32_t tl = sl1_base + t * (UB_WSIZE * 2u);
       // Table steps while even four-code entries cannot overshoot the group.  Only the bit window is

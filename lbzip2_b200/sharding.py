@@ -303,6 +303,25 @@ class SharedStream:
 # rank 0, which checks the CRCs in stream order.  No collective on the data path besides that
 # gather.  Works over any torch.distributed backend (gloo in the CPU test).
 
+def share_of_candidates(hits, n_bytes, rank, world):
+    """This rank's candidates.  Work per candidate grows with the compressed bytes up to the next
+    candidate, and streams written by lbzip2 alternate large blocks with tiny spill blocks, so a
+    plain round robin would give every other rank all the large ones: candidates are dealt out
+    largest span first to the least loaded rank (the same deal on every rank), kept in stream order."""
+    if world == 1:
+        return list(hits)
+    ends = list(hits[1:]) + [8 * n_bytes]
+    fixed = 400_000                                   # per-candidate cost (tables, launches) in "bits": also evens out the counts
+    order = sorted(range(len(hits)), key=lambda i: (-(ends[i] - hits[i]), i))
+    load = [0] * world
+    owner = [0] * len(hits)
+    for i in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += ends[i] - hits[i] + fixed
+    return [h for i, h in enumerate(hits) if owner[i] == rank]
+
+
 def _row(b):
     return (int(b.pos), int(b.end_bit), int(b.out_len), int(b.status), int(b.block_size), int(b.rl_state),
             int(b.bwt_idx), int(b.rand))
@@ -318,7 +337,7 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
     still checks the CRCs in stream order; rank 0 then returns None for the output.  `keep` (a dict)
     receives this rank's (parts, payload) for checks by the caller."""
     hits = dec.scan(z)
-    mine = hits[rank::world]
+    mine = share_of_candidates(hits, len(z), rank, world)
     cap_blocks = getattr(dec, "max_blocks", None)
     if cap_blocks is not None and len(mine) > cap_blocks:
         # every candidate of the share stays resident between decode_at and emit_at (the framing walk
@@ -352,23 +371,36 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
             cursor += b[2]
         else:
             local_off.append(noemit)
-    payload, crcs = dec.emit_at(local_off, max(cursor, 1))
+    # a failure on one rank (e.g. its output buffer is too small) must not leave the others waiting
+    # in a collective: it travels with the gathered parts and is raised everywhere afterwards
+    failure = None
+    try:
+        payload, crcs = dec.emit_at(local_off, max(cursor, 1))
+    except Exception as ex:
+        failure, payload, crcs = "rank %d: %s" % (rank, ex), b"", [0] * len(rows)
     parts = [(goff[b[0]], b[2], local_off[i], crcs[i]) for i, b in enumerate(rows) if b[0] in goff]
     if keep is not None:
         keep["parts"], keep["payload"] = parts, payload
     gathered = [None] * world
     if world > 1:
-        dist.gather_object((parts, payload if gather_payload else None), gathered if rank == 0 else None, dst=0)
+        dist.gather_object((parts, payload if gather_payload else None, failure), gathered if rank == 0 else None, dst=0)
     else:
-        gathered = [(parts, payload if gather_payload else None)]
+        gathered = [(parts, payload if gather_payload else None, failure)]
     if rank != 0:
         final = [None]
         dist.broadcast_object_list(final, src=0)      # a CRC error found by rank 0 outranks the walk's verdict
-        info.status, info.num_blocks = final[0]
+        if final[0][2]:
+            raise RuntimeError(final[0][2])
+        info.status, info.num_blocks = final[0][:2]
         return final[0][0], None, info
+    failures = [g[2] for g in gathered if g[2]]
+    if failures:
+        if world > 1:
+            dist.broadcast_object_list([(status, 0, "; ".join(failures))], src=0)
+        raise RuntimeError("; ".join(failures))
     # rank 0: CRCs in stream order; the first bad block ends the output (src/expand.c:731-736)
     got = {}
-    for prt, pay in gathered:
+    for prt, pay, _ in gathered:
         for g, ln, lo, crc in prt:
             got[g] = (pay[lo:lo + ln] if pay is not None else None, crc)
     out, nblocks = [], 0
@@ -382,5 +414,5 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
     info.num_blocks = nblocks
     info.status = status
     if world > 1:
-        dist.broadcast_object_list([(status, nblocks)], src=0)
+        dist.broadcast_object_list([(status, nblocks, None)], src=0)
     return status, (b"".join(out) if gather_payload else None), info
