@@ -388,14 +388,35 @@ class Decoder:
             pass
 
     def decompress(self, z, cap=None):
-        """(status, output bytes, DStreamInfo).  status: 0, the reference's error kind, or 100."""
+        """(status, output bytes, DStreamInfo).  status: 0, the reference's error kind, or 100.
+        Without `cap` the output grows as needed: the stream is decoded wave by wave
+        (lbz_decoder_open / lbz_decoder_next) into a wave buffer that holds at least the largest
+        possible block (a block of 900 000 bytes of RLE1 output can expand to 46.6 MB), so inputs
+        that expand far beyond any fixed ratio (long runs) decode like everything else."""
         a = _as_u8(z)
+        src = a if a.size else np.zeros(1, np.uint8)
         if cap is None:
-            cap = max(1 << 20, 64 * a.size)
+            wave_cap = max(64 << 20, 4 * a.size)
+            st = self.L.lbz_decoder_open(self.h, src.ctypes.data, a.size, 0)
+            if st < 0:
+                raise LbzError("lbz_decoder_open failed (%d)" % st)
+            info = DStreamInfo()
+            if st != 0:
+                info.status = st
+                return st, b"", info
+            buf = np.empty(wave_cap, dtype=np.uint8)
+            parts = []
+            while True:
+                n = C.c_size_t(0)
+                st = self.L.lbz_decoder_next(self.h, buf.ctypes.data, wave_cap, C.byref(n), C.byref(info))
+                if st < 0:
+                    raise LbzError("lbz_decoder_next failed (%d)" % st)
+                parts.append(buf[: n.value].tobytes())
+                if st != 1:                      # LBZ_MORE: another wave follows
+                    return st, b"".join(parts), info
         out = np.empty(max(cap, 1), dtype=np.uint8)
         n = C.c_size_t(0)
         info = DStreamInfo()
-        src = a if a.size else np.zeros(1, np.uint8)
         st = self.L.lbz_decompress_stream(self.h, src.ctypes.data, a.size, out.ctypes.data, cap, C.byref(n),
                                           C.byref(info))
         if st < 0:

@@ -169,8 +169,12 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
   // window of the lean reader, carried from group to group: v = the next `avail` bits of the block,
   // left-justified (at least 32 of them whenever a table is consulted), wi = index of the word that
   // is appended next, nxt = that word (raw).  Position = 32 wi - avail.
+  // (the next word is addressed by a pointer that lives in registers: indexing the parameter made the
+  // compiler re-load the base from the constant bank, ~40 cycles in front of every refill test)
   uint64_t v = 0;
-  uint32_t avail = 0, wi = 0, nxt = 0;
+  uint32_t avail = 0, nxt = 0;
+  const uint32_t *wp = words;                        // address of the word that is appended next (= nxt)
+#define wi ((uint32_t)(wp - words))
   const uint32_t pf_lim = nwords > 64u ? (uint32_t)(nwords - 64u < 0xFFFFFFFFull ? nwords - 64u : 0xFFFFFFFFull) : 0u;   // prefetch stays inside the input
   // wi = (pos >> 5) + 2 or + 1 (+2 right after a refill, the window then holds 33..64 bits): wi + 34 <= nwords implies the lean test
   const uint32_t lean_lim = nwords > 34u ? (uint32_t)(nwords - 34u < 0xFFFFFFFFull ? nwords - 34u : 0xFFFFFFFFull) : 0u;
@@ -179,8 +183,8 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
   do {                                                                                           \
     v |= (uint64_t)ch_bswap(nxt) << (32u - avail);                                               \
     avail += 32u;                                                                                \
-    wi++;                                                                                        \
-    nxt = words[wi];                                                                             \
+    wp++;                                                                                        \
+    nxt = *wp;                                                                                   \
   } while (0)
 
   for (; g < nsel; g++) {
@@ -203,11 +207,11 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
         const uint32_t w0 = (uint32_t)(pos >> 5), bp = (uint32_t)(pos & 31u);
         v = (((uint64_t)ch_bswap(words[w0]) << 32) | ch_bswap(words[w0 + 1])) << bp;
         avail = 64u - bp;
-        wi = w0 + 2u;
-        nxt = words[wi];
+        wp = words + w0 + 2u;
+        nxt = *wp;
         window = true;
       }
-      if (wi < pf_lim) asm volatile("prefetch.global.L1 [%0];" ::"l"(words + wi + 64));   // the stream two cache lines ahead
+      if (wi < pf_lim) asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));          // the stream two cache lines ahead
       const uint32_t tb = smq_base + t * UB_WSIZE;
       const uint32_t tl = sl1_base + t * (UB_WSIZE * 2u);
       // Table steps while even four-code entries cannot overshoot the group.  Only the bit window is
@@ -276,6 +280,7 @@ k_ub_chain2(const uint32_t *__restrict__ words, uint64_t nwords, UbBlock *blk, u
   }
   if (window && status != UB_OK) pos = ((uint64_t)wi << 5) - avail;              // ran out of selectors inside the window reader
 #undef CH_REFILL
+#undef wi
   if (writer) {
     B.nsym = nsym;
     B.ngrp = g;

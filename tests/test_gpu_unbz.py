@@ -198,3 +198,14 @@ def test_fuzz_against_oracle(dec):
         assert st == ost and out == oout and info.num_blocks == osi.num_blocks, (st, ost, z.hex()[:80])
         seen[st] = seen.get(st, 0) + 1
     assert len(seen) >= 10, seen
+
+
+def test_default_capacity_grows_with_the_output(dec):
+    """Decoder.decompress without `cap`: inputs that expand far beyond any fixed ratio (10 MB of zeros
+    are a few hundred bytes of .bz2) decode wave by wave into a growing output."""
+    import bz2
+    data = b"\0" * 10_000_000 + b"tail"
+    z = bz2.compress(data, 9)
+    assert len(z) * 64 < len(data)
+    st, out, info = dec.decompress(z)
+    assert st == 0 and out == data and info.num_blocks >= 11
