@@ -471,10 +471,7 @@ def run_ours(a):
     gth = sharding.BlockGatherer(dist, dev, max_blocks=2 * nchunks + 2, max_payload=cap) if world > 1 else None
     # N > 1, host leg: ONE stream-ordered .bz2 in host memory shared by the ranks (a /dev/shm file
     # mapped by every rank, registered with CUDA); completed inside the timed region of every step
-    sink = None
-    if world > 1:
-        sink = sharding.SharedStream(dist, dev, "/dev/shm/lbz_bench_stream_%s.bz2" % os.environ.get("MASTER_PORT", "0"),
-                                     world * cap + 64, max_blocks=2 * nchunks + 2)
+    sink = None                                   # created after the device leg, when the stream size is known
 
     def gather(recs, payload_dev):
         """Device leg: NCCL gather of the block bitstreams into rank 0's HBM in one
@@ -541,6 +538,13 @@ def run_ours(a):
                     clocks=clocks, last=last, eng_ms=sum(eng_ms))
 
     rd = timed(step_device)
+    if world > 1:
+        # the output is deterministic: the device leg tells how long the assembled stream is, so the
+        # shared mapping (registered with CUDA by every rank) is no larger than it has to be
+        tot_out = torch.tensor([rd["last"][2]], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot_out)
+        sink = sharding.SharedStream(dist, dev, "/dev/shm/lbz_bench_stream_%s.bz2" % os.environ.get("MASTER_PORT", "0"),
+                                     int(tot_out.item()) + (1 << 20), max_blocks=2 * nchunks + 2)
     rh = timed(step_host)
     sort_rounds = eng.last_rounds
     dev_bytes = eng.device_bytes

@@ -150,6 +150,8 @@ do_stage(void)
 }
 
 
+static int deferred_err = LBZ_OK;   /* data error found by the last wave, raised after its valid bytes are written */
+
 static bool
 input_complete(void)
 {
@@ -202,8 +204,14 @@ do_decode(void)
   stat_gpu += now() - t0;
   if (rv < 0 || rv == LBZ_ERR_OUTCAP)
     failx(0, "GPU decompression failed (lbz_decoder_next returned %d)", rv);
-  if (rv != LBZ_OK && rv != LBZ_MORE)
-    failf(&ispec, "compressed data error: %s", lbz_strerror(rv));
+  if (rv != LBZ_OK && rv != LBZ_MORE) {
+    /* a data error: the `got` bytes in front of the bad block are valid (lbz_decoder_next
+       guarantees it).  Like the reference, which has handed the blocks before the bad one to
+       the writer when it fails (src/expand.c:703-741), they are written first; the error is
+       raised once the writer has drained (uninit). */
+    deferred_err = rv;
+    rv = LBZ_OK;
+  }
 
   oblk = XMALLOC(struct out_blk);
   oblk->buffer = buf;
@@ -326,6 +334,11 @@ init(void)
 static void
 uninit(void)
 {
+  if (deferred_err != LBZ_OK) {
+    int e = deferred_err;
+    deferred_err = LBZ_OK;
+    failf(&ispec, "compressed data error: %s", lbz_strerror(e));
+  }
   if (stats) {
     fprintf(stderr, "lbzip2_b200: %zu compressed bytes, %lu blocks in %lu "
             "waves (%lu scanner candidates, %lu rejected); decoder set-up "

@@ -234,6 +234,13 @@ class SharedStream:
                 self.registered = int(rc) == 0
             except Exception:
                 self.registered = False
+            if not self.registered:
+                # a refused registration (locked-memory limits) leaves a CUDA error behind that the next
+                # torch call would report: clear it; the copies then go through staged (pageable) D2H
+                try:
+                    torch.cuda.cudart().cudaGetLastError()
+                except Exception:
+                    pass
         on_gpu = str(device) != "cpu"
         self.tbuf = torch.zeros((1 + self.max_blocks, 3), dtype=torch.int64, device=device)
         self.tstage = torch.zeros((1 + self.max_blocks, 3), dtype=torch.int64)
