@@ -663,12 +663,65 @@ extern "C" int lbz_compress_chunks_h2d(lbz_engine *e, const uint8_t *in, size_t 
   return compress_any(e, in, n, reinterpret_cast<uint8_t *>(d_out), out_cap, false, true, out_len, recs, max_recs, num_recs);
 }
 
+// One launch instead of one copy per block: every CTA row moves one block from HBM to its place in
+// the (CUDA-registered, hence device-visible) host buffer, 4-byte words assembled from the two
+// source words they straddle (source and destination are byte-aligned independently).
+__global__ void __launch_bounds__(256)
+k_scatter_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, uint8_t *__restrict__ dst,
+                 const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ len) {
+  const uint32_t i = blockIdx.y;
+  const uint64_t n = len[i];
+  const uint8_t *s = src + src_off[i];
+  uint8_t *d = dst + dst_off[i];
+  // head bytes up to the first 4-byte boundary of the destination
+  const uint64_t head0 = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(d) & 3u)) & 3u;
+  const uint64_t head = n < head0 ? n : head0;
+  const uint64_t words = (n - head) / 4u;
+  const uint64_t tail0 = head + 4u * words;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
+    if (threadIdx.x < n - tail0) d[tail0 + threadIdx.x] = s[tail0 + threadIdx.x];
+  }
+  const uint8_t *sb = s + head;
+  const uint32_t sh = 8u * (uint32_t)(reinterpret_cast<uintptr_t>(sb) & 3u);
+  const uint32_t *sw = reinterpret_cast<const uint32_t *>(sb - (sh >> 3));     // aligned word that holds sb[0]
+  uint32_t *dw = reinterpret_cast<uint32_t *>(d + head);
+  for (uint64_t w = (uint64_t)blockIdx.x * 256u + threadIdx.x; w < words; w += (uint64_t)gridDim.x * 256u) {
+    const uint32_t lo = sw[w];
+    const uint32_t hi = sh ? sw[w + 1] : 0u;            // within the source allocation: the block has >= 4 more bytes or slack follows
+    dw[w] = sh ? __funnelshift_r(lo, hi, sh) : lo;
+  }
+}
+
 extern "C" int lbz_scatter_to_host(lbz_engine *e, const void *d_src, const uint64_t *src_off, void *h_dst,
                                    const uint64_t *dst_off, const uint64_t *len, size_t count) {
   if (!e) return -1;
+  if (count == 0) return 0;
   ENG_CHECK(cudaSetDevice(e->device));
   const uint8_t *s = reinterpret_cast<const uint8_t *>(d_src);
   uint8_t *d = reinterpret_cast<uint8_t *>(h_dst);
+  // a pinned / registered destination is visible from the device: one kernel writes all blocks
+  cudaPointerAttributes at;
+  void *dev_view = nullptr;
+  if (cudaPointerGetAttributes(&at, h_dst) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+    dev_view = at.devicePointer;
+  else
+    cudaGetLastError();
+  static int use_kernel = -1;
+  if (use_kernel < 0) { const char *ev = getenv("LBZ_SCATTER_KERNEL"); use_kernel = ev ? atoi(ev) : 1; }
+  if (dev_view && use_kernel && count <= 65535) {
+    uint64_t *tab = nullptr;                           // [src_off | dst_off | len] on the device
+    ENG_CHECK(cudaMallocAsync((void **)&tab, 3 * count * sizeof(uint64_t), e->st));
+    ENG_CHECK(cudaMemcpyAsync(tab, src_off, count * sizeof(uint64_t), cudaMemcpyHostToDevice, e->st));
+    ENG_CHECK(cudaMemcpyAsync(tab + count, dst_off, count * sizeof(uint64_t), cudaMemcpyHostToDevice, e->st));
+    ENG_CHECK(cudaMemcpyAsync(tab + 2 * count, len, count * sizeof(uint64_t), cudaMemcpyHostToDevice, e->st));
+    k_scatter_blocks<<<dim3(8, (unsigned)count), 256, 0, e->st>>>(s, tab, reinterpret_cast<uint8_t *>(dev_view), tab + count,
+                                                                 tab + 2 * count);
+    ENG_CHECK(cudaGetLastError());
+    ENG_CHECK(cudaFreeAsync(tab, e->st));
+    ENG_CHECK(cudaStreamSynchronize(e->st));
+    return 0;
+  }
   for (size_t i = 0; i < count; i++)
     if (len[i]) ENG_CHECK(cudaMemcpyAsync(d + dst_off[i], s + src_off[i], len[i], cudaMemcpyDeviceToHost, (i & 1) ? e->st_copy : e->st));
   ENG_CHECK(cudaStreamSynchronize(e->st));

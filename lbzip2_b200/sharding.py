@@ -198,9 +198,12 @@ def place_blocks(tables, world, header=4):
     off = np.empty_like(off_sorted)
     off[order] = off_sorted
     offs = [off[owner == r] for r in range(world)]
-    cc = 0
-    for c in crcs[order].tolist():
-        cc = (((cc << 1) & 0xFFFFFFFF) ^ (cc >> 31) ^ (c & 0xFFFFFFFF) ^ 0xFFFFFFFF) & 0xFFFFFFFF
+    # combined CRC (cc' = rotl(cc, 1) ^ ~crc, src/encode.h:38) without a Python loop: the fold is linear
+    # over GF(2), block k of n contributes ~crc_k rotated left by (n - 1 - k) mod 32
+    x = (~crcs[order]) & 0xFFFFFFFF
+    r = (len(x) - 1 - np.arange(len(x))) % 32
+    rot = ((x << r) | (x >> (32 - r))) & 0xFFFFFFFF
+    cc = int(np.bitwise_xor.reduce(rot)) if len(x) else 0
     return offs, int(header + lens.sum()), cc
 
 
