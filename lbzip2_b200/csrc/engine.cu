@@ -663,6 +663,9 @@ extern "C" int lbz_compress_chunks_h2d(lbz_engine *e, const uint8_t *in, size_t 
   return compress_any(e, in, n, reinterpret_cast<uint8_t *>(d_out), out_cap, false, true, out_len, recs, max_recs, num_recs);
 }
 
+// Optional (LBZ_SCATTER_KERNEL=1; measured SLOWER than the per-block copies on B200 -- SM stores over
+// PCIe reach a fraction of the copy engines' rate: 30.2 vs 18.3 ms per 100 MB step at N=2,
+// profiles/r02_n2_scatter_kernel_vs_memcpy.log -- so the copy engines are the default).
 // One launch instead of one copy per block: every CTA row moves one block from HBM to its place in
 // the (CUDA-registered, hence device-visible) host buffer, 4-byte words assembled from the two
 // source words they straddle (source and destination are byte-aligned independently).
@@ -708,7 +711,7 @@ extern "C" int lbz_scatter_to_host(lbz_engine *e, const void *d_src, const uint6
   else
     cudaGetLastError();
   static int use_kernel = -1;
-  if (use_kernel < 0) { const char *ev = getenv("LBZ_SCATTER_KERNEL"); use_kernel = ev ? atoi(ev) : 1; }
+  if (use_kernel < 0) { const char *ev = getenv("LBZ_SCATTER_KERNEL"); use_kernel = ev ? atoi(ev) : 0; }
   if (dev_view && use_kernel && count <= 65535) {
     uint64_t *tab = nullptr;                           // [src_off | dst_off | len] on the device
     ENG_CHECK(cudaMallocAsync((void **)&tab, 3 * count * sizeof(uint64_t), e->st));
@@ -839,6 +842,10 @@ extern "C" void lbz_set_fatal_handler(void (*fn)(const char *msg)) { g_fatal = f
 // time from the polynomial (build-aux/make-crctab.pl:29-33): poly 0x04C11DB7, MSB first.
 extern "C" { uint32_t crc_table[256]; }
 __attribute__((constructor)) static void lbz_init_crc_table() {
+  // The per-block API keeps one stream per worker thread busy (pooled contexts, single-block decoders);
+  // with the default of 8 hardware work queues, streams beyond the eighth are serialised behind the
+  // others.  Takes effect if the CUDA context is created after this library is loaded.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   for (uint32_t i = 0; i < 256; i++) {
     uint32_t r = i << 24;
     for (int k = 0; k < 8; k++) r = (r & 0x80000000u) ? (r << 1) ^ 0x04C11DB7u : (r << 1);
