@@ -238,7 +238,8 @@ enum lbz_status {
   LBZ_ERR_SELECTOR = 8, LBZ_ERR_DELTA = 9, LBZ_ERR_PREFIX = 10, LBZ_ERR_INCOMPLT = 11,
   LBZ_ERR_EMPTY = 12, LBZ_ERR_UNTERM = 13, LBZ_ERR_RUNLEN = 14, LBZ_ERR_BLKCRC = 15,
   LBZ_ERR_STRMCRC = 16, LBZ_ERR_OVERFLOW = 17, LBZ_ERR_BWTIDX = 18, LBZ_ERR_EOF = 19,
-  LBZ_ERR_OUTCAP = 100       /* ours: the caller's output buffer is too small */
+  LBZ_ERR_OUTCAP = 100,      /* ours: the caller's output buffer is too small */
+  LBZ_NEED_INPUT = 101       /* ours: lbz_decoder_next of a streaming session wants lbz_decoder_feed first */
 };
 /* The reference's message for a status (src/expand.c:70-94, src/process.c:680). */
 const char *lbz_strerror(int status);
@@ -304,6 +305,20 @@ int lbz_decompress_ex(lbz_decoder *d, const uint8_t *in, size_t n, uint8_t *out,
    last call. */
 int lbz_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags);
 int lbz_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info);
+
+/* The same for a file that ARRIVES IN PIECES (a pipe, a file larger than memory): only a window of
+   at most in_cap compressed bytes is resident, on the device for the kernels and mirrored on the
+   host for the framing walk -- memory is bounded by the decoder's capacities, not by the file, and
+   reading overlaps decoding.  open_stream starts the session; feed appends up to n bytes (*taken of
+   them were accepted: the window is full until further waves have consumed its front; the consumed
+   front is dropped when room is needed) and says with eof != 0 that these were the last bytes;
+   next works as above on the blocks that are completely resident and returns LBZ_NEED_INPUT (no
+   output) when the next block or the framing behind it has not arrived yet.  While eof has not been
+   announced, running out of input is never an error (the reference's retrieve() answers MORE in the
+   same situation, src/decode.c:387-396); afterwards the end-of-file rules of lbz_decoder_open apply.
+   info->end_bit stays an absolute position in the file. */
+int lbz_decoder_open_stream(lbz_decoder *d, unsigned flags);
+int lbz_decoder_feed(lbz_decoder *d, const uint8_t *in, size_t n, int eof, size_t *taken);
 
 /* Building blocks for sharding the blocks of ONE file over several decoders / GPUs (blocks are
    independent once the scanner has found their start bits; lbzip2_b200/sharding.py

@@ -83,7 +83,7 @@ EXPORTS = [
     "lbz_decoder_load", "lbz_scan_blocks", "lbz_decoder_read", "lbz_decoder_last_wave_blocks",
     "lbz_decoder_launches", "lbz_decoder_device_bytes", "lbz_decoder_last_ms", "lbz_decoder_stage_ms",
     "lbz_strerror", "lbz_decoder_open", "lbz_decoder_next",
-    "lbz_decoder_decode_at", "lbz_decoder_emit_at", "lbz_walk_table",
+    "lbz_decoder_decode_at", "lbz_decoder_emit_at", "lbz_walk_table", "lbz_decoder_open_stream", "lbz_decoder_feed",
 ]
 
 
@@ -183,6 +183,10 @@ def load_library():
     L.lbz_decoder_stage_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.lbz_decoder_open.restype = C.c_int
     L.lbz_decoder_open.argtypes = [vp, vp, C.c_size_t, C.c_uint]
+    L.lbz_decoder_open_stream.restype = C.c_int
+    L.lbz_decoder_open_stream.argtypes = [vp, C.c_uint]
+    L.lbz_decoder_feed.restype = C.c_int
+    L.lbz_decoder_feed.argtypes = [vp, vp, C.c_size_t, C.c_int, szp]
     L.lbz_decoder_next.restype = C.c_int
     L.lbz_decoder_next.argtypes = [vp, vp, C.c_size_t, szp, C.POINTER(DStreamInfo)]
     L.lbz_decoder_decode_at.restype = C.c_int
@@ -196,6 +200,25 @@ def load_library():
     L.lbz_strerror.argtypes = [C.c_int]
     _LIB = L
     return L
+
+
+class PinnedArray:
+    """A uint8 numpy array over page-locked host memory (lbz_host_alloc): copies to and from the
+    device run at the full link rate and asynchronously.  `.a` is the array; close() frees it."""
+
+    def __init__(self, nbytes, L=None):
+        self.L = L or load_library()
+        self.n = max(int(nbytes), 1)
+        self.ptr = self.L.lbz_host_alloc(self.n)
+        if not self.ptr:
+            raise LbzError("lbz_host_alloc(%d) failed" % self.n)
+        self.a = np.ctypeslib.as_array((C.c_uint8 * self.n).from_address(self.ptr))
+
+    def close(self):
+        if self.ptr:
+            self.a = None
+            self.L.lbz_host_free(self.ptr)
+            self.ptr = None
 
 
 def _as_u8(data):
@@ -444,28 +467,87 @@ class Decoder:
             if st != 1:
                 return
 
+    def decompress_pieces(self, pieces, wave_cap):
+        """Streaming session (lbz_decoder_open_stream / feed / next): `pieces` is an iterable of
+        bytes-like parts of one file, of any sizes; only a window of in_cap compressed bytes is
+        resident.  Returns (status, output bytes, info)."""
+        if self.L.lbz_decoder_open_stream(self.h, 0) != 0:
+            raise LbzError("lbz_decoder_open_stream failed")
+        buf = np.empty(max(wave_cap, 1), dtype=np.uint8)
+        out = []
+        info = DStreamInfo()
+        it = iter(pieces)
+        cur, off, eof = np.zeros(0, np.uint8), 0, False
+
+        def feed():
+            nonlocal cur, off, eof
+            progressed = False
+            while not eof:
+                if off >= cur.size:
+                    nxt = next(it, None)
+                    if nxt is None:
+                        if self.L.lbz_decoder_feed(self.h, buf.ctypes.data, 0, 1, None) != 0:
+                            raise LbzError("lbz_decoder_feed failed")
+                        eof = True
+                        return True
+                    cur, off = _as_u8(nxt), 0
+                    continue
+                took = C.c_size_t(0)
+                if self.L.lbz_decoder_feed(self.h, cur[off:].ctypes.data, cur.size - off, 0, C.byref(took)) != 0:
+                    raise LbzError("lbz_decoder_feed failed")
+                off += took.value
+                progressed = progressed or took.value > 0
+                if off < cur.size:          # window full
+                    return progressed
+            return progressed
+
+        feed()
+        while True:
+            n = C.c_size_t(0)
+            st = self.L.lbz_decoder_next(self.h, buf.ctypes.data, wave_cap, C.byref(n), C.byref(info))
+            if st < 0:
+                raise LbzError("lbz_decoder_next failed")
+            if n.value:
+                out.append(buf[: n.value].tobytes())
+            if st == 1:                     # LBZ_MORE: blocks remain in the window; top it up meanwhile
+                feed()
+                continue
+            if st == 101:                   # LBZ_NEED_INPUT
+                if not feed():
+                    raise LbzError("the decoder wants input but its window is full")
+                continue
+            return st, b"".join(out), info
+
     # ---- sharding building blocks (see lbzip2_b200/sharding.py sharded_decompress) ----
-    def decode_at(self, z, positions):
-        """Decode the candidate blocks whose magics start at the given bit positions; list of DBlock."""
+    keeps_scanned_input = True        # scan() leaves the stream on the device: decode_at(..., resident=True)
+
+    def decode_at(self, z, positions, resident=False):
+        """Decode the candidate blocks whose magics start at the given bit positions; list of DBlock.
+        resident=True: `z` is the input the decoder already holds (scan() / load() of the same bytes),
+        no second upload."""
         a = _as_u8(z)
         k = len(positions)
         pos = (C.c_uint64 * max(k, 1))(*positions)
         table = (DBlock * max(k, 1))()
         src = a if a.size else np.zeros(1, np.uint8)
-        if self.L.lbz_decoder_decode_at(self.h, src.ctypes.data, a.size, pos, k, table, 0):
+        if self.L.lbz_decoder_decode_at(self.h, src.ctypes.data, a.size, pos, k, table, 1 if resident else 0):
             raise LbzError("lbz_decoder_decode_at failed")
         return [dblock_copy(table[i]) for i in range(k)]
 
-    def emit_at(self, out_offs, cap):
-        """Write the blocks of the last decode_at at the given offsets (NOEMIT = skip): (bytes, crcs)."""
+    def emit_at(self, out_offs, cap, out=None):
+        """Write the blocks of the last decode_at at the given offsets (NOEMIT = skip): (bytes, crcs).
+        `out` (a uint8 array of >= cap bytes, e.g. pinned_u8()): the decoded bytes land there and a
+        view of it is returned instead of a copy."""
         k = len(out_offs)
         offs = (C.c_uint64 * max(k, 1))(*out_offs)
         crc = (C.c_uint32 * max(k, 1))()
-        buf = np.empty(max(cap, 1), dtype=np.uint8)
+        if out is not None and out.size < cap:
+            raise LbzError("emit_at: the output array holds %d bytes, %d needed" % (out.size, cap))
+        buf = out if out is not None else np.empty(max(cap, 1), dtype=np.uint8)
         n = C.c_size_t(0)
         if self.L.lbz_decoder_emit_at(self.h, offs, k, buf.ctypes.data, cap, C.byref(n), crc):
             raise LbzError("lbz_decoder_emit_at failed")
-        return buf[: n.value].tobytes(), list(crc[:k])
+        return (buf[: n.value] if out is not None else buf[: n.value].tobytes()), list(crc[:k])
 
     def walk_table(self, z, table):
         return walk_table(self.L.lbz_walk_table, z, table)
@@ -486,12 +568,12 @@ class Decoder:
     def scan(self, z):
         a = _as_u8(z)
         cap = a.size // 6 + 64
-        pos = (C.c_uint64 * cap)()
+        pos = np.empty(cap, dtype=np.uint64)           # untouched pages cost nothing: only the hits are written
         src = a if a.size else np.zeros(1, np.uint8)
-        k = self.L.lbz_scan_blocks(self.h, src.ctypes.data, a.size, pos, cap)
+        k = self.L.lbz_scan_blocks(self.h, src.ctypes.data, a.size, pos.ctypes.data_as(C.POINTER(C.c_uint64)), cap)
         if k < 0:
             raise LbzError("lbz_scan_blocks failed")
-        return list(pos[:k])
+        return pos[:k].tolist()
 
     def block(self, slot):
         b = DBlock()

@@ -396,42 +396,22 @@ struct TextSmem2 {
 
 // LIST = 1: the same pass over the (32-bit key, index) pairs of a block's round list L
 // (segment = meta.ul elements at list offset meta.lbase; digit bases per block and pass).
-template <int MODE, int LAST, int MINB, int LIST = 0>
-__global__ void __launch_bounds__(512, MINB)
-k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
-             const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
-             uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
-             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride,
-             uint32_t xpose, uint32_t nb) {
-  extern __shared__ __align__(16) unsigned char radix_smem_raw[];
-  TextSmem2 &S = *reinterpret_cast<TextSmem2 *>(radix_smem_raw);
+// SH >= 0: the digit's bit offset is a compile-time constant (byte extraction becomes one PRMT, no
+// reload of the launch parameter); FULL: a tile of exactly RTILE elements, no per-item bound checks
+// (all tiles of a block but its last).  The digit start table `delta` includes the slot offset, so
+// the write-out index is one 32-bit add.
+template <int MODE, int LAST, int LIST, int SH, bool FULL>
+__device__ __forceinline__ void text_pass2_tile(TextSmem2 &S, const uint8_t *__restrict__ T, const uint2 *__restrict__ src,
+                                                uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
+                                                uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
+                                                uint32_t shift_rt, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff,
+                                                uint32_t gstride, uint32_t b, uint32_t tile, uint32_t n, uint32_t off,
+                                                uint32_t tbase, uint32_t tile_cnt_rt, uint32_t rtiles) {
   constexpr int THREADS = 512, ITEMS = 8;
   constexpr uint32_t RTILE = THREADS * ITEMS;
-  const uint32_t rtiles = g.S1 / RTILE;
-  // xpose: grid = (blocks of a group, tiles, groups) -- CTAs are dispatched x-fastest, so consecutive
-  // CTAs then work on different blocks and a tile's predecessor has usually published its inclusive
-  // prefix.  The group is the whole batch except for the pass that gathers from the text (MODE 1):
-  // there 32 blocks share the resident CTAs, so that their text (29 MB) stays in L2 -- spread over
-  // all blocks of the batch every gathered sector came from DRAM (5.2 GB per launch instead of 0.8).
-  const uint32_t b = xpose ? blockIdx.z * gridDim.x + blockIdx.x : blockIdx.y, tile = xpose ? blockIdx.y : blockIdx.x;
-  if (b >= nb) return;
-  const uint32_t n = meta[b].n;
-  const uint32_t cnt = LIST ? meta[b].ul : n;
-  const uint32_t tbase = tile * RTILE;
-  if (tbase >= cnt) return;
-  const uint32_t off = lbz_slot_off(g, b) + (LIST ? meta[b].lbase : 0u);
-  const uint32_t tile_cnt = min(RTILE, cnt - tbase);
+  const uint32_t shift = SH >= 0 ? (uint32_t)SH : shift_rt;
+  const uint32_t tile_cnt = FULL ? RTILE : tile_cnt_rt;
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-  if (MODE == 0 && xpose > 1u && tid == 0) {
-    // TMA bulk prefetch into L2 of the tile that the CTA dispatched `xpose` rows later will load
-    // (block-fastest dispatch: that CTA starts about when the CTAs resident now retire)
-    const uint32_t t2 = tbase + xpose * RTILE;
-    if (t2 < cnt) {
-      const uint32_t e0 = (off + t2) & ~1u;
-      const uint32_t bytes = (min(RTILE, cnt - t2) * 8u) & ~15u;
-      if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + e0), "r"(bytes) : "memory");
-    }
-  }
   const uint32_t wbase = warp * (32 * ITEMS) + lane;              // tile index of this thread's item 0
   const uint32_t lim = tile_cnt > wbase ? tile_cnt - wbase : 0u;  // item `it` exists iff it * 32 < lim
 
@@ -443,7 +423,7 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
     const uint2 *sp = src + off + tbase + wbase;
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
-      const uint2 pr = (it * 32u < lim) ? sp[it * 32] : make_uint2(0u, 0u);
+      const uint2 pr = (FULL || it * 32u < lim) ? sp[it * 32] : make_uint2(0u, 0u);
       key[it] = pr.x; val[it] = pr.y;
     }
   }
@@ -454,11 +434,11 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   }
   if (MODE == 1) {
 #pragma unroll
-    for (int it = 0; it < ITEMS; it++) key[it] = (it * 32u < lim) ? text_key4(T + off, val[it], n) : 0u;
+    for (int it = 0; it < ITEMS; it++) key[it] = (FULL || it * 32u < lim) ? text_key4(T + off, val[it], n) : 0u;
   }
   if (MODE == 2) {
 #pragma unroll
-    for (int it = 0; it < ITEMS; it++) key[it] = (it * 32u < lim) ? text_key4(T + off, wrap_add(val[it], koff, n), n) : 0u;
+    for (int it = 0; it < ITEMS; it++) key[it] = (FULL || it * 32u < lim) ? text_key4(T + off, wrap_add(val[it], koff, n), n) : 0u;
   }
   __syncthreads();
 
@@ -469,7 +449,7 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
   for (int q = 0; q < ITEMS / 4; q++) rkp[q] = 0;
 #pragma unroll
   for (int it = 0; it < ITEMS; it++) {
-    const bool valid = it * 32u < lim;
+    const bool valid = FULL || it * 32u < lim;
     const uint32_t digit = valid ? ((key[it] >> shift) & 0xFFu) : 0x100u;   // missing items: a group of their own
     const uint32_t mask = __match_any_sync(0xffffffffu, digit);
     uint32_t base = 0;
@@ -515,7 +495,7 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
     const uint32_t *drow = &S.dstart[half][0];
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
-      if (it * 32u < lim) {
+      if (FULL || it * 32u < lim) {
         const uint32_t digit = (key[it] >> shift) & 0xFFu;
         const uint32_t slot = drow[digit] + wrow[digit] + ((rkp[it >> 2] >> (8 * (it & 3))) & 0xFFu);
         S.spair[slot] = make_uint2(key[it], val[it]);
@@ -558,26 +538,65 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
       }
       st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total) & TS_VALUE_MASK));
     }
-    S.delta[d] = gbase[(size_t)b * gstride + d] + excl - dst0;
+    S.delta[d] = gbase[(size_t)b * gstride + d] + excl - dst0 + off;   // slot offset folded in
   }
   __syncthreads();
   if (LAST) {
-    uint32_t *o = sa_out + off;
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
       const uint32_t i = tid + k * THREADS;
-      if (i < tile_cnt) { const uint2 pr = S.spair[i]; o[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr.y; }
+      if (FULL || i < tile_cnt) { const uint2 pr = S.spair[i]; sa_out[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr.y; }
     }
   } else {
-    uint2 *o = dst + off;
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
       const uint32_t i = tid + k * THREADS;
-      if (i < tile_cnt) { const uint2 pr = S.spair[i]; o[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr; }
+      if (FULL || i < tile_cnt) { const uint2 pr = S.spair[i]; dst[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr; }
     }
   }
 }
 
+template <int MODE, int LAST, int MINB, int LIST = 0, int SH = -1>
+__global__ void __launch_bounds__(512, MINB)
+k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+             const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
+             uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
+             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride,
+             uint32_t xpose, uint32_t nb) {
+  extern __shared__ __align__(16) unsigned char radix_smem_raw[];
+  TextSmem2 &S = *reinterpret_cast<TextSmem2 *>(radix_smem_raw);
+  constexpr uint32_t RTILE = 512 * 8;
+  const uint32_t rtiles = g.S1 / RTILE;
+  // xpose: grid = (blocks of a group, tiles, groups) -- CTAs are dispatched x-fastest, so consecutive
+  // CTAs then work on different blocks and a tile's predecessor has usually published its inclusive
+  // prefix.  The group is the whole batch except for the pass that gathers from the text (MODE 1):
+  // there 32 blocks share the resident CTAs, so that their text (29 MB) stays in L2 -- spread over
+  // all blocks of the batch every gathered sector came from DRAM (5.2 GB per launch instead of 0.8).
+  const uint32_t b = xpose ? blockIdx.z * gridDim.x + blockIdx.x : blockIdx.y, tile = xpose ? blockIdx.y : blockIdx.x;
+  if (b >= nb) return;
+  const uint32_t n = meta[b].n;
+  const uint32_t cnt = LIST ? meta[b].ul : n;
+  const uint32_t tbase = tile * RTILE;
+  if (tbase >= cnt) return;
+  const uint32_t off = lbz_slot_off(g, b) + (LIST ? meta[b].lbase : 0u);
+  const uint32_t tile_cnt = min(RTILE, cnt - tbase);
+  if (MODE == 0 && xpose > 1u && threadIdx.x == 0) {
+    // TMA bulk prefetch into L2 of the tile that the CTA dispatched `xpose` rows later will load
+    // (block-fastest dispatch: that CTA starts about when the CTAs resident now retire)
+    const uint32_t t2 = tbase + xpose * RTILE;
+    if (t2 < cnt) {
+      const uint32_t e0 = (off + t2) & ~1u;
+      const uint32_t bytes = (min(RTILE, cnt - t2) * 8u) & ~15u;
+      if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + e0), "r"(bytes) : "memory");
+    }
+  }
+  if (tile_cnt == RTILE)
+    text_pass2_tile<MODE, LAST, LIST, SH, true>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
+                                                tbase, tile_cnt, rtiles);
+  else
+    text_pass2_tile<MODE, LAST, LIST, SH, false>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
+                                                 tbase, tile_cnt, rtiles);
+}
 
 // ---------------------------------------------------------------------------
 // Third implementation of the pass: a PERSISTENT kernel fed by TMA.
@@ -1184,6 +1203,13 @@ static uint32_t tp_xpose() {
   if (v < 0) { const char *ev = getenv("LBZ_TP_XPOSE"); v = ev ? atoi(ev) : 2; if (v < 0 || v > 8) v = 2; }
   return (uint32_t)v;
 }
+// 1 (default): kernels with the digit offset as a compile-time constant; 0: one kernel per pass kind, offset
+// read from the launch parameters
+static bool tp_const_shift() {
+  static int v = -1;
+  if (v < 0) { const char *ev = getenv("LBZ_TP_CONST_SHIFT"); v = ev ? (atoi(ev) != 0) : 1; }
+  return v != 0;
+}
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -1243,14 +1269,33 @@ static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, co
                                                                                           shift, epoch, err, koff);
     return 0;
   }
-  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
   const uint32_t xp = tp_xpose();
   static int ggrp = -1;
   if (ggrp < 0) { const char *ev = getenv("LBZ_TP_GATHER_GROUP"); ggrp = ev ? atoi(ev) : 32; if (ggrp < 1) ggrp = 1; }
   const uint32_t gsz = (MODE == 1) ? min(nb, (uint32_t)ggrp) : nb;
   const dim3 grid = xp ? dim3(gsz, g.S1 / 4096u, (nb + gsz - 1) / gsz) : dim3(g.S1 / 4096u, nb);
-  k_text_pass2<MODE, LAST, MINB><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
-                                                                        shift, epoch, err, koff, 256u, xp, nb);
+#define LBZ_TP2_LAUNCH(SH)                                                                                                  \
+  do {                                                                                                                      \
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB, 0, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)sizeof(TextSmem2)));                                                           \
+    k_text_pass2<MODE, LAST, MINB, 0, SH><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,  \
+                                                                                shift, epoch, err, koff, 256u, xp, nb);     \
+  } while (0)
+  // the digit offsets of the default sort depth (8 bytes) as compile-time constants: the passes that
+  // build keys from the text (MODE 1, 2) work on the lowest digit, the last pass on the highest
+  if (MINB == 3 && tp_const_shift()) {
+    if constexpr (MODE != 0 && !LAST) {
+      if (shift == 0u) { LBZ_TP2_LAUNCH(0); return 0; }
+    } else if constexpr (MODE == 0 && LAST) {
+      if (shift == 24u) { LBZ_TP2_LAUNCH(24); return 0; }
+    } else if constexpr (MODE == 0 && !LAST) {
+      if (shift == 8u) { LBZ_TP2_LAUNCH(8); return 0; }
+      if (shift == 16u) { LBZ_TP2_LAUNCH(16); return 0; }
+      if (shift == 24u) { LBZ_TP2_LAUNCH(24); return 0; }
+    }
+  }
+  LBZ_TP2_LAUNCH(-1);
+#undef LBZ_TP2_LAUNCH
   return 0;
 }
 template <int MODE, int LAST>
@@ -1276,11 +1321,21 @@ static int launch_list_pass(uint32_t max_count, uint32_t nb, cudaStream_t st, co
     return launch_pass4<0, 0, 1>(tiles, nb, st, g, meta, nullptr, src, dst, nullptr, tstat, gbase, gstride, shift, epoch, err, 0u);
   if (tp_version() == 3)
     return launch_pass3<0, 0, 1>(tiles, nb, st, g, meta, nullptr, src, dst, nullptr, tstat, gbase, gstride, shift, epoch, err, 0u, B);
-  LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<0, 0, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
   const uint32_t xp = tp_xpose();
   const dim3 grid = xp ? dim3(nb, tiles) : dim3(tiles, nb);
-  k_text_pass2<0, 0, 3, 1><<<grid, 512, sizeof(TextSmem2), st>>>(
-      g, meta, nullptr, src, dst, nullptr, tstat, gbase, shift, epoch, err, 0u, gstride, xp, nb);
+#define LBZ_TP2_LIST(SH)                                                                                                  \
+  do {                                                                                                                    \
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<0, 0, 3, 1, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                        (int)sizeof(TextSmem2)));                                                         \
+    k_text_pass2<0, 0, 3, 1, SH><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, nullptr, src, dst, nullptr, tstat, gbase,  \
+                                                                       shift, epoch, err, 0u, gstride, xp, nb);           \
+  } while (0)
+  if (tp_const_shift() && shift == 0u) LBZ_TP2_LIST(0);
+  else if (tp_const_shift() && shift == 8u) LBZ_TP2_LIST(8);
+  else if (tp_const_shift() && shift == 16u) LBZ_TP2_LIST(16);
+  else if (tp_const_shift() && shift == 24u) LBZ_TP2_LIST(24);
+  else LBZ_TP2_LIST(-1);
+#undef LBZ_TP2_LIST
   return 0;
 }
 

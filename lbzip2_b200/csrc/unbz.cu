@@ -49,6 +49,16 @@ static int ub_dev_fill32(lbz_decoder *d, uint32_t *p, uint32_t v, size_t count) 
   UB_CUDA(cudaMemsetAsync(p, (int)(v & 0xFFu), count * 4, ub_stream(d)));
   return 0;
 }
+// dst < src inside one allocation: pieces no longer than the distance moved never overlap, and the
+// stream keeps them in order
+static int ub_dev_move(lbz_decoder *d, void *dst, const void *src, size_t bytes) {
+  const size_t gap = (size_t)((const uint8_t *)src - (uint8_t *)dst);
+  for (size_t done = 0; done < bytes; done += gap) {
+    const size_t c = bytes - done < gap ? bytes - done : gap;
+    UB_CUDA(cudaMemcpyAsync((uint8_t *)dst + done, (const uint8_t *)src + done, c, cudaMemcpyDeviceToDevice, ub_stream(d)));
+  }
+  return 0;
+}
 static int ub_sync(lbz_decoder *d) { UB_CUDA(cudaStreamSynchronize(ub_stream(d))); return 0; }
 static void ub_mark(lbz_decoder *d, int i) {
   UbBackend *b = ub_backend(d);
@@ -424,6 +434,17 @@ extern "C" int lbz_decompress_stream(lbz_decoder *d, const uint8_t *in, size_t n
 extern "C" int lbz_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags) {
   if (cudaSetDevice(d->be.device) != cudaSuccess) return -1;
   return ub_open(d, in, n, flags);
+}
+
+extern "C" int lbz_decoder_open_stream(lbz_decoder *d, unsigned flags) {
+  if (cudaSetDevice(d->be.device) != cudaSuccess) return -1;
+  return ub_open_stream(d, flags);
+}
+
+extern "C" int lbz_decoder_feed(lbz_decoder *d, const uint8_t *in, size_t n, int eof, size_t *taken) {
+  if (cudaSetDevice(d->be.device) != cudaSuccess) return -1;
+  size_t dummy = 0;
+  return ub_feed(d, in, n, eof, taken ? taken : &dummy);
 }
 
 extern "C" int lbz_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info) {

@@ -337,7 +337,15 @@ def _row(b):
             int(b.bwt_idx), int(b.rand))
 
 
-def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFFFFFFFFFF, gather_payload=True, keep=None):
+def _decode_share(dec, z, mine):
+    # decoders that keep the scanned input on the device skip the second upload
+    if getattr(dec, "keeps_scanned_input", False):
+        return dec.decode_at(z, mine, resident=True)
+    return dec.decode_at(z, mine)
+
+
+def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFFFFFFFFFF, gather_payload=True, keep=None,
+                       out=None):
     """Decompress the file `z` (bytes, present on every rank) with `world` decoders.
     `dec` offers scan / decode_at / emit_at / walk_table (lbzip2_b200.Decoder).
     Returns (status, output bytes, info) on rank 0 and (the same status, None, info) elsewhere.
@@ -345,7 +353,10 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
     gather_payload=False: the decoded bytes stay in every rank's host memory (a multi-process writer
     would pwrite them at their offsets); only (offset, length, CRC) per block travel to rank 0, which
     still checks the CRCs in stream order; rank 0 then returns None for the output.  `keep` (a dict)
-    receives this rank's (parts, payload) for checks by the caller."""
+    receives this rank's (parts, payload) for checks by the caller.  `out`: a uint8 array (page-locked:
+    api.PinnedArray) that receives this rank's decoded bytes instead of a fresh buffer per call.
+    The stream is uploaded once: the decode of the share works on the bytes the scanner left on
+    the device."""
     hits = dec.scan(z)
     mine = share_of_candidates(hits, len(z), rank, world)
     cap_blocks = getattr(dec, "max_blocks", None)
@@ -354,7 +365,7 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
         # over ALL ranks' tables decides which candidates are blocks): size the decoder for the share
         raise ValueError("decoder holds %d blocks, this rank's share of the file has %d candidates: create the "
                          "Decoder with max_blocks >= ceil(candidates / world)" % (cap_blocks, len(mine)))
-    rows = [_row(b) for b in dec.decode_at(z, mine)]
+    rows = [_row(b) for b in _decode_share(dec, z, mine)]
     every = [None] * world
     if world > 1:
         dist.all_gather_object(every, rows)
@@ -385,7 +396,7 @@ def sharded_decompress(dist, dec, z, rank, world, dblock_type, noemit=0xFFFFFFFF
     # in a collective: it travels with the gathered parts and is raised everywhere afterwards
     failure = None
     try:
-        payload, crcs = dec.emit_at(local_off, max(cursor, 1))
+        payload, crcs = dec.emit_at(local_off, max(cursor, 1)) if out is None else dec.emit_at(local_off, max(cursor, 1), out=out)
     except Exception as ex:
         failure, payload, crcs = "rank %d: %s" % (rank, ex), b"", [0] * len(rows)
     parts = [(goff[b[0]], b[2], local_off[i], crcs[i]) for i, b in enumerate(rows) if b[0] in goff]

@@ -68,6 +68,12 @@ def lib():
         L.emu_walk_table.restype = C.c_int
         L.emu_walk_table.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(DBlock), C.c_size_t, C.POINTER(C.c_uint32),
                                      C.POINTER(C.c_uint32), C.POINTER(C.c_size_t), C.POINTER(DStreamInfo)]
+        L.emu_decoder_open_stream.restype = C.c_int
+        L.emu_decoder_open_stream.argtypes = [C.c_void_p, C.c_uint]
+        L.emu_decoder_feed.restype = C.c_int
+        L.emu_decoder_feed.argtypes = [C.c_void_p, u8p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
+        L.emu_decoder_next.restype = C.c_int
+        L.emu_decoder_next.argtypes = [C.c_void_p, u8p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(DStreamInfo)]
         _lib = L
     return _lib
 
@@ -95,6 +101,55 @@ class EmuDecoder:
         st = self.L.emu_decompress(self.h, a.ctypes.data_as(u8p), len(z), out.ctypes.data_as(u8p), cap,
                                    C.byref(n), C.byref(info), 0)
         return st, out[: n.value].tobytes(), info
+
+    def decompress_pieces(self, pieces, wave_cap, trace=None, greedy=True):
+        """Streaming session (open_stream / feed / next) over the parts of one file; same driver logic
+        as lbzip2_b200.Decoder.decompress_pieces.  trace (a list) receives the status of every next();
+        greedy=False hands over one piece per request (the decoder starves often)."""
+        assert self.L.emu_decoder_open_stream(self.h, 0) == 0
+        buf = np.empty(max(wave_cap, 1), np.uint8)
+        out, info = [], DStreamInfo()
+        it = iter(pieces)
+        state = {"cur": np.zeros(0, np.uint8), "off": 0, "eof": False}
+
+        def feed():
+            progressed = False
+            while not state["eof"]:
+                cur, off = state["cur"], state["off"]
+                if off >= cur.size:
+                    nxt = next(it, None)
+                    if nxt is None:
+                        took = C.c_size_t(0)
+                        assert self.L.emu_decoder_feed(self.h, buf.ctypes.data_as(u8p), 0, 1, C.byref(took)) == 0
+                        state["eof"] = True
+                        return True
+                    state["cur"], state["off"] = np.frombuffer(bytes(nxt), dtype=np.uint8), 0
+                    continue
+                took = C.c_size_t(0)
+                part = cur[off:]
+                assert self.L.emu_decoder_feed(self.h, part.ctypes.data_as(u8p), part.size, 0, C.byref(took)) == 0
+                state["off"] = off + took.value
+                progressed = progressed or took.value > 0
+                if state["off"] < cur.size or not greedy:
+                    return progressed
+            return progressed
+
+        feed()
+        while True:
+            n = C.c_size_t(0)
+            st = self.L.emu_decoder_next(self.h, buf.ctypes.data_as(u8p), wave_cap, C.byref(n), C.byref(info))
+            assert st >= 0, "emu_decoder_next failed"
+            if trace is not None:
+                trace.append(st)
+            if n.value:
+                out.append(buf[: n.value].tobytes())
+            if st == 1:
+                feed()
+                continue
+            if st == 101:
+                assert feed(), "the decoder wants input but its window is full"
+                continue
+            return st, b"".join(out), info
 
     def scan(self, z):
         a = np.frombuffer(bytes(z), dtype=np.uint8) if len(z) else np.zeros(1, np.uint8)

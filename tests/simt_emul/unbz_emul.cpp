@@ -27,6 +27,7 @@ static int ub_h2d(lbz_decoder *, void *dst, const void *src, size_t bytes) { mem
 static int ub_d2h(lbz_decoder *, void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
 static int ub_dev_zero(lbz_decoder *, void *p, size_t bytes) { memset(p, 0, bytes); return 0; }
 static int ub_dev_fill32(lbz_decoder *, uint32_t *p, uint32_t v, size_t count) { memset(p, (int)(v & 0xFFu), count * 4); return 0; }
+static int ub_dev_move(lbz_decoder *, void *dst, const void *src, size_t bytes) { memmove(dst, src, bytes); return 0; }
 static int ub_sync(lbz_decoder *) { return 0; }
 static void ub_mark(lbz_decoder *, int) {}
 static void ub_timers_collect(lbz_decoder *) {}
@@ -82,6 +83,8 @@ int emu_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags
 int emu_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info) {
   return ub_next(d, out, out_cap, out_len, info);
 }
+int emu_decoder_open_stream(lbz_decoder *d, unsigned flags) { return ub_open_stream(d, flags); }
+int emu_decoder_feed(lbz_decoder *d, const uint8_t *in, size_t n, int eof, size_t *taken) { return ub_feed(d, in, n, eof, taken); }
 int emu_decode_at(lbz_decoder *d, const uint8_t *in, size_t n, const uint64_t *pos, uint32_t count, lbz_dblock *table, unsigned flags) {
   return ub_decode_at(d, in, n, pos, count, table, flags);
 }
@@ -124,6 +127,11 @@ void lbz_decoder_destroy(lbz_decoder *d) { emu_decoder_destroy(d); }
 int lbz_decoder_open(lbz_decoder *d, const uint8_t *in, size_t n, unsigned flags) { return ub_open(d, in, n, flags); }
 int lbz_decoder_next(lbz_decoder *d, uint8_t *out, size_t out_cap, size_t *out_len, lbz_dstream_info *info) {
   return ub_next(d, out, out_cap, out_len, info);
+}
+int lbz_decoder_open_stream(lbz_decoder *d, unsigned flags) { return ub_open_stream(d, flags); }
+int lbz_decoder_feed(lbz_decoder *d, const uint8_t *in, size_t n, int eof, size_t *taken) {
+  size_t dummy = 0;
+  return ub_feed(d, in, n, eof, taken ? taken : &dummy);
 }
 const char *lbz_strerror(int status) {
   static const char *const text[] = {

@@ -196,3 +196,27 @@ def test_expansion_task_graph_several_operands_and_thread_counts(tmp_path):
         r = subprocess.run([HOSTTEST, "-d", "-c", "-n%d" % n], input=z, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                            env=dict(os.environ, LBZIP2_B200_DBLOCKS=blocks, LBZIP2_B200_DWAVE_MB="48"), timeout=600)
         assert r.returncode == 0 and r.stdout == files["b"], (n, blocks, r.stderr[-200:])
+
+
+def test_expansion_task_graph_streams_through_a_window_smaller_than_the_file():
+    """6 MB of incompressible data at -1 (61 blocks of 100 KB, 6.03 MB compressed) through the minimum
+    window of 4 MB (LBZIP2_B200_DWINDOW_MB=2 is raised to it): the decoder must drop the consumed front
+    of its window and the stage task must wait for room, from a pipe (size unknown) and from a file."""
+    if not (os.path.exists(HOSTTEST) and os.path.exists(CPU_CLI)):
+        pytest.skip("oracle/_ref binaries not present")
+    data = synth.random_bytes(6_000_000, seed=77) + synth.text(300_000, offset=9)
+    z = _reference(1, data)
+    assert len(z) > 5_000_000
+    env = dict(os.environ, LBZIP2_B200_DWINDOW_MB="2", LBZIP2_B200_DBLOCKS="16", LBZIP2_B200_DWAVE_MB="48", LBZIP2_B200_STATS="1")
+    for n in (1, 4):
+        r = subprocess.run([HOSTTEST, "-d", "-c", "-n%d" % n], input=z, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=900)
+        assert r.returncode == 0 and r.stdout == data, r.stderr[-300:]
+        assert b"through a window of 4194304" in r.stderr, r.stderr[-300:]
+    # a damaged block in the last third: the bytes in front of it are still written, then the reference's message
+    bad = bytearray(z)
+    bad[len(z) * 2 // 3] ^= 0x10
+    r = subprocess.run([HOSTTEST, "-d", "-c", "-n3"], input=bytes(bad), stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=900)
+    ref = subprocess.run([CPU_CLI, "-d", "-c", "-n1"], input=bytes(bad), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+    assert r.returncode != 0 and ref.returncode != 0
+    assert len(r.stdout) >= 3_000_000 and data.startswith(r.stdout)
+    assert b"compressed data error" in r.stderr or b"block CRC mismatch" in r.stderr, r.stderr[-300:]

@@ -200,3 +200,77 @@ def test_fuzz_against_oracle():
         seen[st] = seen.get(st, 0) + 1
     assert len(seen) >= 10, seen
     d.close()
+
+
+# ---- streaming session: lbz_decoder_open_stream / lbz_decoder_feed / lbz_decoder_next -------------
+def _pieces(z, rng, lo, hi):
+    pos = 0
+    while pos < len(z):
+        k = int(rng.integers(lo, hi + 1))
+        yield z[pos:pos + k]
+        pos += k
+
+
+@pytest.mark.parametrize("max_blocks,piece", [(8, (1, 7)), (3, (200, 5000)), (2, (60000, 90000))])
+def test_streaming_session_equals_whole_file_session(max_blocks, piece):
+    """Every golden fed in pieces of random sizes (single bytes up to more than a block) through a
+    window far smaller than the larger files: status, output, block/stream counts and the absolute
+    end position must equal the whole-file session's (which the goldens pin to the reference CLI)."""
+    rng = np.random.default_rng(7 + max_blocks)
+    whole = emulib.EmuDecoder(max_blocks=max_blocks, in_cap=1 << 20)
+    # the window: a few blocks' worth (the largest compressed block of the goldens is < 200 KB)
+    win = emulib.EmuDecoder(max_blocks=max_blocks, in_cap=300_000)
+    cases = MANIFEST if piece[0] > 100 else [c for c in MANIFEST if os.path.getsize(os.path.join(GOLD, c["file"])) < 3000]
+    try:
+        for c in cases:
+            z = load(c)
+            if len(z) > 300_000 and c["status"] != "OK":
+                continue                      # truncated giants: covered by the whole-file tests
+            cap = max(48 << 20, c["out_len"] + 16)
+            st0, out0, info0 = whole.decompress(z, cap=cap)
+            trace = []
+            st, out, info = win.decompress_pieces(_pieces(z, rng, *piece), cap, trace=trace)
+            assert st == st0, (c["file"], c["name"], st, st0, trace[-5:])
+            assert out == out0, (c["file"], c["name"])
+            assert (info.num_blocks, info.num_streams, info.garbage) == (info0.num_blocks, info0.num_streams, info0.garbage), c["file"]
+            if st == 0:                   # where the walk stands after an error depends on how far ahead it could look
+                assert info.end_bit == info0.end_bit, (c["file"], c["name"], info.end_bit, info0.end_bit)
+    finally:
+        whole.close()
+        win.close()
+
+
+def test_streaming_session_window_slides_over_a_large_file():
+    """A 2.6 MB stream of 40 small blocks + a concatenated second stream through a 160 KB window (the incompressible block alone takes 100 KB of it):
+    the consumed front must be dropped many times, output and counters stay those of the file."""
+    import synth
+    data = synth.text(1_200_000, offset=3) + synth.random_bytes(90_000, seed=3) + b"\0" * 500_000
+    z = orclib.orc_stream(data, 1)[0] + orclib.orc_stream(data[:250_000], 2)[0]
+    whole = emulib.EmuDecoder(max_blocks=4, in_cap=len(z) + 64)
+    st0, out0, info0 = whole.decompress(z, cap=len(data) + 300_000)
+    whole.close()
+    assert st0 == 0 and out0 == data + data[:250_000]
+    win = emulib.EmuDecoder(max_blocks=4, in_cap=160_000)
+    rng = np.random.default_rng(11)
+    trace = []
+    st, out, info = win.decompress_pieces(_pieces(z, rng, 1000, 40000), 48 << 20, trace=trace, greedy=False)
+    assert st == 0 and out == out0
+    st, out, _ = win.decompress_pieces(_pieces(z, rng, 1000, 40000), 48 << 20)
+    win.close()
+    assert st == 0 and out == out0
+    assert (info.num_blocks, info.num_streams, info.end_bit) == (info0.num_blocks, info0.num_streams, info0.end_bit)
+    assert trace.count(101) >= 5          # it really had to wait for input again and again
+
+
+def test_streaming_session_fuzz_against_whole_file():
+    d0 = emulib.EmuDecoder(max_blocks=6, in_cap=1 << 16)
+    d1 = emulib.EmuDecoder(max_blocks=6, in_cap=1 << 16)
+    rng = np.random.default_rng(5)
+    for z in _mutations(int(os.environ.get("LBZ_FUZZ", "700")) // 2, 123):
+        st0, out0, info0 = d0.decompress(z, cap=48 << 20)
+        st, out, info = d1.decompress_pieces(_pieces(z, rng, 1, 300), 48 << 20, greedy=bool(len(z) & 1))
+        assert (st, out, info.num_blocks) == (st0, out0, info0.num_blocks), z.hex()[:80]
+        if st == 0:                       # where the walk stands after an error depends on how far ahead it could look
+            assert info.end_bit == info0.end_bit, z.hex()[:80]
+    d0.close()
+    d1.close()
