@@ -225,10 +225,12 @@ int lbz_dbg_set_chunks(lbz_engine *e, uint32_t nchunks);   /* slots are then fil
  *    (src/parse.c:281-342, src/decode.h:76), retrieve()/decode()/emit()
  *    (src/decode.h:78-81, src/decode.c:518-1143) and the stream walk of
  *    parse() (src/parse.c:147-263) with the per-block checks of
- *    src/expand.c:725-736.  The per-block decode.h calls themselves are NOT
- *    offered: retrieve() is a resumable bit-serial automaton fed 256 KiB at a
- *    time that must return exactly at the block's last bit, which only the
- *    decoding itself reveals; a device version has to see many whole blocks
+ *    src/expand.c:725-736.  This is the fast path: many whole blocks per
+ *    launch.  The per-block decode.h calls themselves are offered too
+ *    (section 1b: the unmodified src/expand.c drives them), but retrieve()
+ *    is a resumable bit-serial automaton fed 256 KiB at a time, which the
+ *    device can only honour one block per call -- a device version that
+ *    performs has to see many whole blocks
  *    at once.  Status values are the reference's
  *    `enum error` (src/common.h:54-76), same numbering.
  * ---------------------------------------------------------------------- */

@@ -400,7 +400,7 @@ struct TextSmem2 {
 // reload of the launch parameter); FULL: a tile of exactly RTILE elements, no per-item bound checks
 // (all tiles of a block but its last).  The digit start table `delta` includes the slot offset, so
 // the write-out index is one 32-bit add.
-template <int MODE, int LAST, int LIST, int SH, bool FULL>
+template <int MODE, int LAST, int LIST, int SH, bool FULL, int RANKV>
 __device__ __forceinline__ void text_pass2_tile(TextSmem2 &S, const uint8_t *__restrict__ T, const uint2 *__restrict__ src,
                                                 uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
                                                 uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
@@ -447,17 +447,43 @@ __device__ __forceinline__ void text_pass2_tile(TextSmem2 &S, const uint8_t *__r
   uint32_t rkp[ITEMS / 4];                                         // in-warp ranks (< 256), four per register
 #pragma unroll
   for (int q = 0; q < ITEMS / 4; q++) rkp[q] = 0;
+  if (RANKV == 1) {
+    // All eight match operations are issued before the first result is used, and the per-warp digit
+    // counters advance by shared-memory atomics of the group leaders whose results are independent of
+    // each other: the ranking is no longer a chain of eight (match -> counter load -> counter store)
+    // round trips (profiles/r02_ncu_pass_cs.txt: 33 % of the stall samples sat on that chain).
+    uint32_t m[ITEMS];
 #pragma unroll
-  for (int it = 0; it < ITEMS; it++) {
-    const bool valid = FULL || it * 32u < lim;
-    const uint32_t digit = valid ? ((key[it] >> shift) & 0xFFu) : 0x100u;   // missing items: a group of their own
-    const uint32_t mask = __match_any_sync(0xffffffffu, digit);
-    uint32_t base = 0;
-    if (valid) base = wrow[digit];
-    __syncwarp();
-    if (valid && (mask & lt) == 0) wrow[digit] = base + __popc(mask);       // group leader
-    __syncwarp();
-    rkp[it >> 2] |= (base + __popc(mask & lt)) << (8 * (it & 3));
+    for (int it = 0; it < ITEMS; it++) {
+      const bool valid = FULL || it * 32u < lim;
+      const uint32_t digit = valid ? ((key[it] >> shift) & 0xFFu) : 0x100u;
+      m[it] = __match_any_sync(0xffffffffu, digit);
+    }
+    uint32_t old[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const bool valid = FULL || it * 32u < lim;
+      old[it] = 0;
+      if (valid && (m[it] & lt) == 0) old[it] = atomicAdd(&wrow[(key[it] >> shift) & 0xFFu], (uint32_t)__popc(m[it]));
+    }
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const uint32_t base = __shfl_sync(0xffffffffu, old[it], __ffs(m[it]) - 1);     // from the group leader
+      rkp[it >> 2] |= (base + __popc(m[it] & lt)) << (8 * (it & 3));
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const bool valid = FULL || it * 32u < lim;
+      const uint32_t digit = valid ? ((key[it] >> shift) & 0xFFu) : 0x100u;   // missing items: a group of their own
+      const uint32_t mask = __match_any_sync(0xffffffffu, digit);
+      uint32_t base = 0;
+      if (valid) base = wrow[digit];
+      __syncwarp();
+      if (valid && (mask & lt) == 0) wrow[digit] = base + __popc(mask);       // group leader
+      __syncwarp();
+      rkp[it >> 2] |= (base + __popc(mask & lt)) << (8 * (it & 3));
+    }
   }
   __syncthreads();
 
@@ -556,7 +582,7 @@ __device__ __forceinline__ void text_pass2_tile(TextSmem2 &S, const uint8_t *__r
   }
 }
 
-template <int MODE, int LAST, int MINB, int LIST = 0, int SH = -1>
+template <int MODE, int LAST, int MINB, int LIST = 0, int SH = -1, int RANKV = 0>
 __global__ void __launch_bounds__(512, MINB)
 k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
              const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
@@ -591,10 +617,10 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
     }
   }
   if (tile_cnt == RTILE)
-    text_pass2_tile<MODE, LAST, LIST, SH, true>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
+    text_pass2_tile<MODE, LAST, LIST, SH, true, RANKV>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
                                                 tbase, tile_cnt, rtiles);
   else
-    text_pass2_tile<MODE, LAST, LIST, SH, false>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
+    text_pass2_tile<MODE, LAST, LIST, SH, false, RANKV>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
                                                  tbase, tile_cnt, rtiles);
 }
 
@@ -1210,6 +1236,12 @@ static bool tp_const_shift() {
   if (v < 0) { const char *ev = getenv("LBZ_TP_CONST_SHIFT"); v = ev ? (atoi(ev) != 0) : 1; }
   return v != 0;
 }
+// ranking inside a warp: 0 = counter load / store per item, 1 = matches first + shared-memory atomics
+static int tp_rankv() {
+  static int v = -1;
+  if (v < 0) { const char *ev = getenv("LBZ_TP_RANK"); v = ev ? atoi(ev) : 0; if (v < 0 || v > 1) v = 0; }
+  return v;
+}
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -1274,12 +1306,17 @@ static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, co
   if (ggrp < 0) { const char *ev = getenv("LBZ_TP_GATHER_GROUP"); ggrp = ev ? atoi(ev) : 32; if (ggrp < 1) ggrp = 1; }
   const uint32_t gsz = (MODE == 1) ? min(nb, (uint32_t)ggrp) : nb;
   const dim3 grid = xp ? dim3(gsz, g.S1 / 4096u, (nb + gsz - 1) / gsz) : dim3(g.S1 / 4096u, nb);
+#define LBZ_TP2_LAUNCH_R(SH, RV)                                                                                            \
+  do {                                                                                                                      \
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB, 0, SH, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)sizeof(TextSmem2)));                                                           \
+    k_text_pass2<MODE, LAST, MINB, 0, SH, RV><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase, \
+                                                                                    shift, epoch, err, koff, 256u, xp, nb);  \
+  } while (0)
 #define LBZ_TP2_LAUNCH(SH)                                                                                                  \
   do {                                                                                                                      \
-    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB, 0, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)sizeof(TextSmem2)));                                                           \
-    k_text_pass2<MODE, LAST, MINB, 0, SH><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,  \
-                                                                                shift, epoch, err, koff, 256u, xp, nb);     \
+    if (SH >= 0 && tp_rankv() == 1) LBZ_TP2_LAUNCH_R(SH, (SH >= 0 ? 1 : 0));                                                \
+    else LBZ_TP2_LAUNCH_R(SH, 0);                                                                                           \
   } while (0)
   // the digit offsets of the default sort depth (8 bytes) as compile-time constants: the passes that
   // build keys from the text (MODE 1, 2) work on the lowest digit, the last pass on the highest
@@ -1296,6 +1333,7 @@ static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, co
   }
   LBZ_TP2_LAUNCH(-1);
 #undef LBZ_TP2_LAUNCH
+#undef LBZ_TP2_LAUNCH_R
   return 0;
 }
 template <int MODE, int LAST>
@@ -1323,12 +1361,17 @@ static int launch_list_pass(uint32_t max_count, uint32_t nb, cudaStream_t st, co
     return launch_pass3<0, 0, 1>(tiles, nb, st, g, meta, nullptr, src, dst, nullptr, tstat, gbase, gstride, shift, epoch, err, 0u, B);
   const uint32_t xp = tp_xpose();
   const dim3 grid = xp ? dim3(nb, tiles) : dim3(tiles, nb);
+#define LBZ_TP2_LIST_R(SH, RV)                                                                                            \
+  do {                                                                                                                    \
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<0, 0, 3, 1, SH, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                        (int)sizeof(TextSmem2)));                                                         \
+    k_text_pass2<0, 0, 3, 1, SH, RV><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, nullptr, src, dst, nullptr, tstat, gbase, \
+                                                                           shift, epoch, err, 0u, gstride, xp, nb);       \
+  } while (0)
 #define LBZ_TP2_LIST(SH)                                                                                                  \
   do {                                                                                                                    \
-    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<0, 0, 3, 1, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                        (int)sizeof(TextSmem2)));                                                         \
-    k_text_pass2<0, 0, 3, 1, SH><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, nullptr, src, dst, nullptr, tstat, gbase,  \
-                                                                       shift, epoch, err, 0u, gstride, xp, nb);           \
+    if (SH >= 0 && tp_rankv() == 1) LBZ_TP2_LIST_R(SH, (SH >= 0 ? 1 : 0));                                                \
+    else LBZ_TP2_LIST_R(SH, 0);                                                                                           \
   } while (0)
   if (tp_const_shift() && shift == 0u) LBZ_TP2_LIST(0);
   else if (tp_const_shift() && shift == 8u) LBZ_TP2_LIST(8);
@@ -1336,6 +1379,7 @@ static int launch_list_pass(uint32_t max_count, uint32_t nb, cudaStream_t st, co
   else if (tp_const_shift() && shift == 24u) LBZ_TP2_LIST(24);
   else LBZ_TP2_LIST(-1);
 #undef LBZ_TP2_LIST
+#undef LBZ_TP2_LIST_R
   return 0;
 }
 

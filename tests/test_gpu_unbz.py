@@ -209,3 +209,46 @@ def test_default_capacity_grows_with_the_output(dec):
     assert len(z) * 64 < len(data)
     st, out, info = dec.decompress(z)
     assert st == 0 and out == data
+
+
+def _pieces(z, rng, lo, hi):
+    pos = 0
+    while pos < len(z):
+        k = int(rng.integers(lo, hi + 1))
+        yield z[pos:pos + k]
+        pos += k
+
+
+def test_streaming_session_equals_whole_file_session(dec):
+    """lbz_decoder_open_stream / lbz_decoder_feed / lbz_decoder_next: every golden in pieces of random
+    sizes through a window of 300 KB -- status, output and counters of the whole-file session (which the
+    goldens pin to the reference CLI); then 60 MB of text (66 blocks, 17 MB compressed) and 20 MB of
+    incompressible bytes at -9 through windows of 6 MB and 3 MB: the window has to slide many times."""
+    import lbzip2_b200
+    rng = np.random.default_rng(21)
+    win = lbzip2_b200.Decoder(device=0, max_blocks=8, in_cap=300_000, out_cap=96 << 20)
+    try:
+        for c in MANIFEST:
+            z = load(c)
+            if len(z) > 300_000 and c["status"] != "OK":
+                continue
+            cap = max(48 << 20, c["out_len"] + 16)
+            st, out, info = win.decompress_pieces(_pieces(z, rng, 1 if len(z) < 2000 else 500, 7 if len(z) < 2000 else 70000), cap)
+            name = orclib.ERR_NAMES[st] if 0 <= st < 20 else str(st)
+            assert name == c["status"], (c["file"], c["name"], name, c["status"])
+            assert len(out) == c["out_len"] and hashlib.sha256(out).hexdigest() == c["out_sha256"], (c["file"], c["name"])
+            assert info.num_blocks == c["num_blocks"], (c["file"], c["name"])
+            if st == 0:
+                assert info.num_streams == c["num_streams"] and info.garbage == c["garbage"], c["file"]
+    finally:
+        win.close()
+    eng = lbzip2_b200.Engine(device=0, level=9, max_chunks=80)
+    for data, window in ((synth.text(60_000_000, offset=17), 6 << 20), (synth.random_bytes(20_000_000, seed=17), 3 << 20)):
+        z = eng.compress_stream(data)
+        assert len(z) > 2 * window
+        d = lbzip2_b200.Decoder(device=0, max_blocks=16, in_cap=window, out_cap=64 << 20)
+        st, out, info = d.decompress_pieces(_pieces(z, rng, 100_000, 2_000_000), 64 << 20)
+        d.close()
+        assert st == 0 and out == data
+        assert info.end_bit == 8 * len(z) and info.num_streams == 1
+    eng.close()
