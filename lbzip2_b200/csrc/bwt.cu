@@ -396,12 +396,199 @@ struct TextSmem2 {
 
 // LIST = 1: the same pass over the (32-bit key, index) pairs of a block's round list L
 // (segment = meta.ul elements at list offset meta.lbase; digit bases per block and pass).
+template <int MODE, int LAST, int MINB, int LIST = 0>
+__global__ void __launch_bounds__(512, MINB)
+k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+             const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
+             uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
+             uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride,
+             uint32_t xpose, uint32_t nb) {
+  extern __shared__ __align__(16) unsigned char radix_smem_raw[];
+  TextSmem2 &S = *reinterpret_cast<TextSmem2 *>(radix_smem_raw);
+  constexpr int THREADS = 512, ITEMS = 8;
+  constexpr uint32_t RTILE = THREADS * ITEMS;
+  const uint32_t rtiles = g.S1 / RTILE;
+  // xpose: grid = (blocks of a group, tiles, groups) -- CTAs are dispatched x-fastest, so consecutive
+  // CTAs then work on different blocks and a tile's predecessor has usually published its inclusive
+  // prefix.  The group is the whole batch except for the pass that gathers from the text (MODE 1):
+  // there 32 blocks share the resident CTAs, so that their text (29 MB) stays in L2 -- spread over
+  // all blocks of the batch every gathered sector came from DRAM (5.2 GB per launch instead of 0.8).
+  const uint32_t b = xpose ? blockIdx.z * gridDim.x + blockIdx.x : blockIdx.y, tile = xpose ? blockIdx.y : blockIdx.x;
+  if (b >= nb) return;
+  const uint32_t n = meta[b].n;
+  const uint32_t cnt = LIST ? meta[b].ul : n;
+  const uint32_t tbase = tile * RTILE;
+  if (tbase >= cnt) return;
+  const uint32_t off = lbz_slot_off(g, b) + (LIST ? meta[b].lbase : 0u);
+  const uint32_t tile_cnt = min(RTILE, cnt - tbase);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  if (MODE == 0 && xpose > 1u && tid == 0) {
+    // TMA bulk prefetch into L2 of the tile that the CTA dispatched `xpose` rows later will load
+    // (block-fastest dispatch: that CTA starts about when the CTAs resident now retire)
+    const uint32_t t2 = tbase + xpose * RTILE;
+    if (t2 < cnt) {
+      const uint32_t e0 = (off + t2) & ~1u;
+      const uint32_t bytes = (min(RTILE, cnt - t2) * 8u) & ~15u;
+      if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + e0), "r"(bytes) : "memory");
+    }
+  }
+  const uint32_t wbase = warp * (32 * ITEMS) + lane;              // tile index of this thread's item 0
+  const uint32_t lim = tile_cnt > wbase ? tile_cnt - wbase : 0u;  // item `it` exists iff it * 32 < lim
+
+  uint32_t val[ITEMS], key[ITEMS];
+  if (MODE == 2) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) val[it] = tbase + wbase + it * 32;
+  } else {
+    const uint2 *sp = src + off + tbase + wbase;
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      const uint2 pr = (it * 32u < lim) ? sp[it * 32] : make_uint2(0u, 0u);
+      key[it] = pr.x; val[it] = pr.y;
+    }
+  }
+  {
+    uint4 *z = reinterpret_cast<uint4 *>(&S.wcnt[0][0]);
+    z[tid] = make_uint4(0u, 0u, 0u, 0u);
+    z[tid + THREADS] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) key[it] = (it * 32u < lim) ? text_key4(T + off, val[it], n) : 0u;
+  }
+  if (MODE == 2) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) key[it] = (it * 32u < lim) ? text_key4(T + off, wrap_add(val[it], koff, n), n) : 0u;
+  }
+  __syncthreads();
+
+  const uint32_t lt = lanemask_lt();
+  uint32_t *wrow = &S.wcnt[warp][0];
+  uint32_t rkp[ITEMS / 4];                                         // in-warp ranks (< 256), four per register
+#pragma unroll
+  for (int q = 0; q < ITEMS / 4; q++) rkp[q] = 0;
+#pragma unroll
+  for (int it = 0; it < ITEMS; it++) {
+    const bool valid = it * 32u < lim;
+    const uint32_t digit = valid ? ((key[it] >> shift) & 0xFFu) : 0x100u;   // missing items: a group of their own
+    const uint32_t mask = __match_any_sync(0xffffffffu, digit);
+    uint32_t base = 0;
+    if (valid) base = wrow[digit];
+    __syncwarp();
+    if (valid && (mask & lt) == 0) wrow[digit] = base + __popc(mask);       // group leader
+    __syncwarp();
+    rkp[it >> 2] |= (base + __popc(mask & lt)) << (8 * (it & 3));
+  }
+  __syncthreads();
+
+  // per-digit totals: thread (d, half) sums eight warps, the halves meet in hsum
+  const uint32_t d = tid & 255u, half = tid >> 8;
+  {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t c = S.wcnt[half * 8 + w][d]; S.wcnt[half * 8 + w][d] = run; run += c; }
+    S.hsum[half][d] = run;
+  }
+  __syncthreads();
+  uint32_t *mine = tstat + ((size_t)b * rtiles + tile) * 256 + d;
+  const uint32_t ep = (epoch << 20) & TS_EPOCH_MASK;
+  uint32_t inc = 0, total = 0, h0 = 0;
+  if (half == 0) {
+    h0 = S.hsum[0][d];
+    total = h0 + S.hsum[1][d];
+    st_volatile_u32(mine, (tile == 0 ? TS_FLAG_PREFIX : TS_FLAG_AGG) | ep | total);
+    inc = warp_incl_sum(total);
+    if (lane == 31) S.ws[warp] = inc;
+  }
+  __syncthreads();
+  uint32_t dst0 = 0;
+  if (half == 0) {
+    uint32_t wb = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; w++) wb += (w < warp) ? S.ws[w] : 0u;
+    dst0 = wb + inc - total;                                       // start of digit d inside the tile
+    S.dstart[0][d] = dst0;                                         // warps 0..7
+    S.dstart[1][d] = dst0 + h0;                                    // warps 8..15 come after the first half's items
+  }
+  __syncthreads();
+  {
+    const uint32_t *drow = &S.dstart[half][0];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+      if (it * 32u < lim) {
+        const uint32_t digit = (key[it] >> shift) & 0xFFu;
+        const uint32_t slot = drow[digit] + wrow[digit] + ((rkp[it >> 2] >> (8 * (it & 3))) & 0xFFu);
+        S.spair[slot] = make_uint2(key[it], val[it]);
+      }
+    }
+  }
+  if (half == 0) {
+    uint32_t excl = 0;
+    if (tile != 0) {
+      // Look-back over the preceding tiles of this block, a window of TS_WINDOW status
+      // words at a time: the loads of a window are independent and issued together, so
+      // the walk costs one memory round trip per window instead of one per tile (the
+      // predecessors are typically still in flight and only offer their aggregates).
+      const uint32_t *row0 = mine - (size_t)tile * 256;            // status word of tile 0, this digit
+      int t = (int)tile - 1;
+      uint32_t spins = 0;
+      bool done = false;
+      while (!done) {
+        uint32_t sw[TS_WINDOW];
+#pragma unroll
+        for (int k = 0; k < TS_WINDOW; k++)
+          sw[k] = (t - k >= 0) ? ld_volatile_u32(row0 + (size_t)(t - k) * 256) : (TS_FLAG_PREFIX | ep);
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < TS_WINDOW; k++) {
+          if (!done && used == k) {
+            const uint32_t w = sw[k];
+            if ((w & TS_EPOCH_MASK) == ep && (w >> 30) != 0u) {
+              excl += w & TS_VALUE_MASK;
+              used = k + 1;
+              if (w & TS_FLAG_PREFIX) done = true;
+            }
+          }
+        }
+        t -= used;
+        if (!done && used < TS_WINDOW) {                             // tile t has not published yet
+          if (++spins > TS_SPIN_LIMIT) { *err = 1u; break; }
+          __nanosleep(40);
+        }
+      }
+      st_volatile_u32(mine, TS_FLAG_PREFIX | ep | ((excl + total) & TS_VALUE_MASK));
+    }
+    S.delta[d] = gbase[(size_t)b * gstride + d] + excl - dst0;
+  }
+  __syncthreads();
+  if (LAST) {
+    uint32_t *o = sa_out + off;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+      const uint32_t i = tid + k * THREADS;
+      if (i < tile_cnt) { const uint2 pr = S.spair[i]; o[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr.y; }
+    }
+  } else {
+    uint2 *o = dst + off;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+      const uint32_t i = tid + k * THREADS;
+      if (i < tile_cnt) { const uint2 pr = S.spair[i]; o[S.delta[(pr.x >> shift) & 0xFFu] + i] = pr; }
+    }
+  }
+}
+
+
+
+// ---- k_text_pass2s: the same pass, specialised (LBZ_TP_SPEC=1).  26 % fewer instructions, measured 5 % SLOWER
+// than k_text_pass2 (0.535 against 0.507 ms per launch; with the atomic ranking 0.557 ms): the pass is bound by the
+// latency of its shared-memory round trips and barriers, not by issue slots (profiles/r02_pass_variants.md).
 // SH >= 0: the digit's bit offset is a compile-time constant (byte extraction becomes one PRMT, no
 // reload of the launch parameter); FULL: a tile of exactly RTILE elements, no per-item bound checks
 // (all tiles of a block but its last).  The digit start table `delta` includes the slot offset, so
 // the write-out index is one 32-bit add.
 template <int MODE, int LAST, int LIST, int SH, bool FULL, int RANKV>
-__device__ __forceinline__ void text_pass2_tile(TextSmem2 &S, const uint8_t *__restrict__ T, const uint2 *__restrict__ src,
+__device__ __forceinline__ void text_pass2s_tile(TextSmem2 &S, const uint8_t *__restrict__ T, const uint2 *__restrict__ src,
                                                 uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
                                                 uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
                                                 uint32_t shift_rt, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff,
@@ -584,7 +771,7 @@ __device__ __forceinline__ void text_pass2_tile(TextSmem2 &S, const uint8_t *__r
 
 template <int MODE, int LAST, int MINB, int LIST = 0, int SH = -1, int RANKV = 0>
 __global__ void __launch_bounds__(512, MINB)
-k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
+k_text_pass2s(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__restrict__ T,
              const uint2 *__restrict__ src, uint2 *__restrict__ dst, uint32_t *__restrict__ sa_out,
              uint32_t *__restrict__ tstat, const uint32_t *__restrict__ gbase,
              uint32_t shift, uint32_t epoch, uint32_t *__restrict__ err, uint32_t koff, uint32_t gstride,
@@ -617,10 +804,10 @@ k_text_pass2(LbzGeom g, const LbzBlockMeta *__restrict__ meta, const uint8_t *__
     }
   }
   if (tile_cnt == RTILE)
-    text_pass2_tile<MODE, LAST, LIST, SH, true, RANKV>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
+    text_pass2s_tile<MODE, LAST, LIST, SH, true, RANKV>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
                                                 tbase, tile_cnt, rtiles);
   else
-    text_pass2_tile<MODE, LAST, LIST, SH, false, RANKV>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
+    text_pass2s_tile<MODE, LAST, LIST, SH, false, RANKV>(S, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff, gstride, b, tile, n, off,
                                                  tbase, tile_cnt, rtiles);
 }
 
@@ -1236,6 +1423,12 @@ static bool tp_const_shift() {
   if (v < 0) { const char *ev = getenv("LBZ_TP_CONST_SHIFT"); v = ev ? (atoi(ev) != 0) : 1; }
   return v != 0;
 }
+// 0 (default): k_text_pass2; 1: k_text_pass2s, the variant specialised for full tiles and constant digit offsets
+static bool tp_spec() {
+  static int v = -1;
+  if (v < 0) { const char *ev = getenv("LBZ_TP_SPEC"); v = ev ? (atoi(ev) != 0) : 0; }
+  return v != 0;
+}
 // ranking inside a warp: 0 = counter load / store per item, 1 = matches first + shared-memory atomics
 static int tp_rankv() {
   static int v = -1;
@@ -1308,9 +1501,9 @@ static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, co
   const dim3 grid = xp ? dim3(gsz, g.S1 / 4096u, (nb + gsz - 1) / gsz) : dim3(g.S1 / 4096u, nb);
 #define LBZ_TP2_LAUNCH_R(SH, RV)                                                                                            \
   do {                                                                                                                      \
-    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB, 0, SH, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2s<MODE, LAST, MINB, 0, SH, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         (int)sizeof(TextSmem2)));                                                           \
-    k_text_pass2<MODE, LAST, MINB, 0, SH, RV><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase, \
+    k_text_pass2s<MODE, LAST, MINB, 0, SH, RV><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase, \
                                                                                     shift, epoch, err, koff, 256u, xp, nb);  \
   } while (0)
 #define LBZ_TP2_LAUNCH(SH)                                                                                                  \
@@ -1320,6 +1513,12 @@ static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, co
   } while (0)
   // the digit offsets of the default sort depth (8 bytes) as compile-time constants: the passes that
   // build keys from the text (MODE 1, 2) work on the lowest digit, the last pass on the highest
+  if (!tp_spec()) {
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
+    k_text_pass2<MODE, LAST, MINB><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
+                                                                          shift, epoch, err, koff, 256u, xp, nb);
+    return 0;
+  }
   if (MINB == 3 && tp_const_shift()) {
     if constexpr (MODE != 0 && !LAST) {
       if (shift == 0u) { LBZ_TP2_LAUNCH(0); return 0; }
@@ -1363,9 +1562,9 @@ static int launch_list_pass(uint32_t max_count, uint32_t nb, cudaStream_t st, co
   const dim3 grid = xp ? dim3(nb, tiles) : dim3(tiles, nb);
 #define LBZ_TP2_LIST_R(SH, RV)                                                                                            \
   do {                                                                                                                    \
-    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<0, 0, 3, 1, SH, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2s<0, 0, 3, 1, SH, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                         (int)sizeof(TextSmem2)));                                                         \
-    k_text_pass2<0, 0, 3, 1, SH, RV><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, nullptr, src, dst, nullptr, tstat, gbase, \
+    k_text_pass2s<0, 0, 3, 1, SH, RV><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, nullptr, src, dst, nullptr, tstat, gbase, \
                                                                            shift, epoch, err, 0u, gstride, xp, nb);       \
   } while (0)
 #define LBZ_TP2_LIST(SH)                                                                                                  \
@@ -1373,6 +1572,12 @@ static int launch_list_pass(uint32_t max_count, uint32_t nb, cudaStream_t st, co
     if (SH >= 0 && tp_rankv() == 1) LBZ_TP2_LIST_R(SH, (SH >= 0 ? 1 : 0));                                                \
     else LBZ_TP2_LIST_R(SH, 0);                                                                                           \
   } while (0)
+  if (!tp_spec()) {
+    LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<0, 0, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
+    k_text_pass2<0, 0, 3, 1><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, nullptr, src, dst, nullptr, tstat, gbase, shift, epoch, err, 0u,
+                                                                    gstride, xp, nb);
+    return 0;
+  }
   if (tp_const_shift() && shift == 0u) LBZ_TP2_LIST(0);
   else if (tp_const_shift() && shift == 8u) LBZ_TP2_LIST(8);
   else if (tp_const_shift() && shift == 16u) LBZ_TP2_LIST(16);

@@ -39,14 +39,18 @@
   the framing walk) and drops what its waves have consumed; two accumulation
   buffers of half that size let the reader run ahead while a wave is decoded.  The
   decoded data is streamed, one wave (LBZIP2_B200_DWAVE_MB, default 256 MB) at a
-  time, through a small pool of page-locked buffers (lbz_host_alloc) that the
-  writer hands back: a fresh pageable buffer per wave cost one page fault per 4 KiB
-  and a staged device-to-host copy.  Files of any size and pipes work the same way
-  (the reference's expand.c has the same property through its 256 KiB buffers).
+  time, through a small pool of buffers that the writer hands back (a fresh buffer
+  per wave cost one page fault per 4 KiB of output).  The buffers are ordinary
+  memory by default: page-locking them (LBZIP2_B200_PINNED=1, lbz_host_alloc) makes
+  the copies faster but was measured at 1.8 s per GB locked on the B200 boxes
+  (profiles/r02_run21_rank_ab_streaming_cli.log), which only files of tens of GB
+  earn back.  Files of any size and pipes work the same way (the reference's
+  expand.c has the same property through its 256 KiB buffers).
 
   Environment: LBZIP2_B200_DBLOCKS   candidate blocks per wave   (default 320)
                LBZIP2_B200_DWAVE_MB  decoded bytes per wave      (default 256)
                LBZIP2_B200_DWINDOW_MB  compressed bytes resident (default 256; less for smaller files)
+               LBZIP2_B200_PINNED    1: page-locked staging buffers (for very large files)
                LBZIP2_B200_DEVICE    device ordinal              (default 0)
                LBZIP2_B200_STATS     print statistics to stderr at the end
 */
@@ -109,6 +113,7 @@ static uint64_t next_wave, write_wave;
 static unsigned pending;
 static size_t weight_done;
 static bool stats;
+static bool pinned;             /* staging buffers are page-locked (LBZIP2_B200_PINNED=1) */
 static double stat_t0, stat_gpu, stat_setup;
 static unsigned long stat_waves, stat_blocks, stat_candidates, stat_false, stat_starved;
 
@@ -137,6 +142,29 @@ env_size(const char *name, size_t dflt, size_t lo, size_t hi)
   if (v > hi)
     v = hi;
   return (size_t)v;
+}
+
+
+static void *
+stage_alloc(size_t n)
+{
+  void *p;
+
+  if (!pinned)
+    return xmalloc(n);
+  p = lbz_host_alloc(n);
+  if (p == NULL)
+    failx(0, "cannot allocate a page-locked buffer of %zu bytes", n);
+  return p;
+}
+
+static void
+stage_free(void *p)
+{
+  if (pinned)
+    lbz_host_free(p);
+  else
+    free(p);
 }
 
 
@@ -184,10 +212,8 @@ do_setup(void)
 
     for (i = 0; i < 2u; i++) {
       if (acc[i] != NULL)
-        lbz_host_free(acc[i]);
-      acc[i] = lbz_host_alloc(want / 2);
-      if (acc[i] == NULL)
-        failx(0, "cannot allocate a page-locked input buffer of %zu bytes", want / 2);
+        stage_free(acc[i]);
+      acc[i] = stage_alloc(want / 2);
     }
     acc_alloc = want / 2;
   }
@@ -308,9 +334,7 @@ do_decode(void)
 
   if (buf == NULL) {
     t0 = now();
-    buf = lbz_host_alloc(dec_wave_cap);
-    if (buf == NULL)
-      failx(0, "cannot allocate a page-locked output buffer of %zu bytes", dec_wave_cap);
+    buf = stage_alloc(dec_wave_cap);
     stat_setup += now() - t0;
   }
   t0 = now();
@@ -424,7 +448,7 @@ on_write_complete(void *buffer)
   ++out_slots;
   sched_unlock();
   if (buffer != NULL)
-    lbz_host_free(buffer);
+    stage_free(buffer);
 }
 
 
@@ -433,6 +457,8 @@ init(void)
 {
   stat_t0 = now();
   stats = getenv("LBZIP2_B200_STATS") != NULL;
+  if (dec == NULL)              /* fixed for the process: the buffers outlive an operand */
+    pinned = env_size("LBZIP2_B200_PINNED", 0, 0, 1) != 0;
   stat_gpu = stat_setup = 0.0;
   stat_waves = stat_blocks = stat_candidates = stat_false = stat_starved = 0;
   dec_blocks = (unsigned)env_size("LBZIP2_B200_DBLOCKS", 320, 1, 16384);
