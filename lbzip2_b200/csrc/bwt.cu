@@ -1515,6 +1515,8 @@ static int launch_text_pass_b(uint32_t nb, cudaStream_t st, const LbzGeom &g, co
   // build keys from the text (MODE 1, 2) work on the lowest digit, the last pass on the highest
   if (!tp_spec()) {
     LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem2)));
+    if (MINB == 4)
+      LBZ_CUDA_CHECK(cudaFuncSetAttribute(k_text_pass2<MODE, LAST, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     k_text_pass2<MODE, LAST, MINB><<<grid, 512, sizeof(TextSmem2), st>>>(g, meta, T, src, dst, sa_out, tstat, gbase,
                                                                           shift, epoch, err, koff, 256u, xp, nb);
     return 0;
@@ -1544,7 +1546,9 @@ static int launch_text_pass(uint32_t nb, cudaStream_t st, const LbzGeom &g, cons
   if (tp_version() == 3)
     return launch_pass3<MODE, LAST, 0>(g.S1 / 4096u, nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, 256u, shift, epoch, err, koff, B);
   static int minb = 0;
-  if (!minb) { const char *ev = getenv("LBZ_TP_MINB"); minb = (ev && atoi(ev) == 2) ? 2 : 3; }
+  if (!minb) { const char *ev = getenv("LBZ_TP_MINB"); minb = (ev && atoi(ev) == 2) ? 2 : (ev && atoi(ev) == 4) ? 4 : 3; }
+  // 4 CTAs per SM: 32 registers per thread (spills) against 64 instead of 48 resident warps; needs the largest shared-memory carve-out
+  if (minb == 4) return launch_text_pass_b<MODE, LAST, 4>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff);
   if (minb == 3) return launch_text_pass_b<MODE, LAST, 3>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff);
   return launch_text_pass_b<MODE, LAST, 2>(nb, st, g, meta, T, src, dst, sa_out, tstat, gbase, shift, epoch, err, koff);
 }

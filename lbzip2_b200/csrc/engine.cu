@@ -842,10 +842,9 @@ extern "C" void lbz_set_fatal_handler(void (*fn)(const char *msg)) { g_fatal = f
 // time from the polynomial (build-aux/make-crctab.pl:29-33): poly 0x04C11DB7, MSB first.
 extern "C" { uint32_t crc_table[256]; }
 __attribute__((constructor)) static void lbz_init_crc_table() {
-  // The per-block API keeps one stream per worker thread busy (pooled contexts, single-block decoders);
-  // with the default of 8 hardware work queues, streams beyond the eighth are serialised behind the
-  // others.  Takes effect if the CUDA context is created after this library is loaded.
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+  // (32 hardware work queues instead of the default 8 -- CUDA_DEVICE_MAX_CONNECTIONS -- were tried for the
+  // per-block shims, which keep one stream per worker thread busy: lbzip2_gpu -d fell from 35-44 to 18 MB/s,
+  // profiles/r02_run20_shim_queues.log; the default stays.)
   for (uint32_t i = 0; i < 256; i++) {
     uint32_t r = i << 24;
     for (int k = 0; k < 8; k++) r = (r & 0x80000000u) ? (r << 1) ^ 0x04C11DB7u : (r << 1);
