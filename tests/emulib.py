@@ -183,14 +183,15 @@ class EmuDecoder:
             out.append(c)
         return out
 
-    def emit_at(self, out_offs, cap):
+    def emit_at(self, out_offs, cap, out=None):
         k = len(out_offs)
         offs = (C.c_uint64 * max(k, 1))(*out_offs)
         crc = (C.c_uint32 * max(k, 1))()
-        buf = np.empty(max(cap, 1), dtype=np.uint8)
+        assert out is None or out.size >= cap
+        buf = out if out is not None else np.empty(max(cap, 1), dtype=np.uint8)
         n = C.c_size_t(0)
         assert self.L.emu_emit_at(self.h, offs, k, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), crc) == 0
-        return buf[: n.value].tobytes(), list(crc[:k])
+        return (buf[: n.value] if out is not None else buf[: n.value].tobytes()), list(crc[:k])
 
     def walk_table(self, z, table):
         a = np.frombuffer(bytes(z), dtype=np.uint8) if len(z) else np.zeros(1, np.uint8)
