@@ -244,8 +244,11 @@ head_is_next(void)
 static bool
 can_stage(void)
 {
-  return setup_done && !staging && head_is_next() &&
-    acc_len + peek(stage_q)->size <= acc_cap;
+  if (!setup_done || staging || !head_is_next())
+    return false;
+  /* once the decoder has reached its verdict (the end of the last stream with garbage behind it, or
+     a data error) the rest of the input is read and dropped, as the reference does (src/expand.c:428-436) */
+  return decode_done || acc_len + peek(stage_q)->size <= acc_cap;
 }
 
 static void
@@ -253,16 +256,21 @@ do_stage(void)
 {
   struct in_blk *iblk = dequeue(stage_q);
   uint8_t *dst = acc[fill_i] + acc_len;
+  bool drop = decode_done;
 
+  if (!drop && iblk->size > acc_cap)
+    failx(0, "an input buffer of %zu bytes does not fit the staging buffer (%zu)", iblk->size, acc_cap);
   next_stage++;
   staging = true;               /* appends are ordered: one at a time; no buffer swap meanwhile */
   sched_unlock();
 
-  memcpy(dst, iblk->buffer, iblk->size);
+  if (!drop)
+    memcpy(dst, iblk->buffer, iblk->size);
   source_release_buffer(iblk->buffer);
 
   sched_lock();
-  acc_len += iblk->size;
+  if (!drop)
+    acc_len += iblk->size;
   total_in += iblk->size;
   staging = false;
   free(iblk);

@@ -220,3 +220,24 @@ def test_expansion_task_graph_streams_through_a_window_smaller_than_the_file():
     assert r.returncode != 0 and ref.returncode != 0
     assert len(r.stdout) >= 3_000_000 and data.startswith(r.stdout)
     assert b"compressed data error" in r.stderr or b"block CRC mismatch" in r.stderr, r.stderr[-300:]
+
+
+def test_expansion_task_graph_drops_the_input_behind_its_verdict():
+    """Once the decoder has its verdict -- the end of the last stream with megabytes of garbage behind it,
+    or a damaged block -- the rest of the input is read and dropped (a bounded staging buffer must not
+    dam up the reader: found as a deadlock by review).  Code, bytes and message of the reference CLI."""
+    if not (os.path.exists(HOSTTEST) and os.path.exists(CPU_CLI)):
+        pytest.skip("oracle/_ref binaries not present")
+    data = synth.text(300_000, offset=3)
+    z = _reference(1, data)
+    garbage = z + synth.random_bytes(12_000_000, seed=5)
+    bad = bytearray(z + z)
+    bad[len(z) // 2] ^= 0x20
+    bad = bytes(bad) + synth.random_bytes(9_000_000, seed=6)
+    env = dict(os.environ, LBZIP2_B200_DWINDOW_MB="2", LBZIP2_B200_DBLOCKS="8", LBZIP2_B200_DWAVE_MB="48")
+    for inp in (garbage, bad):
+        want = subprocess.run([CPU_CLI, "-d", "-c", "-n1"], input=inp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        for n in (1, 4):
+            got = subprocess.run([HOSTTEST, "-d", "-c", "-n%d" % n], input=inp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300)
+            assert got.returncode == want.returncode and got.stdout == want.stdout
+            assert got.stderr.split(b": ", 1)[-1] == want.stderr.split(b": ", 1)[-1], (got.stderr, want.stderr)
