@@ -77,3 +77,26 @@ def test_decompress_leg_plumbing(monkeypatch):
     assert res["more_blocks_in_flight"]["blocks"] == 12 and res["more_blocks_in_flight"]["last_copy_sha256_equals_input"]
     for key in ("value", "e2e", "roofline", "path_roofline", "stage_ms"):
         assert key in res
+
+
+def test_traffic_comes_from_the_committed_captures(monkeypatch):
+    """`roofline.traffic` is looked up in profiles/ncu_traffic.json by kernel and element count: the default
+    workload (100 MB text = 100.14 M rotations) must find the newest capture of the plain pass, whose DRAM
+    bytes are the algorithmic 16 B per element within a few per cent; an unknown size gives null."""
+    monkeypatch.syspath_prepend(ROOT)
+    import bench
+    t = bench.ncu_traffic("k_text_pass2", 100136441)
+    assert t is not None and abs(t - 16 * 100136441) < 0.05 * 16 * 100136441
+    assert bench.ncu_traffic("k_text_pass2", 55_000_000) is None
+    assert bench.ncu_traffic("k_ub_chain2", 223) is not None
+    assert bench.ncu_traffic("no_such_kernel", 100136441) is None
+
+
+def test_both_arms_name_the_workload_alike(monkeypatch):
+    monkeypatch.syspath_prepend(ROOT)
+    import bench
+    import types as _t
+    for wl, mb in (("text", 100), ("text", 1250), ("random", 1000), ("runs_fib", 1000)):
+        a = _t.SimpleNamespace(workload=wl, size_mb=mb, level=9)
+        name = bench.workload_name(a)
+        assert str(mb) in name and "-9" in name
