@@ -76,3 +76,24 @@ def test_product_does_not_link_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "liboracle" not in txt and "bz_oracle" not in txt and "orclib" not in txt, f
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 and as C++17 on its own (no CUDA or torch
+    types in any signature), and a C translation unit that uses every streaming-session entry point must
+    link against the library."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    c = tmp_path / "t.c"
+    c.write_text('#include "lbzip2_b200.h"\n'
+                 "int use(lbz_decoder *d, const uint8_t *p, size_t n, uint8_t *o, size_t cap) {\n"
+                 "  size_t taken = 0, got = 0; lbz_dstream_info inf;\n"
+                 "  if (lbz_decoder_open_stream(d, 0) != LBZ_OK) return -1;\n"
+                 "  if (lbz_decoder_feed(d, p, n, 1, &taken)) return -1;\n"
+                 "  return lbz_decoder_next(d, o, cap, &got, &inf) == LBZ_NEED_INPUT;\n"
+                 "}\n")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + inc, "-c", str(c), "-o", str(tmp_path / "t.o")])
+    cxx = tmp_path / "t.cpp"
+    cxx.write_text('#include "lbzip2_b200.h"\nint main() { return lbz_version() == nullptr; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + inc, str(cxx), "-L" + os.path.join(ROOT, "lbzip2_b200"),
+                           "-lbz2b200", "-Wl,-rpath," + os.path.join(ROOT, "lbzip2_b200"), "-o", str(tmp_path / "t")])
