@@ -50,3 +50,37 @@ def test_single_byte_run_known_answer():
 def test_empty_stream():
     got, infos = orclib.orc_stream(b"", 9)
     assert got == b"BZh9\x17\x72\x45\x38\x50\x90\x00\x00\x00\x00" and infos == []
+
+
+def test_periodic_goldens_differ_from_the_reference_in_the_primary_index_only():
+    """The documented exception, pinned down to the bit: on the goldens with an exactly periodic block the
+    oracle's stream (which the GPU stream must equal, tests/test_gpu_parity.py) and the reference CLI's stream
+    have the same length and differ ONLY inside the 24-bit primary index of blocks whose rotations tie
+    (header layout: 48-bit magic, 32-bit CRC, 1 randomisation bit, 24-bit index; lbzip2's blocks start on
+    byte boundaries, src/encode.c:514-525).  Every other bit -- CRCs, trees, selectors, codes -- is the
+    reference's."""
+    if not orclib.have_ref():
+        pytest.skip("compiled reference not present")
+    checked = differ = 0
+    for name, lv in CASES:
+        exp = MAN[name]["levels"][str(lv)]
+        if not exp["periodic"]:
+            continue
+        raw = golden_util.load_input(name)
+        ours, infos = orclib.orc_stream(raw, lv)
+        ref = orclib.ref_cli(raw, lv)
+        assert hashlib.sha256(ref).hexdigest() == exp["ref_sha256"] and len(ours) == len(ref)
+        a, b = bytearray(ours), bytearray(ref)
+        start = 4
+        for i in infos:
+            if i.tie_count > 1:
+                for bit in range(81, 105):                       # the index field of this block
+                    byte, mask = start + (bit >> 3), 0x80 >> (bit & 7)
+                    a[byte] &= ~mask & 0xFF
+                    b[byte] &= ~mask & 0xFF
+            start += i.out_len
+        assert start + 10 == len(ours)
+        assert a == b, (name, lv)
+        differ += ours != ref                                    # (the reference's pick may happen to be the first index too)
+        checked += 1
+    assert checked >= 5 and differ >= 1
